@@ -1,0 +1,201 @@
+/* lhgt.h — C ABI of liblhgt.so: the B200-native k-mer screening stage of LocalHGT (`extract_ref`).
+ *
+ * The reference exposes this path only as a PROCESS boundary (scripts/pipeline.sh:35 execs
+ * `extract_ref` with 12 positional arguments, src/extract_ref_normal_peak.cpp:1352-1364).  The
+ * drop-in for that boundary is the `extract_ref` executable built from csrc/extract_ref_main.cpp,
+ * whose whole body is lhgt_main().  Everything else below is the thin layer underneath it that a
+ * ctypes / cgo / JNI binding can call stage by stage; each entry cites the reference
+ * code it replaces ("E:" = src/extract_ref_normal_peak.cpp).
+ *
+ * Conventions: plain pointers and sizes; caller owns every buffer it passes; no exceptions cross
+ * the boundary; return 0 (or a non-negative count) on success and a negative LHGT_E_* code on
+ * failure, with a message in lhgt_last_error() (thread-local).  A context is bound to one CUDA
+ * device and is not re-entrant.  Results follow the reference's `-t 1` semantics bit for bit
+ * (SURVEY.md Appendix A); there is no CPU fallback: without a CUDA device every GPU entry fails
+ * with LHGT_E_CUDA.
+ */
+#ifndef LHGT_H
+#define LHGT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LHGT_ABI_VERSION 1
+#define LHGT_CODER_SLOTS 300          /* short choose_coder[300], E:1186 */
+#define LHGT_MAX_E 10                 /* int base_kmer[10], E:99-100 */
+#define LHGT_MAX_READ_LEN 500         /* int reads_int[500], E:322-323, 1004-1005 */
+#define LHGT_RANDOM_ARRAY 50000000    /* MAX_RANDOM_NUM, E:40 */
+
+enum {
+    LHGT_OK = 0,
+    LHGT_E_ARG = -1,             /* bad argument (k, e, null pointer, ...) */
+    LHGT_E_IO = -2,              /* file cannot be opened / read / written */
+    LHGT_E_CUDA = -3,            /* CUDA runtime error or no device */
+    LHGT_E_FORMAT = -4,          /* malformed index image / FASTQ */
+    LHGT_E_TOO_MANY_PEAKS = -5,  /* E:272-274 prints and overruns; we stop (Q13) */
+    LHGT_E_READ_TOO_LONG = -6,   /* E:322-323 would overflow its stack arrays */
+    LHGT_E_UNPAIRED = -7,        /* first records of fq1/fq2 carry different read ids (E:368-399) */
+    LHGT_E_STATE = -8,           /* stage called before its inputs exist */
+    LHGT_E_NOMEM = -9
+};
+
+typedef struct lhgt_ctx lhgt_ctx;
+
+int         lhgt_abi_version(void);
+const char* lhgt_last_error(void);
+
+/* ------------------------------------------------------------------ host-only helpers (no GPU) */
+
+/* glibc srand(seed)/rand() stream (E:1386; consumed at E:1199 and E:1336): writes draws
+ * skip .. skip+n-1 to out. */
+int lhgt_rand_stream(unsigned seed, long skip, long n, int32_t* out);
+
+/* random_coder (E:1182-1222) after srand(seed): fills cc[300]; returns the number of rand() draws
+ * it consumed (k * (e/3 + 1)) so the caller can position the sampling stream (Q3). */
+int lhgt_random_coder(unsigned seed, int k, int e, int16_t* cc);
+
+/* The 300-word index header as the reference writes it (E:755-757, quirk Q1) and its inverse
+ * (saved_random_coder, E:1224-1242). */
+int lhgt_coder_to_header(const int16_t* cc, uint32_t* words300);
+int lhgt_header_to_coder(const uint32_t* words300, int16_t* cc);
+
+/* ------------------------------------------------------------------ context */
+
+/* Allocates the 2^k saturating count table (2 bits per k-mer) on `device`.  E:1375-1378. */
+int  lhgt_create(lhgt_ctx** out, int device, int k, int e);
+void lhgt_destroy(lhgt_ctx* c);
+int  lhgt_set_coder(lhgt_ctx* c, const int16_t* cc);
+int  lhgt_get_coder(const lhgt_ctx* c, int16_t* cc);
+/* Run every launch of this context on an existing CUDA stream (cudaStream_t as an integer);
+ * 0 restores the context's own stream. */
+int  lhgt_set_stream(lhgt_ctx* c, uintptr_t cuda_stream);
+int  lhgt_sync(lhgt_ctx* c);
+
+/* Test hook: canonical hashes of every k-mer of ascii[0..n), out[j*e+i], 0 for k-mers holding a
+ * non-ACGTacgt byte; valid[j] (nullable) tells those zeros from a true zero hash.  Runs the same
+ * device code as the index build (E:786-813). */
+int lhgt_hash_seq(lhgt_ctx* c, const uint8_t* ascii, size_t n, uint32_t* out, uint8_t* valid);
+
+/* ------------------------------------------------------------------ IB: index build (read_ref, E:727-886) */
+
+/* Builds the index image in HBM from FASTA text held in host memory.  The image is byte-identical
+ * to <ref>.k<k>.h<e>.index.dat.  genome.len.txt text is returned through lhgt_index_len_text(). */
+int      lhgt_index_build(lhgt_ctx* c, const uint8_t* fasta, size_t n);
+uint64_t lhgt_index_bytes(const lhgt_ctx* c);
+uint64_t lhgt_index_bases(const lhgt_ctx* c);            /* sum of indexed contig lengths */
+long     lhgt_index_contigs(const lhgt_ctx* c);
+int      lhgt_index_download(lhgt_ctx* c, uint8_t* dst, uint64_t cap);
+int      lhgt_index_len_text(const lhgt_ctx* c, char* dst, size_t cap, size_t* n);
+/* Makes an existing image HBM-resident (read_index's input, E:888-979) and adopts its coder
+ * (E:1417).  lhgt_index_attach_device uses an image that already lives on this device. */
+int      lhgt_index_upload(lhgt_ctx* c, const uint8_t* image, uint64_t n);
+/* File-level forms (what main() does at E:1401-1417). */
+int      lhgt_index_build_file(lhgt_ctx* c, const char* fasta_path, const char* index_path,
+                               const char* len_path);
+int      lhgt_index_load_file(lhgt_ctx* c, const char* index_path);
+
+/* ------------------------------------------------------------------ reads */
+
+/* Copies one FASTQ file image (mate 0 = fq1, 1 = fq2) from host memory to HBM and locates its
+ * records there (newline scan).  lhgt_reads_attach_device does the same for bytes that are already
+ * resident on this device (no copy; the caller keeps them alive). */
+int      lhgt_reads_upload(lhgt_ctx* c, int mate, const uint8_t* fq, uint64_t n);
+int      lhgt_reads_attach_device(lhgt_ctx* c, int mate, const void* dev_fq, uint64_t n);
+long     lhgt_reads_records(const lhgt_ctx* c, int mate);
+uint64_t lhgt_reads_seq_bases(const lhgt_ctx* c, int mate);   /* sum of sequence-line lengths */
+
+/* down_sam_ratio in percent (E:1392-1398, cal_sam_ratio E:1244-1270); needs fq1 uploaded when
+ * sample_arg > 1. */
+double lhgt_sample_ratio(lhgt_ctx* c, double sample_arg);
+/* Fixes the sampling rule `random_array[ordinal % 50M] < ratio` (E:1037-1044, 413-419) where
+ * random_array is drawn from srand(seed) after rand_skip earlier draws (get_random, E:1332-1340). */
+int    lhgt_set_sampling(lhgt_ctx* c, double ratio_percent, unsigned seed, long rand_skip);
+
+/* ------------------------------------------------------------------ stages */
+
+/* S1 (read_fastq, E:981-1107): saturating k-mer counts of the sampled reads of one file.  Records
+ * whose sequence line starts beyond byte_budget are ignored (quirk Q15: main() passes size(fq1)
+ * for both files, E:1419-1444).  Returns the number of sampled reads. */
+long lhgt_s1_count(lhgt_ctx* c, int mate, uint64_t byte_budget);
+/* S2 (read_index + slide_window + Peaks::add_peak, E:888-979, 550-725, 239-301).  Returns the
+ * number of peaks.  [tile_begin, tile_end) restricts the table gather to a slice of the reference
+ * (multi-GPU); pass 0, -1 for everything. */
+long lhgt_s2_peaks(lhgt_ctx* c, float hit_ratio, float match_ratio, long max_peak);
+/* S3 (Peaks::slide_reads + Split_reads, E:313-506, 91-202) over record pairs [first, first+count)
+ * (count < 0: all).  Returns the number of sampled pairs. */
+long lhgt_s3_pairs(lhgt_ctx* c, long first, long count);
+/* OUT (count_filtered_peak, E:515-548): the text of <interval_file>. */
+int  lhgt_intervals(lhgt_ctx* c, char* dst, size_t cap, size_t* n);
+/* Clears the count table and the peak tables so the context can screen another sample against the
+ * same index. */
+int  lhgt_reset(lhgt_ctx* c);
+
+/* ------------------------------------------------------------------ state (parity checks, multi-GPU) */
+
+int  lhgt_count_table_copy(lhgt_ctx* c, uint8_t* dst /* 2^k bytes, one counter per byte */);
+long lhgt_peaks_copy(lhgt_ctx* c, int32_t* loci /* 2 per peak */, uint8_t* filter /* 0/1 */, long cap);
+long lhgt_flagged_positions(const lhgt_ctx* c);          /* positions fed to add_peak */
+int  lhgt_peak_kmer_copy(lhgt_ctx* c, uint32_t* dst /* 2^k */);
+
+/* S2 split for multi-GPU: gather the table for tiles [tile_begin, tile_end) only, exchange the two
+ * bit arrays, then finish on every rank. */
+long     lhgt_s2_tiles(const lhgt_ctx* c);
+int      lhgt_s2_gather(lhgt_ctx* c, long tile_begin, long tile_end);
+int      lhgt_s2_finish(lhgt_ctx* c, float hit_ratio, float match_ratio, long max_peak, long* n_peaks);
+/* Raw device pointers for the exchange steps (NCCL / peer loads run by the caller). */
+void*    lhgt_dev_count_table(lhgt_ctx* c, uint64_t* bytes);      /* packed 2-bit counters */
+void*    lhgt_dev_hit_bits(lhgt_ctx* c, int which /*0 single, 1 trio*/, uint64_t* bytes);
+void*    lhgt_dev_peak_filter(lhgt_ctx* c, uint64_t* bytes);
+/* count := min(3, count + other) field-wise on packed tables (other: device pointer, same size). */
+int      lhgt_count_merge(lhgt_ctx* c, const void* dev_other, uint64_t bytes, uint64_t word_offset);
+
+/* Device time of the last call of each stage, measured with CUDA events on the context's stream:
+ * [0] reads index (newline scan)  [1] S1  [2] S2 gather  [3] S2 finish  [4] S3  [5] IB kernel. */
+int  lhgt_stage_ms(const lhgt_ctx* c, float* ms6);
+/* Kernels launched by this context since creation. */
+long lhgt_launch_count(const lhgt_ctx* c);
+
+/* ------------------------------------------------------------------ the whole program */
+
+typedef struct lhgt_args {
+    const char* fq1;            /* argv[1]  */
+    const char* fq2;            /* argv[2]  */
+    const char* fasta;          /* argv[3]  */
+    const char* interval;       /* argv[4]  */
+    double hit_ratio;           /* argv[5]  */
+    double match_ratio;         /* argv[6]  */
+    int    threads;             /* argv[7]: accepted; results are those of -t 1 */
+    int    k;                   /* argv[8]  */
+    long   max_peak;            /* argv[9]  */
+    int    e;                   /* argv[10] */
+    unsigned seed;              /* argv[11] */
+    double sample;              /* argv[12] */
+    int    device;              /* CUDA device ordinal */
+    int    quiet;               /* suppress the stdout log */
+} lhgt_args;
+
+typedef struct lhgt_stats {
+    long   reads_s1[2];         /* sampled reads per file in S1 */
+    long   flagged_positions;   /* positions fed to add_peak */
+    long   peaks;
+    long   pairs_s3;
+    long   kept_peaks;
+    int    index_built;         /* 1 when the index was created in this run */
+    double ratio_percent;
+    double seconds[8];          /* wall: total, io_in, index, s1, s2, s3, out, (spare) */
+} lhgt_stats;
+
+/* main() of the reference (E:1342-1519) at -t 1. */
+int lhgt_extract_ref(const lhgt_args* a, lhgt_stats* stats /* nullable */);
+/* The CLI body: same 12 positional arguments, every numeric parsed like stod (E:1359-1371).
+ * Returns the process exit status. */
+int lhgt_main(int argc, char** argv);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LHGT_H */

@@ -1,0 +1,1160 @@
+// Host side of liblhgt.so: context, FASTA/FASTQ plumbing, stage drivers and the C ABI (include/lhgt.h).
+// "E:" = reference src/extract_ref_normal_peak.cpp, cited for the behaviour each entry reproduces.
+#include "../../include/lhgt.h"
+#include "lhgt_kernels.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+using namespace lhgt;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess)                                                                      \
+            return fail(LHGT_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+static double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// ------------------------------------------------------------------------------------------------ glibc rand()
+// random_r TYPE_3 as published (additive feedback x^31 + x^3 + 1, 310 values discarded after seeding);
+// restated so the sampling stream does not depend on which libc the binary is linked against.
+struct GlibcRand {
+    int32_t ring[31];
+    int f, r;
+    explicit GlibcRand(unsigned seed) {
+        int32_t word = (int32_t)(seed ? seed : 1u);
+        ring[0] = word;
+        for (int i = 1; i < 31; ++i) {
+            long hi = word / 127773, lo = word % 127773;
+            long w = 16807 * lo - 2836 * hi;
+            if (w < 0) w += 2147483647;
+            word = (int32_t)w;
+            ring[i] = word;
+        }
+        f = 3; r = 0;
+        for (int i = 0; i < 310; ++i) next();
+    }
+    int next() {
+        uint32_t v = (uint32_t)ring[f] + (uint32_t)ring[r];
+        ring[f] = (int32_t)v;
+        if (++f == 31) f = 0;
+        if (++r == 31) r = 0;
+        return (int)(v >> 1);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ context
+struct Reads {
+    const uint8_t* d_fq = nullptr;
+    bool owned = false;
+    uint64_t n = 0, nrec = 0, seq_bases = 0;
+    uint64_t* d_start = nullptr;
+    uint64_t* d_end = nullptr;
+    uint64_t tail_start = 0, tail_len = 0;   // what std::getline leaves behind once the file is exhausted
+    bool ready = false;
+};
+
+struct TimedSpan { int stage; cudaEvent_t a, b; };
+
+struct lhgt_ctx {
+    int device = 0, k = 0, e = 0;
+    int16_t cc[LHGT_CODER_SLOTS];
+    HashP hp;
+    cudaStream_t own = nullptr, st = nullptr;
+
+    uint32_t* d_count = nullptr; uint64_t count_words = 0;
+    uint32_t* d_peak_kmer = nullptr;
+    uint32_t* d_prefilter = nullptr;
+
+    uint32_t* d_image = nullptr; uint64_t image_words = 0; bool image_owned = true;
+    std::vector<Contig> contigs; std::vector<Tile> tiles;
+    Contig* d_contigs = nullptr; Tile* d_tiles = nullptr;
+    uint64_t index_bases = 0;
+    std::string len_text;
+    bool index_ready = false;
+
+    uint32_t *d_single = nullptr, *d_trio = nullptr, *d_good = nullptr, *d_flagged = nullptr;
+    uint32_t *d_tile_new = nullptr, *d_tile_base = nullptr, *d_scan_tmp = nullptr;
+    bool gathered = false;
+
+    int32_t* d_loci = nullptr; uint8_t* d_filter = nullptr;
+    long n_peaks = -1, n_flagged = 0; long peaks_cap = 0;
+    bool peak_tables_dirty = false;
+
+    Reads reads[2];
+
+    uint32_t* d_sample_bits = nullptr; bool sampling_set = false; double ratio = 100.0;
+
+    uint32_t* d_cands = nullptr; int32_t* d_tally = nullptr; S3Scratch scratch{};
+
+    unsigned long long* d_counter = nullptr; int* d_err = nullptr;
+
+    std::vector<TimedSpan> spans;
+    long launches = 0;
+};
+
+static void make_hashp(lhgt_ctx* c) {
+    HashP& hp = c->hp;
+    memset(&hp, 0, sizeof hp);
+    hp.k = c->k; hp.e = c->e; hp.shr = 32 - c->k;
+    hp.kmask = c->k == 32 ? 0xffffffffu : ((1u << c->k) - 1u);
+    for (int i = 0; i < c->e; ++i)
+        for (int z = 0; z < c->k; ++z) {
+            int which = c->cc[z * c->e + i];
+            uint32_t bit = 1u << (c->k - 1 - z);
+            if (which == 0) hp.m0[i] |= bit;
+            else if (which == 1) hp.m1[i] |= bit;
+        }
+}
+
+static bool coder_ok(const int16_t* cc, int k, int e) {
+    for (int j = 0; j < k * e; ++j) if (cc[j] < 0 || cc[j] > 2) return false;
+    return true;
+}
+
+struct Span {
+    lhgt_ctx* c; int stage; cudaEvent_t a = nullptr, b = nullptr;
+    Span(lhgt_ctx* c_, int stage_) : c(c_), stage(stage_) {
+        if (cudaEventCreate(&a) == cudaSuccess && cudaEventCreate(&b) == cudaSuccess) cudaEventRecord(a, c->st);
+    }
+    ~Span() {
+        if (a && b) { cudaEventRecord(b, c->st); c->spans.push_back({stage, a, b}); }
+    }
+};
+
+static void free_spans(lhgt_ctx* c) {
+    for (auto& s : c->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    c->spans.clear();
+}
+
+template <class T>
+static int dev_alloc(T** p, size_t count) {
+    *p = nullptr;
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+    if (e != cudaSuccess) return fail(LHGT_E_NOMEM, "cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+    return 0;
+}
+template <class T>
+static void dev_free(T*& p) { if (p) cudaFree((void*)p); p = nullptr; }
+
+// ------------------------------------------------------------------------------------------------ small ABI
+extern "C" int lhgt_abi_version(void) { return LHGT_ABI_VERSION; }
+extern "C" const char* lhgt_last_error(void) { return g_err; }
+
+extern "C" int lhgt_rand_stream(unsigned seed, long skip, long n, int32_t* out) {
+    if (!out || skip < 0 || n < 0) return fail(LHGT_E_ARG, "lhgt_rand_stream: bad argument");
+    GlibcRand g(seed);
+    for (long i = 0; i < skip; ++i) g.next();
+    for (long i = 0; i < n; ++i) out[i] = g.next();
+    return 0;
+}
+
+static int random_coder_from(GlibcRand& g, int k, int e, int16_t* cc) {
+    // E:1182-1222: per k-mer position, e/3+1 draws pick permutations of (0,1,2); the first e entries are kept.
+    static const int16_t perms[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 2, 0}, {1, 0, 2}, {2, 0, 1}, {2, 1, 0}};
+    for (int i = 0; i < LHGT_CODER_SLOTS; ++i) cc[i] = 100;
+    int groups = e / 3 + 1, draws = 0;
+    for (int j = 0; j < k; ++j) {
+        int16_t row[3 * (LHGT_MAX_E / 3 + 1)];
+        for (int q = 0; q < groups; ++q) {
+            int r = g.next() % 6; ++draws;
+            for (int w = 0; w < 3; ++w) row[3 * q + w] = perms[r][w];
+        }
+        for (int i = 0; i < e; ++i) cc[j * e + i] = row[i];
+    }
+    return draws;
+}
+
+static bool ke_ok(int k, int e) { return k >= 2 && k <= 32 && e >= 1 && e <= LHGT_MAX_E && k * e <= LHGT_CODER_SLOTS; }
+
+extern "C" int lhgt_random_coder(unsigned seed, int k, int e, int16_t* cc) {
+    if (!cc || !ke_ok(k, e)) return fail(LHGT_E_ARG, "lhgt_random_coder: need 2<=k<=32, 1<=e<=10, k*e<=300");
+    GlibcRand g(seed);
+    return random_coder_from(g, k, e, cc);
+}
+
+extern "C" int lhgt_coder_to_header(const int16_t* cc, uint32_t* w) {
+    if (!cc || !w) return fail(LHGT_E_ARG, "null pointer");
+    // Q1 (E:755-757): 300 four-byte writes starting at &cc[j] -> word j = cc[j] | cc[j+1] << 16; last high half 0
+    for (int j = 0; j < LHGT_CODER_SLOTS; ++j) {
+        uint32_t lo = (uint16_t)cc[j], hi = j + 1 < LHGT_CODER_SLOTS ? (uint16_t)cc[j + 1] : 0u;
+        w[j] = lo | (hi << 16);
+    }
+    return 0;
+}
+
+extern "C" int lhgt_header_to_coder(const uint32_t* w, int16_t* cc) {
+    if (!cc || !w) return fail(LHGT_E_ARG, "null pointer");
+    for (int j = 0; j < LHGT_CODER_SLOTS; ++j) cc[j] = (int16_t)w[j];   // E:1233
+    return 0;
+}
+
+extern "C" int lhgt_create(lhgt_ctx** out, int device, int k, int e) {
+    if (!out) return fail(LHGT_E_ARG, "lhgt_create: null out");
+    *out = nullptr;
+    if (!ke_ok(k, e)) return fail(LHGT_E_ARG, "lhgt_create: need 2<=k<=32, 1<=e<=10, k*e<=300 (got k=%d e=%d)", k, e);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(LHGT_E_CUDA, "no CUDA device: liblhgt has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(LHGT_E_ARG, "device %d out of range (%d visible)", device, ndev);
+    CU(cudaSetDevice(device));
+    lhgt_ctx* c = new lhgt_ctx();
+    c->device = device; c->k = k; c->e = e;
+    for (int i = 0; i < LHGT_CODER_SLOTS; ++i) c->cc[i] = 100;
+    for (int j = 0; j < k * e; ++j) c->cc[j] = (int16_t)(j % 3);
+    make_hashp(c);
+    int rc = 0;
+    if (cudaStreamCreateWithFlags(&c->own, cudaStreamNonBlocking) != cudaSuccess) rc = fail(LHGT_E_CUDA, "stream create failed");
+    c->st = c->own;
+    uint64_t entries = 1ull << k;
+    c->count_words = std::max<uint64_t>(1, entries / 16);
+    if (!rc) rc = dev_alloc(&c->d_count, c->count_words);
+    if (!rc) rc = dev_alloc(&c->d_peak_kmer, entries);
+    if (!rc) rc = dev_alloc(&c->d_prefilter, (size_t)1 << (kFilterLog2 - 5));
+    if (!rc) rc = dev_alloc(&c->d_counter, 4);
+    if (!rc) rc = dev_alloc(&c->d_err, 4);
+    if (!rc) {
+        cudaMemsetAsync(c->d_count, 0, c->count_words * 4, c->st);
+        cudaMemsetAsync(c->d_peak_kmer, 0, entries * 4, c->st);
+        cudaMemsetAsync(c->d_prefilter, 0, (size_t)1 << (kFilterLog2 - 3), c->st);
+        cudaMemsetAsync(c->d_counter, 0, 4 * sizeof(unsigned long long), c->st);
+        cudaMemsetAsync(c->d_err, 0, 4 * sizeof(int), c->st);
+        if (cudaStreamSynchronize(c->st) != cudaSuccess) rc = fail(LHGT_E_CUDA, "table clear failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    if (rc) { lhgt_destroy(c); return rc; }
+    *out = c;
+    return 0;
+}
+
+static void drop_reads(Reads& r) {
+    if (r.owned) { uint8_t* p = const_cast<uint8_t*>(r.d_fq); dev_free(p); }
+    dev_free(r.d_start); dev_free(r.d_end);
+    r = Reads();
+}
+
+static void drop_index(lhgt_ctx* c) {
+    if (c->image_owned) dev_free(c->d_image);
+    c->d_image = nullptr; c->image_owned = true; c->image_words = 0;
+    dev_free(c->d_contigs); dev_free(c->d_tiles);
+    dev_free(c->d_single); dev_free(c->d_trio); dev_free(c->d_good); dev_free(c->d_flagged);
+    dev_free(c->d_tile_new); dev_free(c->d_tile_base); dev_free(c->d_scan_tmp);
+    c->contigs.clear(); c->tiles.clear(); c->len_text.clear();
+    c->index_ready = false; c->gathered = false; c->index_bases = 0;
+}
+
+extern "C" void lhgt_destroy(lhgt_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->st) cudaStreamSynchronize(c->st);
+    free_spans(c);
+    drop_reads(c->reads[0]); drop_reads(c->reads[1]);
+    drop_index(c);
+    dev_free(c->d_count); dev_free(c->d_peak_kmer); dev_free(c->d_prefilter);
+    dev_free(c->d_loci); dev_free(c->d_filter); dev_free(c->d_sample_bits);
+    dev_free(c->d_cands); dev_free(c->d_tally); dev_free(c->d_counter); dev_free(c->d_err);
+    if (c->own) cudaStreamDestroy(c->own);
+    delete c;
+}
+
+extern "C" int lhgt_set_coder(lhgt_ctx* c, const int16_t* cc) {
+    if (!c || !cc) return fail(LHGT_E_ARG, "null pointer");
+    if (!coder_ok(cc, c->k, c->e)) return fail(LHGT_E_FORMAT, "coder table holds values outside 0..2 in its first k*e slots");
+    memcpy(c->cc, cc, sizeof c->cc);
+    make_hashp(c);
+    return 0;
+}
+
+extern "C" int lhgt_get_coder(const lhgt_ctx* c, int16_t* cc) {
+    if (!c || !cc) return fail(LHGT_E_ARG, "null pointer");
+    memcpy(cc, c->cc, sizeof c->cc);
+    return 0;
+}
+
+extern "C" int lhgt_set_stream(lhgt_ctx* c, uintptr_t s) {
+    if (!c) return fail(LHGT_E_ARG, "null ctx");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->st));
+    c->st = s ? (cudaStream_t)s : c->own;
+    return 0;
+}
+
+extern "C" int lhgt_sync(lhgt_ctx* c) {
+    if (!c) return fail(LHGT_E_ARG, "null ctx");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ index tables
+static int finish_index_tables(lhgt_ctx* c) {
+    // tiles cover every position 0..len-1 of every indexed contig, contig by contig
+    c->tiles.clear();
+    c->index_bases = 0;
+    for (size_t ci = 0; ci < c->contigs.size(); ++ci) {
+        Contig& g = c->contigs[ci];
+        g.tile0 = (uint32_t)c->tiles.size();
+        for (uint32_t j0 = 0; j0 < g.len; j0 += kTile) c->tiles.push_back({(uint32_t)ci, j0});
+        c->index_bases += g.len;
+    }
+    size_t nt = c->tiles.size();
+    int rc = 0;
+    if ((rc = dev_alloc(&c->d_contigs, c->contigs.size()))) return rc;
+    if ((rc = dev_alloc(&c->d_tiles, nt))) return rc;
+    size_t bw = nt * kTileWords;
+    if ((rc = dev_alloc(&c->d_single, bw)) || (rc = dev_alloc(&c->d_trio, bw)) || (rc = dev_alloc(&c->d_good, bw)) ||
+        (rc = dev_alloc(&c->d_flagged, bw)) || (rc = dev_alloc(&c->d_tile_new, nt)) || (rc = dev_alloc(&c->d_tile_base, nt)) ||
+        (rc = dev_alloc(&c->d_scan_tmp, scan_tmp_words(nt))))
+        return rc;
+    CU(cudaMemcpyAsync(c->d_contigs, c->contigs.data(), c->contigs.size() * sizeof(Contig), cudaMemcpyHostToDevice, c->st));
+    CU(cudaMemcpyAsync(c->d_tiles, c->tiles.data(), nt * sizeof(Tile), cudaMemcpyHostToDevice, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    c->index_ready = true;
+    c->gathered = false;
+    return 0;
+}
+
+// get_read_ID (E:303-311): cut at the first '/', then ' ', then '\t'
+static size_t read_id_len(const uint8_t* s, size_t n) {
+    size_t m = n;
+    for (size_t i = 0; i < m; ++i) if (s[i] == '/') { m = i; break; }
+    for (size_t i = 0; i < m; ++i) if (s[i] == ' ') { m = i; break; }
+    for (size_t i = 0; i < m; ++i) if (s[i] == '\t') { m = i; break; }
+    return m;
+}
+
+struct ParsedFasta {
+    std::vector<uint8_t> seq;          // indexed contigs only, back to back
+    std::vector<Contig> contigs;
+    std::string len_text;
+};
+
+// The getline loop of read_ref (E:761-831 + the tail E:833-880) without the hashing.
+static void parse_fasta(const uint8_t* fa, size_t n, int k, int e, ParsedFasta& out) {
+    out.seq.reserve(n);
+    std::string name = "start";                               // E:747
+    long ordinal = 0, cumulative = 0;
+    size_t cur_begin = 0;                                     // start of the current contig inside out.seq
+    uint64_t word = LHGT_CODER_SLOTS;
+    auto close_contig = [&]() {
+        size_t len = out.seq.size() - cur_begin;
+        cumulative += (long)len;
+        if (len > (size_t)k) {                                // E:772, 836
+            char buf[96];
+            snprintf(buf, sizeof buf, "\t%ld\t%zu\t%ld\n", ordinal, len, cumulative);
+            out.len_text += name; out.len_text += buf;
+            Contig c{};
+            c.hash_word = word + 1; c.seq_off = cur_begin; c.len = (uint32_t)len; c.tile0 = 0;
+            out.contigs.push_back(c);
+            word += 1 + (uint64_t)(len - k + 1) * e;
+            cur_begin = out.seq.size();
+        } else {
+            out.seq.resize(cur_begin);                        // skipped contig leaves no bytes behind
+        }
+    };
+    size_t pos = 0;
+    while (pos < n) {
+        const uint8_t* nl = (const uint8_t*)memchr(fa + pos, '\n', n - pos);
+        size_t end = nl ? (size_t)(nl - fa) : n;
+        size_t len = end - pos;
+        if (len > 0 && fa[pos] == '>') {
+            close_contig();
+            ++ordinal;                                        // E:825: every header counts (Q2)
+            size_t idl = read_id_len(fa + pos, len);
+            name.assign((const char*)fa + pos + 1, idl > 0 ? idl - 1 : 0);   // E:764
+        } else if (len) {
+            out.seq.insert(out.seq.end(), fa + pos, fa + end);
+        }
+        pos = nl ? end + 1 : n;
+    }
+    close_contig();
+}
+
+static int alloc_image(lhgt_ctx* c, uint64_t words) {
+    int rc = dev_alloc(&c->d_image, words);
+    if (rc) return rc;
+    c->image_words = words; c->image_owned = true;
+    return 0;
+}
+
+extern "C" int lhgt_index_build(lhgt_ctx* c, const uint8_t* fasta, size_t n) {
+    if (!c || (!fasta && n)) return fail(LHGT_E_ARG, "lhgt_index_build: null pointer");
+    CU(cudaSetDevice(c->device));
+    if (!coder_ok(c->cc, c->k, c->e)) return fail(LHGT_E_STATE, "set the coder before building an index");
+    drop_index(c);
+    ParsedFasta pf;
+    parse_fasta(fasta, n, c->k, c->e, pf);
+    for (auto& g : pf.contigs)
+        if (g.len > 178000000u) return fail(LHGT_E_FORMAT, "contig longer than the reference's int buffers allow (E:925)");
+    c->contigs = pf.contigs;
+    c->len_text = pf.len_text;
+    uint64_t words = LHGT_CODER_SLOTS;
+    for (auto& g : c->contigs) words += 1 + (uint64_t)(g.len - c->k + 1) * c->e;
+    int rc = alloc_image(c, words);
+    if (rc) return rc;
+    if ((rc = finish_index_tables(c))) return rc;
+    uint32_t header[LHGT_CODER_SLOTS];
+    lhgt_coder_to_header(c->cc, header);
+    CU(cudaMemcpyAsync(c->d_image, header, sizeof header, cudaMemcpyHostToDevice, c->st));
+    uint8_t* d_seq = nullptr;
+    if ((rc = dev_alloc(&d_seq, pf.seq.size() + 64))) return rc;
+    CU(cudaMemcpyAsync(d_seq, pf.seq.data(), pf.seq.size(), cudaMemcpyHostToDevice, c->st));
+    {
+        Span sp(c, 5);
+        c->launches += launch_index_build(d_seq, c->d_contigs, c->d_tiles, c->tiles.size(), c->hp, c->d_image, nullptr, c->st);
+    }
+    cudaError_t e1 = cudaStreamSynchronize(c->st);
+    cudaFree(d_seq);
+    if (e1 != cudaSuccess) return fail(LHGT_E_CUDA, "index build kernel failed: %s", cudaGetErrorString(e1));
+    return 0;
+}
+
+// Test hook: the index-build kernel over one anonymous contig.
+extern "C" int lhgt_hash_seq(lhgt_ctx* c, const uint8_t* ascii, size_t n, uint32_t* out, uint8_t* valid) {
+    if (!c || (!ascii && n) || !out) return fail(LHGT_E_ARG, "lhgt_hash_seq: null pointer");
+    if (n > 178000000u) return fail(LHGT_E_ARG, "sequence too long");
+    long np = (long)n - c->k + 1;
+    if (np <= 0) return 0;
+    CU(cudaSetDevice(c->device));
+    Contig g{};
+    g.hash_word = 1; g.seq_off = 0; g.len = (uint32_t)n; g.tile0 = 0;
+    std::vector<Tile> tiles;
+    for (uint32_t j0 = 0; j0 < g.len; j0 += kTile) tiles.push_back({0u, j0});
+    uint8_t *d_seq = nullptr, *d_valid = nullptr; Contig* d_c = nullptr; Tile* d_t = nullptr; uint32_t* d_img = nullptr;
+    size_t words = 1 + (size_t)np * c->e;
+    int rc = 0;
+    if ((rc = dev_alloc(&d_seq, n + 64)) || (rc = dev_alloc(&d_valid, (size_t)np)) || (rc = dev_alloc(&d_c, 1)) ||
+        (rc = dev_alloc(&d_t, tiles.size())) || (rc = dev_alloc(&d_img, words))) {
+        dev_free(d_seq); dev_free(d_valid); dev_free(d_c); dev_free(d_t); dev_free(d_img);
+        return rc;
+    }
+    cudaMemcpyAsync(d_seq, ascii, n, cudaMemcpyHostToDevice, c->st);
+    cudaMemcpyAsync(d_c, &g, sizeof g, cudaMemcpyHostToDevice, c->st);
+    cudaMemcpyAsync(d_t, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice, c->st);
+    c->launches += launch_index_build(d_seq, d_c, d_t, tiles.size(), c->hp, d_img, d_valid, c->st);
+    cudaMemcpyAsync(out, d_img + 1, (size_t)np * c->e * 4, cudaMemcpyDeviceToHost, c->st);
+    if (valid) cudaMemcpyAsync(valid, d_valid, (size_t)np, cudaMemcpyDeviceToHost, c->st);
+    cudaError_t e1 = cudaStreamSynchronize(c->st);
+    dev_free(d_seq); dev_free(d_valid); dev_free(d_c); dev_free(d_t); dev_free(d_img);
+    if (e1 != cudaSuccess) return fail(LHGT_E_CUDA, "hash kernel failed: %s", cudaGetErrorString(e1));
+    return 0;
+}
+
+extern "C" uint64_t lhgt_index_bytes(const lhgt_ctx* c) { return c && c->index_ready ? c->image_words * 4 : 0; }
+extern "C" uint64_t lhgt_index_bases(const lhgt_ctx* c) { return c ? c->index_bases : 0; }
+extern "C" long lhgt_index_contigs(const lhgt_ctx* c) { return c ? (long)c->contigs.size() : 0; }
+
+extern "C" int lhgt_index_download(lhgt_ctx* c, uint8_t* dst, uint64_t cap) {
+    if (!c || !dst) return fail(LHGT_E_ARG, "null pointer");
+    if (!c->index_ready) return fail(LHGT_E_STATE, "no index resident");
+    if (cap < c->image_words * 4) return fail(LHGT_E_ARG, "buffer too small for the index image");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(dst, c->d_image, c->image_words * 4, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+extern "C" int lhgt_index_len_text(const lhgt_ctx* c, char* dst, size_t cap, size_t* n) {
+    if (!c || !n) return fail(LHGT_E_ARG, "null pointer");
+    *n = c->len_text.size();
+    if (dst) {
+        if (cap < c->len_text.size()) return fail(LHGT_E_ARG, "buffer too small");
+        memcpy(dst, c->len_text.data(), c->len_text.size());
+    }
+    return 0;
+}
+
+// Walks an index image held in host memory (E:921-972's record structure) and adopts its header.
+static int adopt_image_layout(lhgt_ctx* c, const uint32_t* words, uint64_t nwords) {
+    if (nwords < LHGT_CODER_SLOTS) return fail(LHGT_E_FORMAT, "index image shorter than its 1200-byte header");
+    int16_t cc[LHGT_CODER_SLOTS];
+    lhgt_header_to_coder(words, cc);
+    if (!coder_ok(cc, c->k, c->e)) return fail(LHGT_E_FORMAT, "index header does not describe k=%d e=%d", c->k, c->e);
+    memcpy(c->cc, cc, sizeof cc);
+    make_hashp(c);
+    c->contigs.clear();
+    uint64_t at = LHGT_CODER_SLOTS;
+    while (at < nwords) {
+        uint32_t len = words[at];
+        if (len <= (uint32_t)c->k || len > 178000000u) return fail(LHGT_E_FORMAT, "bad contig length %u at word %llu", len, (unsigned long long)at);
+        uint64_t span = (uint64_t)(len - c->k + 1) * c->e;
+        if (at + 1 + span > nwords) return fail(LHGT_E_FORMAT, "index image truncated inside a contig record");
+        Contig g{};
+        g.hash_word = at + 1; g.seq_off = 0; g.len = len;
+        c->contigs.push_back(g);
+        at += 1 + span;
+    }
+    return 0;
+}
+
+extern "C" int lhgt_index_upload(lhgt_ctx* c, const uint8_t* image, uint64_t n) {
+    if (!c || !image) return fail(LHGT_E_ARG, "null pointer");
+    if (n % 4) return fail(LHGT_E_FORMAT, "index image size is not a multiple of 4");
+    CU(cudaSetDevice(c->device));
+    drop_index(c);
+    int rc = adopt_image_layout(c, (const uint32_t*)image, n / 4);
+    if (rc) return rc;
+    if ((rc = alloc_image(c, n / 4))) return rc;
+    CU(cudaMemcpyAsync(c->d_image, image, n, cudaMemcpyHostToDevice, c->st));
+    return finish_index_tables(c);
+}
+
+// ------------------------------------------------------------------------------------------------ files
+struct HostFile {
+    uint8_t* p = nullptr; size_t n = 0; bool pinned = false;
+    ~HostFile() { release(); }
+    void release() {
+        if (p) { if (pinned) cudaFreeHost(p); else free(p); }
+        p = nullptr; n = 0;
+    }
+};
+
+static int slurp(const char* path, HostFile& f, bool pin) {
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return fail(LHGT_E_IO, "cannot open %s", path);
+    struct stat st;
+    if (fstat(fd, &st) != 0) { close(fd); return fail(LHGT_E_IO, "cannot stat %s", path); }
+    f.n = (size_t)st.st_size;
+    f.pinned = pin && cudaHostAlloc((void**)&f.p, f.n + 64, cudaHostAllocDefault) == cudaSuccess;
+    if (!f.pinned) { cudaGetLastError(); f.p = (uint8_t*)malloc(f.n + 64); }
+    if (!f.p) { close(fd); return fail(LHGT_E_NOMEM, "cannot allocate %zu bytes for %s", f.n, path); }
+    size_t got = 0;
+    while (got < f.n) {
+        ssize_t r = pread(fd, f.p + got, std::min<size_t>(f.n - got, (size_t)1 << 30), (off_t)got);
+        if (r <= 0) { close(fd); return fail(LHGT_E_IO, "short read on %s", path); }
+        got += (size_t)r;
+    }
+    close(fd);
+    return 0;
+}
+
+static int spill(const char* path, const void* p, size_t n) {
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(LHGT_E_IO, "cannot create %s", path);
+    size_t w = n ? fwrite(p, 1, n, f) : 0;
+    if (fclose(f) != 0 || w != n) return fail(LHGT_E_IO, "short write on %s", path);
+    return 0;
+}
+
+extern "C" int lhgt_index_build_file(lhgt_ctx* c, const char* fasta_path, const char* index_path, const char* len_path) {
+    if (!c || !fasta_path || !index_path || !len_path) return fail(LHGT_E_ARG, "null pointer");
+    HostFile fa;
+    int rc = slurp(fasta_path, fa, false);
+    if (rc) return rc;
+    if ((rc = lhgt_index_build(c, fa.p, fa.n))) return rc;
+    fa.release();
+    // stream the image out through two pinned staging buffers
+    FILE* f = fopen(index_path, "wb");
+    if (!f) return fail(LHGT_E_IO, "cannot create %s", index_path);
+    const size_t chunk = (size_t)64 << 20;
+    uint8_t* stage[2] = {nullptr, nullptr};
+    cudaEvent_t done[2];
+    for (int i = 0; i < 2; ++i) {
+        if (cudaHostAlloc((void**)&stage[i], chunk, cudaHostAllocDefault) != cudaSuccess || cudaEventCreate(&done[i]) != cudaSuccess) {
+            fclose(f);
+            return fail(LHGT_E_NOMEM, "cannot allocate pinned staging buffers");
+        }
+    }
+    size_t total = c->image_words * 4, issued = 0, written = 0;
+    size_t len_of[2] = {0, 0};
+    auto issue = [&](int s) {
+        size_t m = std::min(chunk, total - issued);
+        cudaMemcpyAsync(stage[s], (const uint8_t*)c->d_image + issued, m, cudaMemcpyDeviceToHost, c->st);
+        cudaEventRecord(done[s], c->st);
+        len_of[s] = m; issued += m;
+    };
+    int slot = 0;
+    rc = 0;
+    if (total) issue(0);
+    while (written < total && !rc) {
+        if (issued < total) issue(slot ^ 1);                       // next chunk copies while this one is written
+        if (cudaEventSynchronize(done[slot]) != cudaSuccess) { rc = fail(LHGT_E_CUDA, "index download failed"); break; }
+        if (fwrite(stage[slot], 1, len_of[slot], f) != len_of[slot]) { rc = fail(LHGT_E_IO, "short write on %s", index_path); break; }
+        written += len_of[slot];
+        slot ^= 1;
+    }
+    for (int i = 0; i < 2; ++i) { cudaFreeHost(stage[i]); cudaEventDestroy(done[i]); }
+    if (fclose(f) != 0 && !rc) rc = fail(LHGT_E_IO, "close failed on %s", index_path);
+    if (rc) return rc;
+    return spill(len_path, c->len_text.data(), c->len_text.size());
+}
+
+extern "C" int lhgt_index_load_file(lhgt_ctx* c, const char* index_path) {
+    if (!c || !index_path) return fail(LHGT_E_ARG, "null pointer");
+    HostFile f;
+    int rc = slurp(index_path, f, true);
+    if (rc) return rc;
+    return lhgt_index_upload(c, f.p, f.n);
+}
+
+// ------------------------------------------------------------------------------------------------ reads
+static int index_reads(lhgt_ctx* c, Reads& r, int last_byte, uint64_t tail_start) {
+    uint64_t tiles = fastq_index_tiles(r.n);
+    r.nrec = 0; r.seq_bases = 0;
+    if (r.n == 0) { r.ready = true; return 0; }
+    uint32_t *d_cnt = nullptr, *d_base = nullptr, *d_tmp = nullptr;
+    int rc = 0;
+    if ((rc = dev_alloc(&d_cnt, tiles)) || (rc = dev_alloc(&d_base, tiles)) || (rc = dev_alloc(&d_tmp, scan_tmp_words(tiles)))) {
+        dev_free(d_cnt); dev_free(d_base); dev_free(d_tmp);
+        return rc;
+    }
+    auto cleanup = [&]() { dev_free(d_cnt); dev_free(d_base); dev_free(d_tmp); };
+    {
+        Span sp(c, 0);
+        c->launches += launch_fastq_index(r.d_fq, r.n, d_cnt, d_base, d_tmp, nullptr, nullptr, 0, 0, c->st);
+    }
+    uint32_t last_cnt = 0, last_base = 0;
+    cudaMemcpyAsync(&last_cnt, d_cnt + tiles - 1, 4, cudaMemcpyDeviceToHost, c->st);
+    cudaMemcpyAsync(&last_base, d_base + tiles - 1, 4, cudaMemcpyDeviceToHost, c->st);
+    cudaError_t e1 = cudaStreamSynchronize(c->st);
+    if (e1 != cudaSuccess) { cleanup(); return fail(LHGT_E_CUDA, "newline scan failed: %s", cudaGetErrorString(e1)); }
+    uint64_t newlines = (uint64_t)last_cnt + last_base;
+    bool open_tail = last_byte != '\n';
+    uint64_t lines = newlines + (open_tail ? 1 : 0);
+    r.nrec = (lines + 2) / 4;                                      // lines 1, 5, 9, ... are sequences
+    if ((rc = dev_alloc(&r.d_start, r.nrec)) || (rc = dev_alloc(&r.d_end, r.nrec))) { cleanup(); return rc; }
+    cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), c->st);
+    {
+        Span sp(c, 0);
+        c->launches += launch_fastq_index(r.d_fq, r.n, d_cnt, d_base, d_tmp, r.d_start, r.d_end, r.nrec, 1, c->st);
+        if (r.nrec && open_tail && lines % 4 == 2)                 // last sequence line has no newline
+            cudaMemcpyAsync(r.d_end + (r.nrec - 1), &r.n, 8, cudaMemcpyHostToDevice, c->st);
+        c->launches += launch_sum_lengths(r.d_start, r.d_end, r.nrec, c->d_counter, c->st);
+    }
+    unsigned long long total = 0;
+    cudaMemcpyAsync(&total, c->d_counter, sizeof total, cudaMemcpyDeviceToHost, c->st);
+    e1 = cudaStreamSynchronize(c->st);
+    cleanup();
+    if (e1 != cudaSuccess) return fail(LHGT_E_CUDA, "record location failed: %s", cudaGetErrorString(e1));
+    r.seq_bases = total;
+    // std::getline past the end: with a trailing newline the string is emptied, without one it keeps the last line
+    if (open_tail) { r.tail_start = tail_start; r.tail_len = r.n - tail_start; }
+    else { r.tail_start = 0; r.tail_len = 0; }
+    r.ready = true;
+    return 0;
+}
+
+static uint64_t last_line_start(const uint8_t* p, uint64_t n) {
+    for (uint64_t i = n; i > 0; --i) if (p[i - 1] == '\n') return i;
+    return 0;
+}
+
+extern "C" int lhgt_reads_upload(lhgt_ctx* c, int mate, const uint8_t* fq, uint64_t n) {
+    if (!c || mate < 0 || mate > 1 || (!fq && n)) return fail(LHGT_E_ARG, "lhgt_reads_upload: bad argument");
+    CU(cudaSetDevice(c->device));
+    Reads& r = c->reads[mate];
+    drop_reads(r);
+    uint8_t* d = nullptr;
+    int rc = dev_alloc(&d, n + 64);
+    if (rc) return rc;
+    r.d_fq = d; r.owned = true; r.n = n;
+    if (n) CU(cudaMemcpyAsync(d, fq, n, cudaMemcpyHostToDevice, c->st));
+    uint64_t tail = 0;
+    int last = '\n';
+    if (n) {
+        last = fq[n - 1];
+        if (last != '\n') {
+            uint64_t lo = n > 65536 ? n - 65536 : 0;
+            tail = lo + last_line_start(fq + lo, n - lo);
+        }
+    }
+    return index_reads(c, r, last, tail);
+}
+
+extern "C" int lhgt_reads_attach_device(lhgt_ctx* c, int mate, const void* dev_fq, uint64_t n) {
+    if (!c || mate < 0 || mate > 1 || (!dev_fq && n)) return fail(LHGT_E_ARG, "lhgt_reads_attach_device: bad argument");
+    if ((uintptr_t)dev_fq % 16) return fail(LHGT_E_ARG, "device FASTQ buffer must be 16-byte aligned");
+    CU(cudaSetDevice(c->device));
+    Reads& r = c->reads[mate];
+    drop_reads(r);
+    r.d_fq = (const uint8_t*)dev_fq; r.owned = false; r.n = n;
+    uint64_t tail = 0;
+    int last = '\n';
+    if (n) {
+        std::vector<uint8_t> end(std::min<uint64_t>(n, 65536));
+        CU(cudaMemcpyAsync(end.data(), (const uint8_t*)dev_fq + (n - end.size()), end.size(), cudaMemcpyDeviceToHost, c->st));
+        CU(cudaStreamSynchronize(c->st));
+        last = end.back();
+        if (last != '\n') tail = (n - end.size()) + last_line_start(end.data(), end.size());
+    }
+    return index_reads(c, r, last, tail);
+}
+
+extern "C" long lhgt_reads_records(const lhgt_ctx* c, int mate) { return c && mate >= 0 && mate <= 1 ? (long)c->reads[mate].nrec : 0; }
+extern "C" uint64_t lhgt_reads_seq_bases(const lhgt_ctx* c, int mate) { return c && mate >= 0 && mate <= 1 ? c->reads[mate].seq_bases : 0; }
+
+extern "C" double lhgt_sample_ratio(lhgt_ctx* c, double sample_arg) {
+    if (sample_arg <= 1) return 100 * sample_arg;                  // E:1392-1394
+    if (!c || !c->reads[0].ready) { fail(LHGT_E_STATE, "upload fq1 before asking for the sampling ratio"); return -1; }
+    long sample_size = (long)c->reads[0].seq_bases * 2;            // E:1258-1264
+    return 100 * sample_arg / (double)sample_size;                 // E:1265
+}
+
+extern "C" int lhgt_set_sampling(lhgt_ctx* c, double ratio, unsigned seed, long rand_skip) {
+    if (!c || rand_skip < 0) return fail(LHGT_E_ARG, "bad argument");
+    CU(cudaSetDevice(c->device));
+    c->ratio = ratio;
+    c->sampling_set = true;
+    dev_free(c->d_sample_bits);
+    if (ratio >= 100) return 0;                                    // every drawn value is <= 99.999 (E:1336)
+    uint64_t need = std::max(c->reads[0].nrec, c->reads[1].nrec);
+    need = std::min<uint64_t>(need, kRandomArray);
+    size_t words = (size_t)(kRandomArray + 31) / 32;
+    std::vector<uint32_t> bits(words, 0u);
+    GlibcRand g(seed);
+    for (long i = 0; i < rand_skip; ++i) g.next();
+    for (uint64_t i = 0; i < need; ++i) {
+        float r = (float)((g.next() % 100000) / 1000.0);           // E:1336-1337
+        if ((double)r < ratio) bits[i >> 5] |= 1u << (i & 31);     // E:1044, 419
+    }
+    int rc = dev_alloc(&c->d_sample_bits, words);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(c->d_sample_bits, bits.data(), words * 4, cudaMemcpyHostToDevice, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ stages
+static int check_err_flag(lhgt_ctx* c, int* flag) {
+    CU(cudaMemcpyAsync(flag, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    return 0;
+}
+
+extern "C" long lhgt_s1_count(lhgt_ctx* c, int mate, uint64_t byte_budget) {
+    if (!c || mate < 0 || mate > 1) return fail(LHGT_E_ARG, "bad argument");
+    Reads& r = c->reads[mate];
+    if (!r.ready) return fail(LHGT_E_STATE, "reads of mate %d not uploaded", mate);
+    if (!c->sampling_set) return fail(LHGT_E_STATE, "call lhgt_set_sampling first");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), c->st));
+    CU(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->st));
+    {
+        Span sp(c, 1);
+        c->launches += launch_s1(r.d_fq, r.d_start, r.d_end, r.nrec, byte_budget, c->d_sample_bits, c->hp, c->d_count,
+                                 c->d_counter, c->d_err, c->st);
+    }
+    unsigned long long sampled = 0; int flag = 0;
+    CU(cudaMemcpyAsync(&sampled, c->d_counter, sizeof sampled, cudaMemcpyDeviceToHost, c->st));
+    int rc = check_err_flag(c, &flag);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->st));
+    if (flag) return fail(LHGT_E_READ_TOO_LONG, "a read is longer than %d bases", LHGT_MAX_READ_LEN);
+    return (long)sampled;
+}
+
+extern "C" long lhgt_s2_tiles(const lhgt_ctx* c) { return c ? (long)c->tiles.size() : 0; }
+
+extern "C" int lhgt_s2_gather(lhgt_ctx* c, long tile_begin, long tile_end) {
+    if (!c) return fail(LHGT_E_ARG, "null ctx");
+    if (!c->index_ready) return fail(LHGT_E_STATE, "no index resident");
+    long nt = (long)c->tiles.size();
+    if (tile_end < 0 || tile_end > nt) tile_end = nt;
+    if (tile_begin < 0 || tile_begin > tile_end) return fail(LHGT_E_ARG, "bad tile range");
+    CU(cudaSetDevice(c->device));
+    Span sp(c, 2);
+    c->launches += launch_s2_gather(c->d_image, c->d_contigs, c->d_tiles, (uint64_t)tile_begin, (uint64_t)tile_end, c->hp,
+                                    c->d_count, c->d_single, c->d_trio, c->st);
+    c->gathered = true;
+    return 0;
+}
+
+static int clear_peak_tables(lhgt_ctx* c) {
+    if (c->peak_tables_dirty && c->n_peaks > 0 && c->index_ready) {
+        c->launches += launch_s2_register(c->d_image, c->d_contigs, c->d_tiles, c->tiles.size(), c->hp, c->d_count, c->d_flagged,
+                                          c->d_tile_base, c->d_loci, c->d_peak_kmer, c->d_prefilter, 1, c->st);
+    }
+    c->peak_tables_dirty = false;
+    return 0;
+}
+
+extern "C" int lhgt_s2_finish(lhgt_ctx* c, float hit_ratio, float match_ratio, long max_peak, long* n_peaks) {
+    if (!c) return fail(LHGT_E_ARG, "null ctx");
+    if (!c->index_ready || !c->gathered) return fail(LHGT_E_STATE, "gather the table first");
+    CU(cudaSetDevice(c->device));
+    clear_peak_tables(c);
+    int one_min = (int)(500 * hit_ratio), three_min = (int)(500 * match_ratio);    // E:559-560 (int * float, fp32)
+    uint64_t nt = c->tiles.size();
+    c->n_peaks = 0; c->n_flagged = 0;
+    if (nt == 0) { if (n_peaks) *n_peaks = 0; return 0; }
+    unsigned long long flagged_total = 0; uint32_t last_new = 0, last_base = 0;
+    {
+        Span sp(c, 3);
+        c->launches += launch_s2_good(c->d_contigs, c->d_tiles, nt, c->d_single, c->d_trio, one_min, three_min, c->d_good, c->st);
+        c->launches += launch_s2_flag(c->d_contigs, c->d_tiles, nt, c->k, c->d_single, c->d_good, c->d_flagged, c->st);
+        CU(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), c->st));
+        c->launches += launch_s2_count_new(c->d_contigs, c->d_tiles, nt, c->d_flagged, c->d_tile_new, c->d_counter, c->st);
+        c->launches += launch_scan_exclusive(c->d_tile_new, c->d_tile_base, nt, c->d_scan_tmp, c->st);
+    }
+    CU(cudaMemcpyAsync(&flagged_total, c->d_counter, sizeof flagged_total, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(&last_new, c->d_tile_new + nt - 1, 4, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(&last_base, c->d_tile_base + nt - 1, 4, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    long total = (long)last_new + (long)last_base;
+    c->n_flagged = (long)flagged_total;
+    if (total > max_peak) return fail(LHGT_E_TOO_MANY_PEAKS, "%ld peaks exceed max_peak=%ld (E:272-274)", total, max_peak);
+    if (total > c->peaks_cap) {
+        dev_free(c->d_loci); dev_free(c->d_filter);
+        int rc = dev_alloc(&c->d_loci, (size_t)total * 2);
+        if (!rc) rc = dev_alloc(&c->d_filter, (size_t)total);
+        if (rc) return rc;
+        c->peaks_cap = total;
+    }
+    if (total > 0) {
+        CU(cudaMemsetAsync(c->d_filter, 0, (size_t)total, c->st));
+        Span sp(c, 3);
+        c->launches += launch_s2_register(c->d_image, c->d_contigs, c->d_tiles, nt, c->hp, c->d_count, c->d_flagged, c->d_tile_base,
+                                          c->d_loci, c->d_peak_kmer, c->d_prefilter, 0, c->st);
+        c->peak_tables_dirty = true;
+    }
+    c->n_peaks = total;
+    if (n_peaks) *n_peaks = total;
+    return 0;
+}
+
+extern "C" long lhgt_s2_peaks(lhgt_ctx* c, float hit_ratio, float match_ratio, long max_peak) {
+    int rc = lhgt_s2_gather(c, 0, -1);
+    if (rc) return rc;
+    long n = 0;
+    rc = lhgt_s2_finish(c, hit_ratio, match_ratio, max_peak, &n);
+    return rc ? rc : n;
+}
+
+static int ensure_s3_scratch(lhgt_ctx* c) {
+    if (c->d_cands) return 0;
+    size_t warps = (size_t)s3_grid_blocks(c->device) * s3_warps_per_block();
+    c->scratch.cands_stride = (size_t)2 * kMaxReadLen * c->e;
+    c->scratch.tally_stride = (size_t)3 * 2 * kMaxReadLen;
+    int rc = dev_alloc(&c->d_cands, warps * c->scratch.cands_stride);
+    if (!rc) rc = dev_alloc(&c->d_tally, warps * c->scratch.tally_stride);
+    c->scratch.cands = c->d_cands; c->scratch.tally = c->d_tally;
+    return rc;
+}
+
+extern "C" long lhgt_s3_pairs(lhgt_ctx* c, long first, long count) {
+    if (!c || first < 0) return fail(LHGT_E_ARG, "bad argument");
+    Reads &a = c->reads[0], &b = c->reads[1];
+    if (!a.ready || !b.ready) return fail(LHGT_E_STATE, "upload both FASTQ files first");
+    if (c->n_peaks < 0) return fail(LHGT_E_STATE, "run S2 before S3");
+    if (!c->sampling_set) return fail(LHGT_E_STATE, "call lhgt_set_sampling first");
+    CU(cudaSetDevice(c->device));
+    int rc = ensure_s3_scratch(c);
+    if (rc) return rc;
+    uint64_t cnt = count < 0 ? a.nrec : (uint64_t)count;
+    CU(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), c->st));
+    CU(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->st));
+    if (c->n_peaks > 0) {
+        Span sp(c, 4);
+        c->launches += launch_s3(a.d_fq, a.d_start, a.d_end, a.nrec, b.d_fq, b.d_start, b.d_end, b.nrec, b.tail_start, b.tail_len,
+                                 (uint64_t)first, cnt, c->d_sample_bits, c->hp, c->d_prefilter, c->d_peak_kmer, c->d_loci,
+                                 c->d_filter, c->scratch, s3_grid_blocks(c->device), c->d_counter, c->d_err, c->st);
+    }
+    unsigned long long sampled = 0; int flag = 0;
+    CU(cudaMemcpyAsync(&sampled, c->d_counter, sizeof sampled, cudaMemcpyDeviceToHost, c->st));
+    rc = check_err_flag(c, &flag);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->st));
+    if (flag) return fail(LHGT_E_READ_TOO_LONG, "a read is longer than %d bases", LHGT_MAX_READ_LEN);
+    return (long)sampled;
+}
+
+static int fetch_peaks(lhgt_ctx* c, std::vector<int32_t>& loci, std::vector<uint8_t>& filter) {
+    long n = std::max<long>(c->n_peaks, 0);
+    loci.resize((size_t)n * 2); filter.resize((size_t)n);
+    if (n) {
+        CU(cudaSetDevice(c->device));
+        CU(cudaMemcpyAsync(loci.data(), c->d_loci, (size_t)n * 8, cudaMemcpyDeviceToHost, c->st));
+        CU(cudaMemcpyAsync(filter.data(), c->d_filter, (size_t)n, cudaMemcpyDeviceToHost, c->st));
+        CU(cudaStreamSynchronize(c->st));
+    }
+    return 0;
+}
+
+extern "C" int lhgt_intervals(lhgt_ctx* c, char* dst, size_t cap, size_t* n) {
+    if (!c || !n) return fail(LHGT_E_ARG, "null pointer");
+    if (c->n_peaks < 0) return fail(LHGT_E_STATE, "run S2/S3 first");
+    std::vector<int32_t> loci; std::vector<uint8_t> filter;
+    int rc = fetch_peaks(c, loci, filter);
+    if (rc) return rc;
+    // count_filtered_peak (E:515-548) for the single -t 1 region; the state starts at "1 1 1" (Q9)
+    std::string text;
+    char line[64];
+    int chr = 1, start = 1, end = 1;
+    for (long i = 0; i < c->n_peaks; ++i) {
+        if (!filter[i]) continue;
+        int contig = loci[2 * i], pos = loci[2 * i + 1];
+        if (chr == contig && pos - 500 - end < 500) end = pos + 500;
+        else {
+            snprintf(line, sizeof line, "%d\t%d\t%d\n", chr, start, end);
+            text += line;
+            chr = contig; start = pos - 500; end = pos + 500;
+        }
+    }
+    snprintf(line, sizeof line, "%d\t%d\t%d\n", chr, start, end);
+    text += line;
+    *n = text.size();
+    if (dst) {
+        if (cap < text.size()) return fail(LHGT_E_ARG, "interval buffer too small (%zu needed)", text.size());
+        memcpy(dst, text.data(), text.size());
+    }
+    return 0;
+}
+
+extern "C" int lhgt_reset(lhgt_ctx* c) {
+    if (!c) return fail(LHGT_E_ARG, "null ctx");
+    CU(cudaSetDevice(c->device));
+    clear_peak_tables(c);                       // needs the count table as it was, so it goes first
+    CU(cudaMemsetAsync(c->d_count, 0, c->count_words * 4, c->st));
+    c->n_peaks = -1; c->n_flagged = 0; c->gathered = false;
+    CU(cudaStreamSynchronize(c->st));
+    free_spans(c);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ state access
+extern "C" int lhgt_count_table_copy(lhgt_ctx* c, uint8_t* dst) {
+    if (!c || !dst) return fail(LHGT_E_ARG, "null pointer");
+    CU(cudaSetDevice(c->device));
+    uint64_t entries = 1ull << c->k;
+    uint8_t* d = nullptr;
+    int rc = dev_alloc(&d, entries);
+    if (rc) return rc;
+    c->launches += launch_count_unpack(c->d_count, entries, d, c->st);
+    cudaError_t e1 = cudaMemcpyAsync(dst, d, entries, cudaMemcpyDeviceToHost, c->st);
+    if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(c->st);
+    cudaFree(d);
+    if (e1 != cudaSuccess) return fail(LHGT_E_CUDA, "count table copy failed: %s", cudaGetErrorString(e1));
+    return 0;
+}
+
+extern "C" long lhgt_peaks_copy(lhgt_ctx* c, int32_t* loci, uint8_t* filter, long cap) {
+    if (!c) return fail(LHGT_E_ARG, "null ctx");
+    if (c->n_peaks < 0) return fail(LHGT_E_STATE, "run S2 first");
+    if (cap < c->n_peaks) return c->n_peaks;
+    std::vector<int32_t> l; std::vector<uint8_t> f;
+    int rc = fetch_peaks(c, l, f);
+    if (rc) return rc;
+    if (loci && !l.empty()) memcpy(loci, l.data(), l.size() * 4);
+    if (filter && !f.empty()) memcpy(filter, f.data(), f.size());
+    return c->n_peaks;
+}
+
+extern "C" long lhgt_flagged_positions(const lhgt_ctx* c) { return c ? c->n_flagged : 0; }
+
+extern "C" int lhgt_peak_kmer_copy(lhgt_ctx* c, uint32_t* dst) {
+    if (!c || !dst) return fail(LHGT_E_ARG, "null pointer");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(dst, c->d_peak_kmer, (1ull << c->k) * 4, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+extern "C" void* lhgt_dev_count_table(lhgt_ctx* c, uint64_t* bytes) {
+    if (!c) return nullptr;
+    if (bytes) *bytes = c->count_words * 4;
+    return c->d_count;
+}
+
+extern "C" void* lhgt_dev_hit_bits(lhgt_ctx* c, int which, uint64_t* bytes) {
+    if (!c || !c->index_ready) return nullptr;
+    if (bytes) *bytes = (uint64_t)c->tiles.size() * kTileWords * 4;
+    return which == 0 ? c->d_single : c->d_trio;
+}
+
+extern "C" void* lhgt_dev_peak_filter(lhgt_ctx* c, uint64_t* bytes) {
+    if (!c || c->n_peaks < 0) return nullptr;
+    if (bytes) *bytes = (uint64_t)c->n_peaks;
+    return c->d_filter;
+}
+
+extern "C" int lhgt_count_merge(lhgt_ctx* c, const void* dev_other, uint64_t bytes, uint64_t word_offset) {
+    if (!c || !dev_other || bytes % 4) return fail(LHGT_E_ARG, "bad argument");
+    if (word_offset + bytes / 4 > c->count_words) return fail(LHGT_E_ARG, "merge range exceeds the count table");
+    CU(cudaSetDevice(c->device));
+    c->launches += launch_count_merge(c->d_count + word_offset, (const uint32_t*)dev_other, bytes / 4, c->st);
+    return 0;
+}
+
+extern "C" int lhgt_stage_ms(const lhgt_ctx* cc, float* ms6) {
+    lhgt_ctx* c = const_cast<lhgt_ctx*>(cc);
+    if (!c || !ms6) return fail(LHGT_E_ARG, "null pointer");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->st));
+    for (int i = 0; i < 6; ++i) ms6[i] = 0.f;
+    for (auto& s : c->spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess && s.stage >= 0 && s.stage < 6) ms6[s.stage] += ms;
+    }
+    return 0;
+}
+
+extern "C" long lhgt_launch_count(const lhgt_ctx* c) { return c ? c->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------ the program
+static bool file_exists(const char* p) { struct stat st; return stat(p, &st) == 0; }
+
+extern "C" int lhgt_extract_ref(const lhgt_args* a, lhgt_stats* stats) {
+    if (!a || !a->fq1 || !a->fq2 || !a->fasta || !a->interval) return fail(LHGT_E_ARG, "lhgt_extract_ref: null argument");
+    lhgt_stats st;
+    memset(&st, 0, sizeof st);
+    double t0 = now_s(), t;
+    bool say = !a->quiet;
+    if (say) {
+        printf("kmer length is %d\nseed is %u\nnum of hash functions is %d\n", a->k, a->seed, a->e);
+        if (a->threads != 1) printf("note: -t %d accepted; results follow the reference's single-thread semantics\n", a->threads);
+    }
+    lhgt_ctx* c = nullptr;
+    int rc = lhgt_create(&c, a->device, a->k, a->e);
+    if (rc) return rc;
+    struct Guard { lhgt_ctx* c; ~Guard() { lhgt_destroy(c); } } guard{c};
+
+    // inputs: both FASTQ images go to HBM once and stay there for S1 and S3
+    t = now_s();
+    {
+        HostFile f1, f2;
+        if ((rc = slurp(a->fq1, f1, true)) || (rc = lhgt_reads_upload(c, 0, f1.p, f1.n))) return rc;
+        if ((rc = slurp(a->fq2, f2, true)) || (rc = lhgt_reads_upload(c, 1, f2.p, f2.n))) return rc;
+    }
+    st.seconds[1] = now_s() - t;
+    uint64_t size1 = c->reads[0].n;                                       // E:1419
+
+    double ratio = lhgt_sample_ratio(c, a->sample);                       // E:1392-1398
+    st.ratio_percent = ratio;
+    if (say) {
+        if (a->sample > 1)
+            printf("sample has %ld base pairs.\ndown-sampling ratio: %g%%.\n", (long)c->reads[0].seq_bases * 2, ratio);
+        else printf("down-sampling ratio: %g%%.\n", ratio);
+    }
+
+    // index: reuse when present, otherwise draw the coder and build (E:1401-1413)
+    t = now_s();
+    std::string index_path = std::string(a->fasta) + ".k" + std::to_string(a->k) + ".h" + std::to_string(a->e) + ".index.dat";
+    std::string len_path = std::string(a->fasta) + ".genome.len.txt";
+    long rand_skip = 0;
+    if (!file_exists(index_path.c_str())) {
+        if (say) printf("Reference index not detected, start index...\n");
+        int16_t cc[LHGT_CODER_SLOTS];
+        int draws = lhgt_random_coder(a->seed, a->k, a->e, cc);
+        if (draws < 0) return draws;
+        rand_skip = draws;                                                // Q3: the sampling stream starts after them
+        if ((rc = lhgt_set_coder(c, cc))) return rc;
+        if ((rc = lhgt_index_build_file(c, a->fasta, index_path.c_str(), len_path.c_str()))) return rc;
+        st.index_built = 1;
+    } else {
+        if (say) printf("Reference index is detected.\n");
+        if ((rc = lhgt_index_load_file(c, index_path.c_str()))) return rc;
+    }
+    st.seconds[2] = now_s() - t;
+    if (say) printf("Start extract HGT-related segments...\n");
+
+    if ((rc = lhgt_set_sampling(c, ratio, a->seed, rand_skip))) return rc;   // E:1422
+
+    t = now_s();
+    long n;
+    if ((n = lhgt_s1_count(c, 0, size1)) < 0) return (int)n;
+    st.reads_s1[0] = n;
+    if ((n = lhgt_s1_count(c, 1, size1)) < 0) return (int)n;               // Q15: fq1's size bounds fq2 too
+    st.reads_s1[1] = n;
+    st.seconds[3] = now_s() - t;
+    if (say) printf("K-mer counting is finished.\nconsidered read pair num in kmer counting:%ld\n", (st.reads_s1[0] + st.reads_s1[1]) / 2);
+
+    t = now_s();
+    if ((n = lhgt_s2_peaks(c, (float)a->hit_ratio, (float)a->match_ratio, a->max_peak)) < 0) return (int)n;
+    st.peaks = n; st.flagged_positions = c->n_flagged;
+    st.seconds[4] = now_s() - t;
+    if (say) printf("Slided ref len: %llu bp\tNo. of raw BKPs: %ld\nraw breakpoint screening is done.\n", (unsigned long long)c->index_bases, st.peaks);
+
+    // first records must carry the same read id (E:368-399); we refuse instead of re-seeking fq2
+    t = now_s();
+    if (c->reads[0].nrec && c->reads[1].n) {
+        uint8_t h1[512], h2[512];
+        size_t n1 = std::min<uint64_t>(c->reads[0].n, sizeof h1), n2 = std::min<uint64_t>(c->reads[1].n, sizeof h2);
+        CU(cudaMemcpy(h1, c->reads[0].d_fq, n1, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(h2, c->reads[1].d_fq, n2, cudaMemcpyDeviceToHost));
+        const uint8_t* e1 = (const uint8_t*)memchr(h1, '\n', n1);
+        const uint8_t* e2 = (const uint8_t*)memchr(h2, '\n', n2);
+        size_t l1 = read_id_len(h1, e1 ? (size_t)(e1 - h1) : n1), l2 = read_id_len(h2, e2 ? (size_t)(e2 - h2) : n2);
+        if (l1 != l2 || memcmp(h1, h2, l1) != 0)
+            return fail(LHGT_E_UNPAIRED, "first records of fq1 and fq2 carry different read ids");
+    }
+    if ((n = lhgt_s3_pairs(c, 0, -1)) < 0) return (int)n;
+    st.pairs_s3 = n;
+    st.seconds[5] = now_s() - t;
+    if (say) printf("candidate HGT breakpoint screening is done.\nconsidered read pair num in finding candidate HGT breakpoint:%ld\n", st.pairs_s3);
+
+    t = now_s();
+    size_t need = 0;
+    if ((rc = lhgt_intervals(c, nullptr, 0, &need))) return rc;
+    std::string text(need, '\0');
+    if ((rc = lhgt_intervals(c, &text[0], text.size(), &need))) return rc;
+    if ((rc = spill(a->interval, text.data(), text.size()))) return rc;
+    {
+        std::vector<int32_t> loci; std::vector<uint8_t> filter;
+        if ((rc = fetch_peaks(c, loci, filter))) return rc;
+        for (uint8_t f : filter) st.kept_peaks += f != 0;
+    }
+    st.seconds[6] = now_s() - t;
+    st.seconds[0] = now_s() - t0;
+    if (say) printf("Finish with time:\t%.3f\n", st.seconds[0]);
+    if (stats) *stats = st;
+    return 0;
+}
+
+// stod-like parse of a whole argument (E:1359-1371)
+static bool parse_num(const char* s, double* out) {
+    char* end = nullptr;
+    double v = strtod(s, &end);
+    if (end == s) return false;
+    *out = v;
+    return true;
+}
+
+extern "C" int lhgt_main(int argc, char** argv) {
+    if (argc < 13) {
+        fprintf(stderr,
+                "usage: extract_ref <fq1> <fq2> <ref.fa> <interval_out> <hit_ratio> <match_ratio> <threads> <k> <max_peak> <e> <seed> <sample>\n"
+                "       (same positional arguments as LocalHGT's extract_ref; set LHGT_DEVICE to pick a GPU)\n");
+        return 2;
+    }
+    double v[8];
+    const int idx[8] = {5, 6, 7, 8, 9, 10, 11, 12};
+    for (int i = 0; i < 8; ++i)
+        if (!parse_num(argv[idx[i]], &v[i])) { fprintf(stderr, "extract_ref: argument %d (\"%s\") is not a number\n", idx[i], argv[idx[i]]); return 2; }
+    lhgt_args a;
+    memset(&a, 0, sizeof a);
+    a.fq1 = argv[1]; a.fq2 = argv[2]; a.fasta = argv[3]; a.interval = argv[4];
+    a.hit_ratio = (double)(float)v[0]; a.match_ratio = (double)(float)v[1];   // float hit_ratio = stod(...) (E:1368-1369)
+    a.threads = (int)v[2]; a.k = (int)v[3]; a.max_peak = (long)(int)v[4]; a.e = (int)v[5];
+    a.seed = (unsigned)v[6]; a.sample = v[7];
+    const char* dev = getenv("LHGT_DEVICE");
+    a.device = dev ? atoi(dev) : 0;
+    a.quiet = getenv("LHGT_QUIET") != nullptr;
+    int rc = lhgt_extract_ref(&a, nullptr);
+    if (rc) { fprintf(stderr, "extract_ref: error %d: %s\n", rc, lhgt_last_error()); return 1; }
+    return 0;
+}

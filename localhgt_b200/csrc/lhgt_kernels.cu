@@ -1,0 +1,933 @@
+// sm_100a kernels of the LocalHGT k-mer screen.  Integer hashing + HBM gathers; no tensor cores.
+// "E:" = reference src/extract_ref_normal_peak.cpp (cited for semantics only; nothing here is a
+// translation of it — see DESIGN.md §4 for the data-parallel forms these kernels evaluate).
+#include "lhgt_kernels.cuh"
+
+namespace lhgt {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kSMs = 148;
+
+// ------------------------------------------------------------------------------------------------
+// bit-plane hashing (semantics E:786-813 == E:1052-1081 == E:430-452)
+// ------------------------------------------------------------------------------------------------
+
+// ASCII -> 4 bits: plane0 (A,T) | plane1 (A,C) << 1 | plane2 (A,G) << 2 | valid << 3   (E:1109-1154)
+__device__ __forceinline__ uint32_t base_bits(uint32_t ch) {
+    uint32_t up = ch & 0xDFu;
+    uint32_t a = up == 65u, c = up == 67u, g = up == 71u, t = up == 84u;
+    return (a | t) | ((a | c) << 1) | ((a | g) << 2) | ((a | c | g | t) << 3);
+}
+
+// Planes are stored big-endian in bit order: position p is bit (31 - p%32) of word p/32, so the
+// 32 positions starting at j come out of one funnel shift with position j in bit 31.
+__device__ __forceinline__ uint32_t window32(const uint32_t* plane, int j) {
+    int q = j >> 5;
+    return __funnelshift_l(plane[q + 1], plane[q], j & 31);
+}
+
+struct KmerWin {
+    uint32_t w2, x0, x1;        // forward:  W2, W0^W2, W1^W2
+    uint32_t nrw2, nrx0, rx1;   // mirrored: ~rev(W2), ~rev(W0^W2), rev(W1^W2)
+    bool valid;
+};
+
+template <int STRIDE>
+__device__ __forceinline__ KmerWin make_win(const uint32_t* planes, int j, const HashP& hp) {
+    KmerWin kw;
+    uint32_t a = window32(planes, j) >> hp.shr;
+    uint32_t b = window32(planes + STRIDE, j) >> hp.shr;
+    uint32_t c = window32(planes + 2 * STRIDE, j) >> hp.shr;
+    uint32_t v = window32(planes + 3 * STRIDE, j) >> hp.shr;
+    kw.valid = v == hp.kmask;
+    kw.w2 = c;
+    kw.x0 = a ^ c;
+    kw.x1 = b ^ c;
+    kw.nrw2 = ~(__brev(c) >> hp.shr);
+    kw.nrx0 = ~(__brev(kw.x0) >> hp.shr);
+    kw.rx1 = __brev(kw.x1) >> hp.shr;
+    return kw;
+}
+
+__device__ __forceinline__ uint32_t hash_of(const KmerWin& kw, const HashP& hp, int i) {
+    uint32_t f = kw.w2 ^ (kw.x0 & hp.m0[i]) ^ (kw.x1 & hp.m1[i]);
+    uint32_t r = (kw.nrw2 ^ (kw.nrx0 & hp.m0[i]) ^ (kw.rx1 & hp.m1[i])) & hp.kmask;
+    return min(f, r);
+}
+
+// One warp turns `len` ASCII bytes into four plane arrays of `nw+1` words (last one zero).
+template <int STRIDE>
+__device__ __forceinline__ void warp_pack(const uint8_t* __restrict__ src, int len, uint32_t* planes, int lane) {
+    int nw = (len + 31) >> 5;
+    for (int w = 0; w < nw; ++w) {
+        int p = w * 32 + lane;
+        uint32_t bits = p < len ? base_bits(src[p]) : 0u;
+        uint32_t b0 = __brev(__ballot_sync(kFull, bits & 1u));
+        uint32_t b1 = __brev(__ballot_sync(kFull, bits & 2u));
+        uint32_t b2 = __brev(__ballot_sync(kFull, bits & 4u));
+        uint32_t b3 = __brev(__ballot_sync(kFull, bits & 8u));
+        if (lane == 0) {
+            planes[w] = b0; planes[STRIDE + w] = b1; planes[2 * STRIDE + w] = b2; planes[3 * STRIDE + w] = b3;
+        }
+    }
+    if (lane == 0) {
+        planes[nw] = 0; planes[STRIDE + nw] = 0; planes[2 * STRIDE + nw] = 0; planes[3 * STRIDE + nw] = 0;
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2-bit saturating count table: entry h lives in bits [2*(h&15), +2) of word h>>4
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_table(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_stream(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+// count[h] = min(3, count[h] + 1), exact under any interleaving (E:1082-1084 made race-free).
+__device__ __forceinline__ void bump(uint32_t* count, uint32_t h, uint32_t seen) {
+    uint32_t* addr = count + (h >> 4);
+    int sh = (h & 15u) * 2;
+    while (((seen >> sh) & 3u) < 3u) {
+        uint32_t old = atomicCAS(addr, seen, seen + (1u << sh));
+        if (old == seen) break;
+        seen = old;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// exclusive scan of u32 (tile counts): 1024 elements per block, recursive over block sums
+// ------------------------------------------------------------------------------------------------
+constexpr int kScanBlock = 256, kScanItems = 4, kScanSpan = kScanBlock * kScanItems;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total, uint32_t* smem /*>=9*/) {
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(kFull, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) smem[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < (int)(blockDim.x >> 5) ? smem[lane] : 0;
+        uint32_t winc = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(kFull, winc, d);
+            if (lane >= d) winc += t;
+        }
+        if (lane < (int)(blockDim.x >> 5)) smem[lane] = winc - w;
+        if (lane == 31) smem[32] = winc;
+    }
+    __syncthreads();
+    uint32_t res = smem[warp] + inc - v;
+    *total = smem[32];
+    __syncthreads();
+    return res;
+}
+
+__global__ void __launch_bounds__(kScanBlock) scan_block_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+                                                                uint64_t n, uint32_t* __restrict__ block_sums) {
+    __shared__ uint32_t sm[33];
+    uint64_t base = (uint64_t)blockIdx.x * kScanSpan + (uint64_t)threadIdx.x * kScanItems;
+    uint32_t v[kScanItems], sum = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) { v[i] = base + i < n ? in[base + i] : 0u; sum += v[i]; }
+    uint32_t total, ex = block_exclusive_scan(sum, &total, sm);
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) { if (base + i < n) out[base + i] = ex; ex += v[i]; }
+    if (threadIdx.x == 0 && block_sums) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanBlock) scan_add_kernel(uint32_t* __restrict__ out, uint64_t n,
+                                                              const uint32_t* __restrict__ block_prefix) {
+    uint64_t base = (uint64_t)blockIdx.x * kScanSpan + (uint64_t)threadIdx.x * kScanItems;
+    uint32_t add = block_prefix[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) if (base + i < n) out[base + i] += add;
+}
+
+size_t scan_tmp_words(uint64_t n) {
+    size_t words = 0;
+    while (n > 1) { n = (n + kScanSpan - 1) / kScanSpan; words += 2 * n; }
+    return words + 2;
+}
+
+int launch_scan_exclusive(const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* tmp, cudaStream_t st) {
+    if (n == 0) return 0;
+    uint64_t blocks = (n + kScanSpan - 1) / kScanSpan;
+    int launches = 0;
+    if (blocks == 1) {
+        scan_block_kernel<<<1, kScanBlock, 0, st>>>(in, out, n, nullptr);
+        return 1;
+    }
+    uint32_t* sums = tmp;
+    uint32_t* sums_scanned = tmp + blocks;
+    scan_block_kernel<<<(unsigned)blocks, kScanBlock, 0, st>>>(in, out, n, sums);
+    launches += 1;
+    launches += launch_scan_exclusive(sums, sums_scanned, blocks, tmp + 2 * blocks, st);
+    scan_add_kernel<<<(unsigned)blocks, kScanBlock, 0, st>>>(out, n, sums_scanned);
+    return launches + 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FASTQ record location (the getline loops of E:1020-1034 / E:356-409 as a newline scan)
+// ------------------------------------------------------------------------------------------------
+constexpr int kFqThreads = 256, kFqIter = 4, kFqChunk = 16, kFqSub = kFqThreads * kFqChunk, kFqTile = kFqSub * kFqIter;
+
+uint64_t fastq_index_tiles(uint64_t n) { return (n + kFqTile - 1) / kFqTile; }
+
+__device__ __forceinline__ void load16(const uint8_t* __restrict__ fq, uint64_t off, uint64_t n, uint32_t w[4]) {
+    if (off + 16 <= n) {
+        uint4 v = *reinterpret_cast<const uint4*>(fq + off);
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    } else {
+        w[0] = w[1] = w[2] = w[3] = 0;
+        for (int b = 0; b < 16; ++b)
+            if (off + b < n) w[b >> 2] |= (uint32_t)fq[off + b] << ((b & 3) * 8);
+    }
+}
+
+__global__ void __launch_bounds__(kFqThreads) fq_count_kernel(const uint8_t* __restrict__ fq, uint64_t n,
+                                                              uint32_t* __restrict__ tile_cnt) {
+    __shared__ uint32_t sm[8];
+    uint64_t tile0 = (uint64_t)blockIdx.x * kFqTile;
+    uint32_t c = 0;
+#pragma unroll
+    for (int it = 0; it < kFqIter; ++it) {
+        uint64_t off = tile0 + (uint64_t)it * kFqSub + (uint64_t)threadIdx.x * kFqChunk;
+        if (off < n) {
+            uint32_t w[4];
+            load16(fq, off, n, w);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) c += __popc(__vcmpeq4(w[q], 0x0a0a0a0au)) >> 3;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(kFull, c, d);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < kFqThreads / 32; ++w) t += sm[w];
+        tile_cnt[blockIdx.x] = t;
+    }
+}
+
+// newline with global rank g ends line g: line 4r+1 is the sequence of record r
+__global__ void __launch_bounds__(kFqThreads) fq_assign_kernel(const uint8_t* __restrict__ fq, uint64_t n,
+                                                               const uint32_t* __restrict__ tile_base,
+                                                               uint64_t* __restrict__ rec_start,
+                                                               uint64_t* __restrict__ rec_end, uint64_t rec_cap) {
+    __shared__ uint32_t sm[33];
+    uint64_t tile0 = (uint64_t)blockIdx.x * kFqTile;
+    uint64_t running = tile_base[blockIdx.x];
+    for (int it = 0; it < kFqIter; ++it) {
+        uint64_t off = tile0 + (uint64_t)it * kFqSub + (uint64_t)threadIdx.x * kFqChunk;
+        uint32_t w[4] = {0, 0, 0, 0}, m[4], c = 0;
+        if (off < n) load16(fq, off, n, w);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { m[q] = off < n ? __vcmpeq4(w[q], 0x0a0a0a0au) : 0u; c += __popc(m[q]) >> 3; }
+        uint32_t total, ex = block_exclusive_scan(c, &total, sm);
+        uint64_t g = running + ex;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t mm = m[q];
+            while (mm) {
+                int bit = __ffs(mm) - 1;
+                mm &= ~(0xffu << (bit & ~7));
+                uint64_t pos = off + q * 4 + (bit >> 3);
+                uint64_t r = g >> 2;
+                if (r < rec_cap) {
+                    if ((g & 3) == 0) rec_start[r] = pos + 1;
+                    else if ((g & 3) == 1) rec_end[r] = pos;
+                }
+                ++g;
+            }
+        }
+        running += total;
+    }
+}
+
+int launch_fastq_index(const uint8_t* fq, uint64_t n, uint32_t* tile_cnt, uint32_t* tile_base, uint32_t* scan_tmp,
+                       uint64_t* rec_start, uint64_t* rec_end, uint64_t rec_cap, int phase, cudaStream_t st) {
+    uint64_t tiles = fastq_index_tiles(n);
+    if (tiles == 0) return 0;
+    if (phase == 0) {
+        fq_count_kernel<<<(unsigned)tiles, kFqThreads, 0, st>>>(fq, n, tile_cnt);
+        return 1 + launch_scan_exclusive(tile_cnt, tile_base, tiles, scan_tmp, st);
+    }
+    fq_assign_kernel<<<(unsigned)tiles, kFqThreads, 0, st>>>(fq, n, tile_base, rec_start, rec_end, rec_cap);
+    return 1;
+}
+
+__global__ void sum_lengths_kernel(const uint64_t* __restrict__ s, const uint64_t* __restrict__ e, uint64_t n,
+                                   unsigned long long* out) {
+    unsigned long long acc = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        acc += e[i] - s[i];
+#pragma unroll
+    for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(kFull, acc, d);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
+int launch_sum_lengths(const uint64_t* rec_start, const uint64_t* rec_end, uint64_t nrec, unsigned long long* out,
+                       cudaStream_t st) {
+    if (nrec == 0) return 0;
+    sum_lengths_kernel<<<kSMs * 4, 256, 0, st>>>(rec_start, rec_end, nrec, out);
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// IB: index build.  One block per 1024-position tile: ASCII -> planes in shared memory -> e hashes
+// per position, stored position-major/hash-minor exactly as the file holds them (E:785-813).
+// ------------------------------------------------------------------------------------------------
+constexpr int kIbPlane = kTileWords + 4;   // 33 words used (+1 zero word read by window32)
+
+template <int E>
+__global__ void __launch_bounds__(256) index_build_kernel(const uint8_t* __restrict__ seq, const Contig* __restrict__ contigs,
+                                                          const Tile* __restrict__ tiles, HashP hp,
+                                                          uint32_t* __restrict__ image, uint8_t* __restrict__ valid_out) {
+    __shared__ uint32_t planes[4 * kIbPlane];
+    const int e = E ? E : hp.e;
+    Tile t = tiles[blockIdx.x];
+    Contig c = contigs[t.contig];
+    long np = (long)c.len - hp.k + 1;
+    long j0 = t.j0;
+    if (j0 >= np) return;
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint8_t* src = seq + c.seq_off + j0;
+    long avail = (long)c.len - j0;
+    for (int w = warp; w < kTileWords + 2; w += 8) {
+        int p = w * 32 + lane;
+        uint32_t bits = p < avail ? base_bits(src[p]) : 0u;
+        uint32_t b0 = __brev(__ballot_sync(kFull, bits & 1u));
+        uint32_t b1 = __brev(__ballot_sync(kFull, bits & 2u));
+        uint32_t b2 = __brev(__ballot_sync(kFull, bits & 4u));
+        uint32_t b3 = __brev(__ballot_sync(kFull, bits & 8u));
+        if (lane == 0) {
+            planes[w] = b0; planes[kIbPlane + w] = b1; planes[2 * kIbPlane + w] = b2; planes[3 * kIbPlane + w] = b3;
+        }
+    }
+    __syncthreads();
+    if (j0 == 0 && threadIdx.x == 0) image[c.hash_word - 1] = c.len;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        int jl = r * 256 + threadIdx.x;
+        long j = j0 + jl;
+        if (j < np) {
+            KmerWin kw = make_win<kIbPlane>(planes, jl, hp);
+            uint32_t* dst = image + c.hash_word + (size_t)j * e;
+#pragma unroll
+            for (int i = 0; i < (E ? E : kMaxE); ++i)
+                if (i < e) dst[i] = kw.valid ? hash_of(kw, hp, i) : 0u;
+            if (valid_out) valid_out[j] = kw.valid;
+        }
+    }
+}
+
+template <int E>
+static void ib_launch(const uint8_t* seq, const Contig* contigs, const Tile* tiles, uint64_t ntiles, const HashP& hp,
+                      uint32_t* image, uint8_t* valid_out, cudaStream_t st) {
+    index_build_kernel<E><<<(unsigned)ntiles, 256, 0, st>>>(seq, contigs, tiles, hp, image, valid_out);
+}
+
+int launch_index_build(const uint8_t* seq, const Contig* contigs, const Tile* tiles, uint64_t ntiles, const HashP& hp,
+                       uint32_t* image, uint8_t* valid_out, cudaStream_t st) {
+    if (ntiles == 0) return 0;
+    switch (hp.e) {
+        case 1: ib_launch<1>(seq, contigs, tiles, ntiles, hp, image, valid_out, st); break;
+        case 2: ib_launch<2>(seq, contigs, tiles, ntiles, hp, image, valid_out, st); break;
+        case 3: ib_launch<3>(seq, contigs, tiles, ntiles, hp, image, valid_out, st); break;
+        case 4: ib_launch<4>(seq, contigs, tiles, ntiles, hp, image, valid_out, st); break;
+        default: ib_launch<0>(seq, contigs, tiles, ntiles, hp, image, valid_out, st); break;
+    }
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// S1: sampled-read k-mer counting (E:1037-1087).  One warp per read; the read is 2-bit(+valid)
+// packed into shared memory by ballots; each lane hashes positions lane, lane+32, ... and issues all
+// its table loads before the first compare-and-swap so ~12 independent sectors per lane are in flight.
+// ------------------------------------------------------------------------------------------------
+constexpr int kReadPlane = (kMaxReadLen + 31) / 32 + 2;   // 18 words
+constexpr int kS1Warps = 8, kS1Unroll = 4;
+
+__device__ __forceinline__ bool is_sampled(const uint32_t* __restrict__ sample_bits, uint64_t ordinal) {
+    if (!sample_bits) return true;
+    uint32_t o = (uint32_t)(ordinal % (uint64_t)kRandomArray);
+    return (sample_bits[o >> 5] >> (o & 31)) & 1u;
+}
+
+template <int E>
+__global__ void __launch_bounds__(kS1Warps * 32, 4) s1_count_kernel(
+    const uint8_t* __restrict__ fq, const uint64_t* __restrict__ rec_start, const uint64_t* __restrict__ rec_end,
+    uint64_t nrec, uint64_t budget, const uint32_t* __restrict__ sample_bits, HashP hp, uint32_t* __restrict__ count,
+    unsigned long long* __restrict__ n_sampled, int* __restrict__ err) {
+    __shared__ uint32_t planes_all[kS1Warps][4 * kReadPlane];
+    const int e = E ? E : hp.e;
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* planes = planes_all[warp];
+    unsigned long long mine = 0;
+    uint64_t stride = (uint64_t)gridDim.x * kS1Warps;
+    for (uint64_t r = (uint64_t)blockIdx.x * kS1Warps + warp; r < nrec; r += stride) {
+        uint64_t start = rec_start[r];
+        if (start > budget) continue;                       // Q15 (E:1022-1025 with end = size(fq1))
+        if (!is_sampled(sample_bits, r)) continue;
+        uint64_t len64 = rec_end[r] - start;
+        if (len64 > (uint64_t)kMaxReadLen) { if (lane == 0) atomicExch(err, 1); continue; }
+        int len = (int)len64;
+        ++mine;
+        int np = len - hp.k + 1;
+        if (np <= 0) continue;
+        warp_pack<kReadPlane>(fq + start, len, planes, lane);
+        for (int j0 = 0; j0 < np; j0 += 32 * kS1Unroll) {
+            uint32_t h[kS1Unroll][E ? E : kMaxE];
+            uint32_t seen[kS1Unroll][E ? E : kMaxE];
+            bool ok[kS1Unroll];
+#pragma unroll
+            for (int u = 0; u < kS1Unroll; ++u) {
+                int j = j0 + u * 32 + lane;
+                ok[u] = j < np;
+                KmerWin kw = make_win<kReadPlane>(planes, ok[u] ? j : 0, hp);
+                ok[u] = ok[u] && kw.valid;
+#pragma unroll
+                for (int i = 0; i < (E ? E : kMaxE); ++i)
+                    if (i < e) h[u][i] = hash_of(kw, hp, i);
+            }
+#pragma unroll
+            for (int u = 0; u < kS1Unroll; ++u)
+#pragma unroll
+                for (int i = 0; i < (E ? E : kMaxE); ++i)
+                    if (i < e && ok[u]) seen[u][i] = ld_table(count + (h[u][i] >> 4));
+#pragma unroll
+            for (int u = 0; u < kS1Unroll; ++u)
+#pragma unroll
+                for (int i = 0; i < (E ? E : kMaxE); ++i)
+                    if (i < e && ok[u]) bump(count, h[u][i], seen[u][i]);
+        }
+        __syncwarp();
+    }
+    if (lane == 0 && mine) atomicAdd(n_sampled, mine);
+}
+
+template <int E>
+static void s1_launch(const uint8_t* fq, const uint64_t* rs, const uint64_t* re, uint64_t nrec, uint64_t budget,
+                      const uint32_t* sb, const HashP& hp, uint32_t* count, unsigned long long* ns, int* err,
+                      cudaStream_t st) {
+    uint64_t want = (nrec + kS1Warps - 1) / kS1Warps;
+    unsigned grid = (unsigned)(want < (uint64_t)kSMs * 4 ? want : (uint64_t)kSMs * 4);
+    s1_count_kernel<E><<<grid, kS1Warps * 32, 0, st>>>(fq, rs, re, nrec, budget, sb, hp, count, ns, err);
+}
+
+int launch_s1(const uint8_t* fq, const uint64_t* rec_start, const uint64_t* rec_end, uint64_t nrec, uint64_t budget,
+              const uint32_t* sample_bits, const HashP& hp, uint32_t* count, unsigned long long* n_sampled, int* err,
+              cudaStream_t st) {
+    if (nrec == 0) return 0;
+    switch (hp.e) {
+        case 1: s1_launch<1>(fq, rec_start, rec_end, nrec, budget, sample_bits, hp, count, n_sampled, err, st); break;
+        case 2: s1_launch<2>(fq, rec_start, rec_end, nrec, budget, sample_bits, hp, count, n_sampled, err, st); break;
+        case 3: s1_launch<3>(fq, rec_start, rec_end, nrec, budget, sample_bits, hp, count, n_sampled, err, st); break;
+        case 4: s1_launch<4>(fq, rec_start, rec_end, nrec, budget, sample_bits, hp, count, n_sampled, err, st); break;
+        default: s1_launch<0>(fq, rec_start, rec_end, nrec, budget, sample_bits, hp, count, n_sampled, err, st); break;
+    }
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// S2 (E:888-979 + E:550-725 + E:239-301) as five data-parallel passes over 1024-position tiles.
+// Bit arrays are little-endian in bit order: tile t, local position x -> word t*32 + x/32, bit x%32.
+// ------------------------------------------------------------------------------------------------
+
+// pass a: gather the count table at the stored hashes; single = some hash saturated, trio = all (E:573-595)
+template <int E>
+__global__ void __launch_bounds__(256) s2_gather_kernel(const uint32_t* __restrict__ image, const Contig* __restrict__ contigs,
+                                                        const Tile* __restrict__ tiles, uint64_t tile_begin, HashP hp,
+                                                        const uint32_t* __restrict__ count, uint32_t* __restrict__ single,
+                                                        uint32_t* __restrict__ trio) {
+    const int e = E ? E : hp.e;
+    uint64_t tix = tile_begin + blockIdx.x;
+    Tile t = tiles[tix];
+    Contig c = contigs[t.contig];
+    long np = (long)c.len - hp.k + 1;
+    const uint32_t* hashes = image + c.hash_word;
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t h[4][E ? E : kMaxE], w[4][E ? E : kMaxE];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        long j = (long)t.j0 + r * 256 + threadIdx.x;
+#pragma unroll
+        for (int i = 0; i < (E ? E : kMaxE); ++i)
+            if (i < e) h[r][i] = j < np ? ld_stream(hashes + (size_t)j * e + i) : 0u;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int i = 0; i < (E ? E : kMaxE); ++i)
+            if (i < e) w[r][i] = h[r][i] ? ld_stream(count + (h[r][i] >> 4)) : 0u;   // stored 0 = no hit (Q4, E:936-941)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        int full = 0;
+#pragma unroll
+        for (int i = 0; i < (E ? E : kMaxE); ++i)
+            if (i < e) full += h[r][i] && ((w[r][i] >> ((h[r][i] & 15u) * 2)) & 3u) == 3u;
+        uint32_t ws = __ballot_sync(kFull, full > 0);
+        uint32_t wt = __ballot_sync(kFull, full == e);
+        if (lane == 0) {
+            size_t word = (size_t)tix * kTileWords + r * 8 + warp;
+            single[word] = ws;
+            trio[word] = wt;
+        }
+    }
+}
+
+// inclusive count of set bits in local bit positions [0, x] of `words` given per-word exclusive prefix `cum`
+__device__ __forceinline__ int bits_upto(const uint32_t* words, const int* cum, int x) {
+    if (x < 0) return 0;
+    int q = x >> 5;
+    return cum[q] + __popc(words[q] & (0xffffffffu >> (31 - (x & 31))));
+}
+
+__device__ __forceinline__ void prefix_words(const uint32_t* words, int* cum, int n) {
+    // n <= 96: one warp's worth of serial work is cheaper than a scan here
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int i = 0; i < n; ++i) { cum[i] = acc; acc += __popc(words[i]); }
+        cum[n] = acc;
+    }
+}
+
+// pass b: 500-wide window sums and the good-window flag (E:597-615)
+__global__ void __launch_bounds__(256) s2_good_kernel(const Contig* __restrict__ contigs, const Tile* __restrict__ tiles,
+                                                      const uint32_t* __restrict__ single, const uint32_t* __restrict__ trio,
+                                                      int one_min, int three_min, uint32_t* __restrict__ good) {
+    __shared__ uint32_t ws[2 * kTileWords], wt[2 * kTileWords];
+    __shared__ int cs[2 * kTileWords + 1], ct[2 * kTileWords + 1];
+    Tile t = tiles[blockIdx.x];
+    Contig c = contigs[t.contig];
+    bool has_prev = t.j0 > 0;
+    if (threadIdx.x < 2 * kTileWords) {
+        int q = threadIdx.x;
+        bool take = q >= kTileWords || has_prev;
+        size_t word = (size_t)blockIdx.x * kTileWords + q - kTileWords;
+        ws[q] = take ? single[word] : 0u;
+        wt[q] = take ? trio[word] : 0u;
+    }
+    __syncthreads();
+    prefix_words(ws, cs, 2 * kTileWords);
+    if (threadIdx.x == 32) {
+        int acc = 0;
+        for (int i = 0; i < 2 * kTileWords; ++i) { ct[i] = acc; acc += __popc(wt[i]); }
+    }
+    __syncthreads();
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        int xl = r * 256 + threadIdx.x;
+        long j = (long)t.j0 + xl;
+        int b = kTile + xl;
+        int one = bits_upto(ws, cs, b) - bits_upto(ws, cs, b - 500);
+        int three = bits_upto(wt, ct, b) - bits_upto(wt, ct, b - 500);
+        bool g = j < (long)c.len && one >= one_min && three >= three_min;
+        uint32_t wg = __ballot_sync(kFull, g);
+        if (lane == 0) good[(size_t)blockIdx.x * kTileWords + r * 8 + warp] = wg;
+    }
+}
+
+// pass c: interval membership (E:617-638, 675-686 collapse to "a good window within +-1000") and the
+// coverage-edge peak test (E:640-671) in its closed form:
+//   D(x) = sum single[x-4..x],  C(j) = D(j-5) - D(j-k-5) - D(j),  diff_t(j) = C(j) + D(j-k-5-t), t in [0,k)
+//   peak[j] if some diff_t(j) <= -2;  peak[j-k-5-t] if diff_t(j) >= 2;  only for 2k+10 < j < len.
+__global__ void __launch_bounds__(256) s2_flag_kernel(const Contig* __restrict__ contigs, const Tile* __restrict__ tiles,
+                                                      uint64_t ntiles, int k, const uint32_t* __restrict__ single,
+                                                      const uint32_t* __restrict__ good, uint32_t* __restrict__ flagged) {
+    __shared__ uint32_t ws[3 * kTileWords + 1], wg[3 * kTileWords];
+    __shared__ int cg[3 * kTileWords + 1];
+    __shared__ signed char D[3 * kTile], C[3 * kTile];
+    Tile t = tiles[blockIdx.x];
+    Contig c = contigs[t.contig];
+    bool has_prev = t.j0 > 0;
+    bool has_next = blockIdx.x + 1 < ntiles && tiles[blockIdx.x + 1].contig == t.contig;
+    if (threadIdx.x < 3 * kTileWords) {
+        int q = threadIdx.x;
+        bool take = (q >= kTileWords || has_prev) && (q < 2 * kTileWords || has_next);
+        size_t word = (size_t)blockIdx.x * kTileWords + q - kTileWords;
+        ws[q] = take ? single[word] : 0u;
+        wg[q] = take ? good[word] : 0u;
+    }
+    if (threadIdx.x == 0) ws[3 * kTileWords] = 0;
+    __syncthreads();
+    prefix_words(wg, cg, 3 * kTileWords);
+    for (int x = threadIdx.x; x < 3 * kTile; x += 256) {
+        int d = 0;
+        if (x >= 4) {
+            int lo = x - 4, q = lo >> 5, s = lo & 31;
+            uint64_t two = ((uint64_t)ws[q + 1] << 32) | ws[q];
+            d = __popc((uint32_t)(two >> s) & 31u);
+        }
+        D[x] = (signed char)d;
+    }
+    __syncthreads();
+    for (int x = kTile + threadIdx.x; x < 3 * kTile; x += 256) {
+        long j = (long)t.j0 - kTile + x;
+        bool okj = j > 2 * k + 10 && j < (long)c.len;
+        C[x] = okj ? (signed char)(D[x - 5] - D[x - k - 5] - D[x]) : (signed char)-100;
+    }
+    __syncthreads();
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        int xl = r * 256 + threadIdx.x;
+        int x = kTile + xl;
+        long j = (long)t.j0 + xl;
+        bool f = false;
+        if (j < (long)c.len && j >= 1) {
+            int lo = x - 1000, hi = x + 1000;
+            bool in_iv = bits_upto(wg, cg, hi) - bits_upto(wg, cg, lo - 1) > 0;
+            if (in_iv) {
+                int cj = C[x], dq = D[x];
+                bool pk = false;
+                if (cj != -100) {
+                    int m = 100;
+                    for (int tt = 0; tt < k; ++tt) m = min(m, (int)D[x - k - 5 - tt]);
+                    pk = cj + m <= -2;
+                }
+                for (int tt = 0; tt < k && !pk; ++tt) pk = (int)C[x + k + 5 + tt] + dq >= 2;
+                f = pk;
+            }
+        }
+        uint32_t wf = __ballot_sync(kFull, f);
+        if (lane == 0) flagged[(size_t)blockIdx.x * kTileWords + r * 8 + warp] = wf;
+    }
+}
+
+// A flagged position opens a new peak iff no flagged position precedes it in its 50-bp bucket (E:288-301).
+__device__ __forceinline__ bool flagged_at(const uint32_t* __restrict__ flagged, uint64_t tix, long j0, long j) {
+    long rel = j - j0;                 // may be negative (previous tile of the same contig)
+    long bit = (long)tix * kTile + rel;
+    return (flagged[bit >> 5] >> (bit & 31)) & 1u;
+}
+
+__device__ __forceinline__ bool opens_peak(const uint32_t* __restrict__ flagged, uint64_t tix, long j0, long j) {
+    long bs = (j / 50) * 50;
+    for (long q = bs; q < j; ++q)
+        if (flagged_at(flagged, tix, j0, q)) return false;
+    return true;
+}
+
+__global__ void __launch_bounds__(256) s2_count_new_kernel(const Contig* __restrict__ contigs, const Tile* __restrict__ tiles,
+                                                           const uint32_t* __restrict__ flagged, uint32_t* __restrict__ tile_new,
+                                                           unsigned long long* __restrict__ flagged_total) {
+    __shared__ uint32_t n_new, n_flag;
+    if (threadIdx.x == 0) { n_new = 0; n_flag = 0; }
+    __syncthreads();
+    Tile t = tiles[blockIdx.x];
+    uint32_t mine = 0, mine_f = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        int xl = r * 256 + threadIdx.x;
+        uint32_t w = flagged[(size_t)blockIdx.x * kTileWords + (xl >> 5)];
+        if ((w >> (xl & 31)) & 1u) {
+            ++mine_f;
+            mine += opens_peak(flagged, blockIdx.x, t.j0, (long)t.j0 + xl);
+        }
+    }
+    if (mine) atomicAdd(&n_new, mine);
+    if (mine_f) atomicAdd(&n_flag, mine_f);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tile_new[blockIdx.x] = n_new;
+        if (n_flag) atomicAdd(flagged_total, (unsigned long long)n_flag);
+    }
+}
+
+// Peak ids follow (contig, position) order = tile order: id = tile_base + (#openers at or before me) - 1.
+// Every flagged position stamps its id on the k-mers it holds with count > 0; later ids win, i.e.
+// peak_kmer[h] = max id (E:246-270 executed in order).  Id 0 is the reference's "none" (Q10).
+template <int E>
+__global__ void __launch_bounds__(256) s2_register_kernel(const uint32_t* __restrict__ image, const Contig* __restrict__ contigs,
+                                                          const Tile* __restrict__ tiles, HashP hp,
+                                                          const uint32_t* __restrict__ count, const uint32_t* __restrict__ flagged,
+                                                          const uint32_t* __restrict__ tile_base, int32_t* __restrict__ loci,
+                                                          uint32_t* __restrict__ peak_kmer, uint32_t* __restrict__ prefilter,
+                                                          int mode) {
+    __shared__ uint32_t opener[kTileWords];
+    __shared__ int cum[kTileWords + 1];
+    const int e = E ? E : hp.e;
+    Tile t = tiles[blockIdx.x];
+    Contig c = contigs[t.contig];
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    bool fl[4], op[4];
+    bool any = false;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        int xl = r * 256 + threadIdx.x;
+        uint32_t w = flagged[(size_t)blockIdx.x * kTileWords + (xl >> 5)];
+        fl[r] = (w >> (xl & 31)) & 1u;
+        op[r] = fl[r] && opens_peak(flagged, blockIdx.x, t.j0, (long)t.j0 + xl);
+        uint32_t wo = __ballot_sync(kFull, op[r]);
+        if (lane == 0) opener[r * 8 + warp] = wo;
+        any |= fl[r];
+    }
+    if (!__syncthreads_or(any)) return;
+    prefix_words(opener, cum, kTileWords);
+    __syncthreads();
+    long np = (long)c.len - hp.k + 1;
+    uint32_t base = tile_base[blockIdx.x];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        if (!fl[r]) continue;
+        int xl = r * 256 + threadIdx.x;
+        long j = (long)t.j0 + xl;
+        uint32_t id = base + (uint32_t)bits_upto(opener, cum, xl) - 1u;   // wraps to 0xffffffff only if no opener yet: impossible for a flagged bit
+        if (op[r] && mode == 0) { loci[2 * (size_t)id] = (int32_t)t.contig + 1; loci[2 * (size_t)id + 1] = (int32_t)j; }
+        if (j < np && id != 0u) {                                         // j = len-k+1 reads the zero tail (Q6)
+            const uint32_t* hashes = image + c.hash_word + (size_t)j * e;
+            for (int i = 0; i < e; ++i) {
+                uint32_t h = hashes[i];
+                if (!h) continue;
+                uint32_t cnt = (count[h >> 4] >> ((h & 15u) * 2)) & 3u;
+                if (!cnt) continue;                                        // E:250,265: hit > 0
+                uint32_t slot = prefilter_slot(h);
+                if (mode == 0) {
+                    atomicMax(peak_kmer + h, id);
+                    atomicOr(prefilter + (slot >> 5), 1u << (slot & 31));
+                } else {
+                    peak_kmer[h] = 0u;
+                    prefilter[slot >> 5] = 0u;
+                }
+            }
+        }
+    }
+}
+
+int launch_s2_gather(const uint32_t* image, const Contig* contigs, const Tile* tiles, uint64_t tile_begin, uint64_t tile_end,
+                     const HashP& hp, const uint32_t* count, uint32_t* single, uint32_t* trio, cudaStream_t st) {
+    if (tile_end <= tile_begin) return 0;
+    unsigned grid = (unsigned)(tile_end - tile_begin);
+    switch (hp.e) {
+        case 1: s2_gather_kernel<1><<<grid, 256, 0, st>>>(image, contigs, tiles, tile_begin, hp, count, single, trio); break;
+        case 2: s2_gather_kernel<2><<<grid, 256, 0, st>>>(image, contigs, tiles, tile_begin, hp, count, single, trio); break;
+        case 3: s2_gather_kernel<3><<<grid, 256, 0, st>>>(image, contigs, tiles, tile_begin, hp, count, single, trio); break;
+        case 4: s2_gather_kernel<4><<<grid, 256, 0, st>>>(image, contigs, tiles, tile_begin, hp, count, single, trio); break;
+        default: s2_gather_kernel<0><<<grid, 256, 0, st>>>(image, contigs, tiles, tile_begin, hp, count, single, trio); break;
+    }
+    return 1;
+}
+
+int launch_s2_good(const Contig* contigs, const Tile* tiles, uint64_t ntiles, const uint32_t* single, const uint32_t* trio,
+                   int one_min, int three_min, uint32_t* good, cudaStream_t st) {
+    if (!ntiles) return 0;
+    s2_good_kernel<<<(unsigned)ntiles, 256, 0, st>>>(contigs, tiles, single, trio, one_min, three_min, good);
+    return 1;
+}
+
+int launch_s2_flag(const Contig* contigs, const Tile* tiles, uint64_t ntiles, int k, const uint32_t* single,
+                   const uint32_t* good, uint32_t* flagged, cudaStream_t st) {
+    if (!ntiles) return 0;
+    s2_flag_kernel<<<(unsigned)ntiles, 256, 0, st>>>(contigs, tiles, ntiles, k, single, good, flagged);
+    return 1;
+}
+
+int launch_s2_count_new(const Contig* contigs, const Tile* tiles, uint64_t ntiles, const uint32_t* flagged,
+                        uint32_t* tile_new, unsigned long long* flagged_total, cudaStream_t st) {
+    if (!ntiles) return 0;
+    s2_count_new_kernel<<<(unsigned)ntiles, 256, 0, st>>>(contigs, tiles, flagged, tile_new, flagged_total);
+    return 1;
+}
+
+int launch_s2_register(const uint32_t* image, const Contig* contigs, const Tile* tiles, uint64_t ntiles, const HashP& hp,
+                       const uint32_t* count, const uint32_t* flagged, const uint32_t* tile_base, int32_t* loci,
+                       uint32_t* peak_kmer, uint32_t* prefilter, int mode, cudaStream_t st) {
+    if (!ntiles) return 0;
+    s2_register_kernel<0><<<(unsigned)ntiles, 256, 0, st>>>(image, contigs, tiles, hp, count, flagged, tile_base, loci,
+                                                           peak_kmer, prefilter, mode);
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// S3: read-pair confirmation (E:419-499 + Split_reads E:109-202).  One warp per pair.  Lanes hash
+// positions in parallel and test an L2-resident pre-filter; only k-mers that pass it touch the
+// 2^k-entry peak table.  Positions that hold a peak k-mer are appended, in read order, to a per-warp
+// list; the order-dependent vote (judge_base) then runs on lane 0 over that (usually empty) list.
+// ------------------------------------------------------------------------------------------------
+constexpr int kS3Warps = 8;
+int s3_warps_per_block() { return kS3Warps; }
+int s3_grid_blocks(int) { return kSMs * 4; }
+
+template <int E>
+__device__ __forceinline__ int s3_scan_mate(const uint8_t* __restrict__ src, int len, uint32_t* planes, const HashP& hp,
+                                            const uint32_t* __restrict__ prefilter, const uint32_t* __restrict__ peak_kmer,
+                                            uint32_t* __restrict__ cands, int n_listed, int lane) {
+    const int e = E ? E : hp.e;
+    int np = len - hp.k + 1;
+    if (np <= 0) return n_listed;
+    warp_pack<kReadPlane>(src, len, planes, lane);
+    for (int j0 = 0; j0 < np; j0 += 32) {
+        int j = j0 + lane;
+        bool ok = j < np;
+        KmerWin kw = make_win<kReadPlane>(planes, ok ? j : 0, hp);
+        ok = ok && kw.valid;
+        uint32_t h[E ? E : kMaxE], pk[E ? E : kMaxE], fw[E ? E : kMaxE];
+#pragma unroll
+        for (int i = 0; i < (E ? E : kMaxE); ++i)
+            if (i < e) {
+                h[i] = hash_of(kw, hp, i);
+                uint32_t slot = prefilter_slot(h[i]);
+                fw[i] = ok ? __ldg(prefilter + (slot >> 5)) >> (slot & 31) : 0u;
+            }
+        bool any = false;
+#pragma unroll
+        for (int i = 0; i < (E ? E : kMaxE); ++i)
+            if (i < e) {
+                pk[i] = (fw[i] & 1u) ? __ldg(peak_kmer + h[i]) : 0u;
+                any |= pk[i] != 0u;
+            }
+        uint32_t mask = __ballot_sync(kFull, any);
+        if (mask) {
+            if (any) {
+                int slot = n_listed + __popc(mask & ((1u << lane) - 1u));
+#pragma unroll
+                for (int i = 0; i < (E ? E : kMaxE); ++i)
+                    if (i < e) cands[(size_t)slot * e + i] = pk[i];
+            }
+            n_listed += __popc(mask);
+        }
+    }
+    __syncwarp();
+    return n_listed;
+}
+
+// judge_base (E:118-159) + check_split (E:161-202) for one pair, run by a single lane.
+__device__ void s3_vote(const uint32_t* cands, int n_listed, int e, const int32_t* __restrict__ loci, int32_t* tally,
+                        uint8_t* __restrict__ peak_filter) {
+    int n_t = 0;    // tally[3*t] = contig, [3*t+1] = votes, [3*t+2] = first peak id
+    for (int f = 0; f < n_listed; ++f) {
+        uint32_t sel_peak = 0; int sel_contig = 0, sel_votes = 0, sel_t = -1;
+        for (int i = 0; i < e; ++i) {
+            uint32_t pk = cands[(size_t)f * e + i];
+            if (!pk) continue;
+            int contig = loci[2 * (size_t)pk];
+            int at = -1;
+            for (int t = 0; t < n_t; ++t) if (tally[3 * t] == contig) { at = t; break; }
+            if (at >= 0) {
+                if (tally[3 * at + 1] >= sel_votes) { sel_peak = pk; sel_contig = contig; sel_votes = tally[3 * at + 1]; sel_t = at; }
+            } else if (sel_peak == 0) { sel_peak = pk; sel_contig = contig; sel_votes = 0; sel_t = -1; }
+        }
+        if (sel_t >= 0) tally[3 * sel_t + 1] += 1;
+        else { tally[3 * n_t] = sel_contig; tally[3 * n_t + 1] = 1; tally[3 * n_t + 2] = (int32_t)sel_peak; ++n_t; }
+    }
+    int largest = 0, second = 0, strong = 0;
+    for (int t = 0; t < n_t; ++t) {
+        int n = tally[3 * t + 1];
+        if (n < 6) continue;
+        ++strong;
+        if (n >= largest) { second = largest; largest = n; }
+        else if (n >= second) second = n;
+    }
+    if (strong < 2) return;
+    for (int t = 0; t < n_t; ++t) {
+        int n = tally[3 * t + 1];
+        if (n >= 6 && (n == largest || n == second)) peak_filter[(uint32_t)tally[3 * t + 2]] = 1;   // only >= 1 is consumed (E:526)
+    }
+}
+
+template <int E>
+__global__ void __launch_bounds__(kS3Warps * 32, 4) s3_pairs_kernel(
+    const uint8_t* __restrict__ fq1, const uint64_t* __restrict__ s1, const uint64_t* __restrict__ e1, uint64_t nrec1,
+    const uint8_t* __restrict__ fq2, const uint64_t* __restrict__ s2, const uint64_t* __restrict__ e2, uint64_t nrec2,
+    uint64_t tail_start, uint64_t tail_len, uint64_t first, uint64_t count, const uint32_t* __restrict__ sample_bits,
+    HashP hp, const uint32_t* __restrict__ prefilter, const uint32_t* __restrict__ peak_kmer,
+    const int32_t* __restrict__ loci, uint8_t* __restrict__ peak_filter, S3Scratch scratch,
+    unsigned long long* __restrict__ n_sampled, int* __restrict__ err) {
+    __shared__ uint32_t planes_all[kS3Warps][4 * kReadPlane];
+    const int e = E ? E : hp.e;
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* planes = planes_all[warp];
+    uint64_t gwarp = (uint64_t)blockIdx.x * kS3Warps + warp;
+    uint32_t* cands = scratch.cands + gwarp * scratch.cands_stride;
+    int32_t* tally = scratch.tally + gwarp * scratch.tally_stride;
+    unsigned long long mine = 0;
+    uint64_t stride = (uint64_t)gridDim.x * kS3Warps;
+    uint64_t last = first + count < nrec1 ? first + count : nrec1;
+    for (uint64_t r = first + gwarp; r < last; r += stride) {
+        if (!is_sampled(sample_bits, r)) continue;
+        uint64_t a0 = s1[r], l1 = e1[r] - a0, b0, l2;
+        if (r < nrec2) { b0 = s2[r]; l2 = e2[r] - b0; }
+        else { b0 = tail_start; l2 = tail_len; }            // fq2 exhausted: std::getline leaves its last string
+        if (l1 > (uint64_t)kMaxReadLen || l2 > (uint64_t)kMaxReadLen) { if (lane == 0) atomicExch(err, 1); continue; }
+        ++mine;
+        int n_listed = s3_scan_mate<E>(fq1 + a0, (int)l1, planes, hp, prefilter, peak_kmer, cands, 0, lane);
+        n_listed = s3_scan_mate<E>(fq2 + b0, (int)l2, planes, hp, prefilter, peak_kmer, cands, n_listed, lane);
+        if (n_listed >= 6) {                                 // base_hits >= MIN_BASE_NUM (E:496)
+            __syncwarp();
+            if (lane == 0) s3_vote(cands, n_listed, e, loci, tally, peak_filter);
+            __syncwarp();
+        }
+    }
+    if (lane == 0 && mine) atomicAdd(n_sampled, mine);
+}
+
+int launch_s3(const uint8_t* fq1, const uint64_t* s1, const uint64_t* e1, uint64_t nrec1, const uint8_t* fq2,
+              const uint64_t* s2, const uint64_t* e2, uint64_t nrec2, uint64_t tail_start, uint64_t tail_len,
+              uint64_t first, uint64_t count, const uint32_t* sample_bits, const HashP& hp, const uint32_t* prefilter,
+              const uint32_t* peak_kmer, const int32_t* loci, uint8_t* peak_filter, S3Scratch scratch, int grid_blocks,
+              unsigned long long* n_sampled, int* err, cudaStream_t st) {
+    if (count == 0 || nrec1 == 0) return 0;
+#define LHGT_S3(EE)                                                                                                   \
+    s3_pairs_kernel<EE><<<grid_blocks, kS3Warps * 32, 0, st>>>(fq1, s1, e1, nrec1, fq2, s2, e2, nrec2, tail_start,    \
+                                                               tail_len, first, count, sample_bits, hp, prefilter,   \
+                                                               peak_kmer, loci, peak_filter, scratch, n_sampled, err)
+    switch (hp.e) {
+        case 1: LHGT_S3(1); break;
+        case 2: LHGT_S3(2); break;
+        case 3: LHGT_S3(3); break;
+        case 4: LHGT_S3(4); break;
+        default: LHGT_S3(0); break;
+    }
+#undef LHGT_S3
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// table utilities
+// ------------------------------------------------------------------------------------------------
+__global__ void count_unpack_kernel(const uint32_t* __restrict__ count, uint64_t entries, uint8_t* __restrict__ out) {
+    for (uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h < entries; h += (uint64_t)gridDim.x * blockDim.x)
+        out[h] = (count[h >> 4] >> ((h & 15u) * 2)) & 3u;
+}
+
+int launch_count_unpack(const uint32_t* count, uint64_t entries, uint8_t* out, cudaStream_t st) {
+    count_unpack_kernel<<<kSMs * 8, 256, 0, st>>>(count, entries, out);
+    return 1;
+}
+
+// field-wise min(3, a + b) on sixteen 2-bit counters per word
+__device__ __forceinline__ uint32_t sat_add2(uint32_t a, uint32_t b) {
+    const uint32_t lo = 0x55555555u;
+    uint32_t a0 = a & lo, a1 = (a >> 1) & lo, b0 = b & lo, b1 = (b >> 1) & lo;
+    uint32_t s0 = a0 ^ b0, c0 = a0 & b0;           // bit 0 of the sum, carry into bit 1
+    uint32_t s1 = a1 ^ b1 ^ c0;
+    uint32_t over = (a1 & b1) | (c0 & (a1 ^ b1));  // sum >= 4
+    return ((s0 | over) & lo) | (((s1 | over) & lo) << 1);
+}
+
+__global__ void count_merge_kernel(uint32_t* __restrict__ count, const uint32_t* __restrict__ other, uint64_t words) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (uint64_t)gridDim.x * blockDim.x)
+        count[i] = sat_add2(count[i], other[i]);
+}
+
+int launch_count_merge(uint32_t* count, const uint32_t* other, uint64_t words, cudaStream_t st) {
+    count_merge_kernel<<<kSMs * 8, 256, 0, st>>>(count, other, words);
+    return 1;
+}
+
+}  // namespace lhgt

@@ -1,0 +1,91 @@
+// Internal interface between the host side (lhgt_api.cu) and the sm_100a kernels (lhgt_kernels.cu).
+// Nothing here is part of the C ABI (include/lhgt.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lhgt {
+
+constexpr int kMaxE = 10;
+constexpr int kMaxReadLen = 500;
+constexpr int kTile = 1024;            // reference positions per S2 / IB tile
+constexpr int kTileWords = kTile / 32;
+constexpr int kRandomArray = 50000000; // E:40
+constexpr int kFilterLog2 = 28;        // S3 pre-filter: 2^28 bits = 32 MiB, L2-resident on B200
+
+// Everything a kernel needs to hash: F_i = W2 ^ ((W0^W2)&m0[i]) ^ ((W1^W2)&m1[i]) and the mirrored
+// form for the reverse complement.  m2 is implied (the three masks partition kmask).
+struct HashP {
+    int k, e;
+    int shr;                           // 32 - k
+    uint32_t kmask;
+    uint32_t m0[kMaxE], m1[kMaxE];
+};
+
+struct Tile { uint32_t contig; uint32_t j0; };
+
+// Per indexed contig.
+struct Contig {
+    uint64_t hash_word;                // word offset of its first hash in the index image
+    uint64_t seq_off;                  // byte offset in the compacted sequence buffer (IB only)
+    uint32_t len;
+    uint32_t tile0;                    // first tile
+};
+
+struct S3Scratch {                     // per resident warp
+    uint32_t* cands;                   // [2*(kMaxReadLen)] * e
+    int32_t* tally;                    // [3 * 2*kMaxReadLen]
+    size_t cands_stride, tally_stride; // elements per warp
+};
+
+// ---- launchers (all asynchronous on `st`; return the number of kernels launched) ----
+int launch_fastq_index(const uint8_t* fq, uint64_t n, uint32_t* tile_cnt, uint32_t* tile_base,
+                       uint32_t* scan_tmp, uint64_t* rec_start, uint64_t* rec_end, uint64_t rec_cap,
+                       int phase, cudaStream_t st);
+uint64_t fastq_index_tiles(uint64_t n);
+size_t scan_tmp_words(uint64_t n);
+int launch_scan_exclusive(const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* tmp, cudaStream_t st);
+int launch_sum_lengths(const uint64_t* rec_start, const uint64_t* rec_end, uint64_t nrec,
+                       unsigned long long* out, cudaStream_t st);
+
+int launch_index_build(const uint8_t* seq, const Contig* contigs, const Tile* tiles, uint64_t ntiles,
+                       const HashP& hp, uint32_t* image, uint8_t* valid_out, cudaStream_t st);
+
+int launch_s1(const uint8_t* fq, const uint64_t* rec_start, const uint64_t* rec_end, uint64_t nrec,
+              uint64_t budget, const uint32_t* sample_bits, const HashP& hp, uint32_t* count,
+              unsigned long long* n_sampled, int* err, cudaStream_t st);
+
+int launch_s2_gather(const uint32_t* image, const Contig* contigs, const Tile* tiles, uint64_t tile_begin,
+                     uint64_t tile_end, const HashP& hp, const uint32_t* count, uint32_t* single,
+                     uint32_t* trio, cudaStream_t st);
+int launch_s2_good(const Contig* contigs, const Tile* tiles, uint64_t ntiles, const uint32_t* single,
+                   const uint32_t* trio, int one_min, int three_min, uint32_t* good, cudaStream_t st);
+int launch_s2_flag(const Contig* contigs, const Tile* tiles, uint64_t ntiles, int k, const uint32_t* single,
+                   const uint32_t* good, uint32_t* flagged, cudaStream_t st);
+int launch_s2_count_new(const Contig* contigs, const Tile* tiles, uint64_t ntiles, const uint32_t* flagged,
+                        uint32_t* tile_new, unsigned long long* flagged_total, cudaStream_t st);
+// mode 0: write loci + scatter-max peak ids + pre-filter bits; mode 1: clear what mode 0 wrote
+int launch_s2_register(const uint32_t* image, const Contig* contigs, const Tile* tiles, uint64_t ntiles,
+                       const HashP& hp, const uint32_t* count, const uint32_t* flagged,
+                       const uint32_t* tile_base, int32_t* loci, uint32_t* peak_kmer, uint32_t* prefilter,
+                       int mode, cudaStream_t st);
+
+int launch_s3(const uint8_t* fq1, const uint64_t* s1, const uint64_t* e1, uint64_t nrec1,
+              const uint8_t* fq2, const uint64_t* s2, const uint64_t* e2, uint64_t nrec2,
+              uint64_t mate2_tail_start, uint64_t mate2_tail_len,
+              uint64_t first, uint64_t count, const uint32_t* sample_bits, const HashP& hp,
+              const uint32_t* prefilter, const uint32_t* peak_kmer, const int32_t* loci,
+              uint8_t* peak_filter, S3Scratch scratch, int grid_blocks, unsigned long long* n_sampled,
+              int* err, cudaStream_t st);
+int s3_grid_blocks(int device);
+int s3_warps_per_block();
+
+int launch_count_unpack(const uint32_t* count, uint64_t entries, uint8_t* out, cudaStream_t st);
+int launch_count_merge(uint32_t* count, const uint32_t* other, uint64_t words, cudaStream_t st);
+
+__host__ __device__ inline uint32_t prefilter_slot(uint32_t h) {
+    // any function of h is exact here (the filter only gates the exact lookup); fold the high bits in
+    return (h ^ (h >> kFilterLog2)) & ((1u << kFilterLog2) - 1u);
+}
+
+}  // namespace lhgt

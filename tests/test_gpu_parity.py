@@ -1,0 +1,325 @@
+"""GPU: the CUDA path, called through the C ABI (ctypes), against
+  (1) the oracle port stage by stage on the same inputs,
+  (2) the committed outputs of the unmodified reference binary (tests/golden/MANIFEST.json),
+  (3) size-independent properties on a workload the oracle could not finish in seconds.
+Bit-exact everywhere: this path is integer/byte work.
+"""
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import fixtures
+import model_np
+from localhgt_b200 import api, build as lhgt_build, synth
+from oracle import orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _read(path):
+    with open(path, "rb") as f:
+        return f.read()
+
+
+# ------------------------------------------------------------------ hashing
+@pytest.mark.parametrize("k,e,seed", [(32, 3, 1), (24, 3, 1), (20, 3, 2), (31, 1, 7), (24, 4, 5), (27, 5, 11), (13, 7, 3), (30, 10, 9), (2, 1, 1)])
+def test_hash_seq_matches_oracle(k, e, seed):
+    rng = np.random.default_rng(seed)
+    alphabet = np.frombuffer(b"ACGTacgtNnRY\r-", dtype=np.uint8)
+    seq = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, 5000)].copy()
+    noise = rng.integers(0, 5000, 40)
+    seq[noise] = alphabet[rng.integers(0, len(alphabet), 40)]
+    seq[3000:3100] |= 0x20                                   # lower-case stretch is valid
+    seq[1020:1030] = ord("N")                                # straddles the 1024-position tile boundary
+    o = orc.Oracle(k, e); o.srand(seed); cc = o.random_coder()
+    cc2, draws = api.random_coder(seed, k, e)
+    assert np.array_equal(cc, cc2) and draws == k * (e // 3 + 1)
+    with api.Screen(k, e) as s:
+        s.set_coder(cc)
+        for piece in (seq.tobytes(), seq[:k].tobytes(), seq[: k - 1].tobytes(), seq[:1025].tobytes(), seq[7:2055].tobytes()):
+            h0, v0 = o.hash_seq(piece)
+            h1, v1 = s.hash_seq(piece)
+            assert np.array_equal(v0, v1)
+            assert np.array_equal(h0, h1)
+    # and the numpy statement of the closed form agrees too
+    h2, v2 = model_np.hash_seq(seq[:600], k, e, cc)
+    h0, v0 = o.hash_seq(seq[:600].tobytes())
+    assert np.array_equal(h0, h2) and np.array_equal(v0, v2)
+
+
+# ------------------------------------------------------------------ stage by stage
+def _stage_run(case, work):
+    """Runs port and GPU side by side with identical decisions; returns both states."""
+    fa, fq1, fq2 = fixtures.materialize(case.data, work)
+    k, e = case.k, case.e
+    o = orc.Oracle(k, e)
+    s = api.Screen(k, e)
+    skip = 0
+    o.srand(case.seed)
+    if not case.prebuilt_index:
+        cc = o.random_coder()
+        cc2, skip = api.random_coder(case.seed, k, e)
+        assert np.array_equal(cc, cc2)
+    else:                                     # coder comes from an index built earlier with the same seed
+        tmp = orc.Oracle(k, e); tmp.srand(case.seed); cc = tmp.random_coder(); o.set_coder(cc)
+    s.set_coder(cc)
+    idx = os.path.join(work, case.name + ".stage.index.dat")
+    lenp = os.path.join(work, case.name + ".stage.len.txt")
+    assert o.index_build(fa, idx, lenp) == 0
+    s.index_build(_read(fa))
+    return fa, fq1, fq2, o, s, idx, lenp, skip
+
+
+@pytest.mark.parametrize("case", [c for c in fixtures.CASES if c.k <= 27], ids=lambda c: c.name)
+def test_stages_match_oracle(case, manifest, workdir):
+    gold = manifest[case.name]
+    fa, fq1, fq2, o, s, idx, lenp, skip = _stage_run(case, workdir)
+    with s:
+        # IB: bit-exact index image and genome.len.txt
+        image = s.index_download()
+        assert image.tobytes() == _read(idx)
+        assert s.index_len_text() == _read(lenp)
+        assert s.index_len_text().decode() == gold["len_text"]
+        # reads
+        b1, b2 = _read(fq1), _read(fq2)
+        s.reads_upload(0, b1); s.reads_upload(1, b2)
+        ratio_o = orc.sample_ratio(fq1, case.sample)
+        ratio_g = s.sample_ratio(case.sample)
+        assert ratio_o == ratio_g
+        if ratio_o < 100:
+            o.fill_random(max(s.reads_records(0), s.reads_records(1)) + 8)
+        s.set_sampling(ratio_g, case.seed, skip)
+        # S1
+        n1o, n2o = o.s1_count(fq1, len(b1), ratio_o), o.s1_count(fq2, len(b1), ratio_o)
+        n1g, n2g = s.s1_count(0, len(b1)), s.s1_count(1, len(b1))
+        assert (n1o, n2o) == (n1g, n2g)
+        assert np.array_equal(o.count_table(), s.count_table())
+        # S2
+        npo = o.s2_peaks(idx, case.hit, case.match, case.max_peak)
+        npg = s.s2_peaks(case.hit, case.match, case.max_peak)
+        assert npo == npg == gold["ref_raw_peaks"]
+        assert o.raw_positions() == s.flagged_positions()
+        loci_g, _ = s.peaks()
+        assert np.array_equal(o.peak_loci(), loci_g)
+        assert np.array_equal(o.peak_kmer(), s.peak_kmer())
+        # S3
+        so, sg = o.s3_pairs(fq1, fq2, ratio_o), s.s3_pairs()
+        assert so == sg == gold["ref_pairs_s3"]
+        _, filt_g = s.peaks()
+        assert np.array_equal(o.peak_filter() >= 1, filt_g >= 1)
+        # OUT
+        assert s.intervals().decode() == gold["interval_text"]
+        # a second sample through the same context after reset gives the same answer
+        s.reset()
+        s.set_sampling(ratio_g, case.seed, skip)
+        s.s1_count(0, len(b1)); s.s1_count(1, len(b1))
+        assert s.s2_peaks(case.hit, case.match, case.max_peak) == npg
+        s.s3_pairs()
+        assert s.intervals().decode() == gold["interval_text"]
+    o.close()
+
+
+# ------------------------------------------------------------------ the whole program, file level
+@pytest.mark.parametrize("case", fixtures.CASES, ids=lambda c: c.name)
+def test_extract_ref_matches_reference_binary(case, manifest, workdir):
+    gold = manifest[case.name]
+    fa, fq1, fq2 = fixtures.materialize(case.data, workdir)
+    fixtures.clean_outputs(fa)
+    out = os.path.join(workdir, case.name + ".gpu.interval.txt")
+    kw = dict(hit_ratio=case.hit, match_ratio=case.match, k=case.k, e=case.e, seed=case.seed, sample=case.sample,
+              max_peak=case.max_peak)
+    try:
+        if case.prebuilt_index:
+            api.extract_ref(fq1, fq2, fa, out + ".first", **kw)
+        st = api.extract_ref(fq1, fq2, fa, out, **kw)
+        idx = fixtures.index_path(fa, case.k, case.e)
+        assert os.path.getsize(idx) == gold["index_bytes"]
+        assert fixtures.sha256(idx) == gold["index_sha256"]
+        assert _read(fa + ".genome.len.txt").decode() == gold["len_text"]
+        assert _read(out).decode() == gold["interval_text"]
+        assert (st.reads_s1[0] + st.reads_s1[1]) // 2 == gold["ref_pairs_s1"]
+        assert st.pairs_s3 == gold["ref_pairs_s3"]
+        assert st.peaks == gold["ref_raw_peaks"]
+        assert bool(st.index_built) == (not case.prebuilt_index)
+    finally:
+        fixtures.clean_outputs(fa)
+
+
+def test_cli_binary_is_a_drop_in(manifest, workdir):
+    """The `extract_ref` executable with the 12 positional arguments of scripts/pipeline.sh:35."""
+    case = fixtures.BY_NAME["noisy"]
+    gold = manifest[case.name]
+    fa, fq1, fq2 = fixtures.materialize(case.data, workdir)
+    fixtures.clean_outputs(fa)
+    out = os.path.join(workdir, "cli.interval.txt")
+    exe = lhgt_build.EXE
+    assert os.path.exists(exe)
+    # Python's f-string spelling of the numbers, as infer_HGT_breakpoint.py:29 passes them
+    argv = [exe, fq1, fq2, fa, out, f"{case.hit}", f"{case.match}", "10", f"{case.k}", f"{float(case.max_peak)}",
+            f"{case.e}", f"{case.seed}", f"{case.sample}"]
+    try:
+        r = subprocess.run(argv, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr
+        assert _read(out).decode() == gold["interval_text"]
+        assert fixtures.sha256(fixtures.index_path(fa, case.k, case.e)) == gold["index_sha256"]
+        # second run reuses the index file (E:1403-1413) and, at ratio<100, samples differently (Q3)
+        r2 = subprocess.run(argv, capture_output=True, text=True, timeout=600)
+        assert r2.returncode == 0 and "Reference index is detected." in r2.stdout
+    finally:
+        fixtures.clean_outputs(fa)
+    bad = subprocess.run([exe, "a", "b"], capture_output=True, text=True)
+    assert bad.returncode != 0 and "usage" in bad.stderr
+
+
+# ------------------------------------------------------------------ error behaviour
+def test_errors_are_loud(workdir):
+    with pytest.raises(api.LhgtError):
+        api.Screen(33, 3)
+    with pytest.raises(api.LhgtError):
+        api.Screen(32, 11)
+    with api.Screen(16, 3) as s:
+        with pytest.raises(api.LhgtError):
+            s.s1_count(0, 10)                                   # nothing uploaded
+        with pytest.raises(api.LhgtError):
+            s.index_upload(b"\0" * 100)                        # shorter than the header
+        long_read = b"@r\n" + b"A" * 600 + b"\n+\n" + b"I" * 600 + b"\n"
+        s.reads_upload(0, long_read); s.reads_upload(1, long_read)
+        s.set_sampling(100.0)
+        with pytest.raises(api.LhgtError) as ei:
+            s.s1_count(0, len(long_read))
+        assert ei.value.code == -6
+    with pytest.raises(api.LhgtError):
+        api.extract_ref("/nonexistent.1.fq", "/nonexistent.2.fq", "/nonexistent.fa", os.path.join(workdir, "x.txt"), k=16)
+
+
+def test_empty_and_degenerate_inputs(workdir):
+    fa = os.path.join(workdir, "tiny.fa")
+    with open(fa, "wb") as f:
+        f.write(b">only_short\nACGTACGT\n>also_short\nAC\n")          # no contig longer than k
+    fq = os.path.join(workdir, "empty.fq")
+    open(fq, "wb").close()
+    out = os.path.join(workdir, "tiny.interval.txt")
+    fixtures.clean_outputs(fa)
+    try:
+        st = api.extract_ref(fq, fq, fa, out, k=16, e=3)
+        assert _read(out) == b"1\t1\t1\n"                                # Q9: the initial state is always printed
+        assert st.peaks == 0 and st.pairs_s3 == 0
+        assert os.path.getsize(fixtures.index_path(fa, 16, 3)) == 1200
+        assert _read(fa + ".genome.len.txt") == b""
+        # the oracle port says the same
+        fixtures.clean_outputs(fa)
+        rc, _ = orc.extract_ref(fq, fq, fa, out + ".port", k=16, e=3)
+        assert rc == 0 and _read(out + ".port") == b"1\t1\t1\n"
+    finally:
+        fixtures.clean_outputs(fa)
+
+
+# ------------------------------------------------------------------ properties at a size the oracle cannot do in seconds
+@pytest.fixture(scope="module")
+def big(tmp_path_factory):
+    d = str(tmp_path_factory.mktemp("big"))
+    w = synth.make_workload(d, "big", seed=9, n_genomes=20, genome_len=400000, n_pairs=400000, n_events=8,
+                            ref_n_rate=0.0001, short_contigs=(20, 31))
+    return w
+
+
+def test_large_run_properties(big):
+    k, e = 32, 3
+    fa, b1, b2 = _read(big.ref_fa), _read(big.fq1), _read(big.fq2)
+    cc, _ = api.random_coder(1, k, e)
+    with api.Screen(k, e) as s:
+        s.set_coder(cc)
+        s.index_build(fa)
+        image = s.index_download()
+        # index: header round trip and record structure
+        assert np.array_equal(api.header_to_coder(image[:1200].view(np.uint32)), cc)
+        assert s.index_bytes() == 1200 + 4 * sum(1 + (len(q) - k + 1) * e for q in _contigs(fa) if len(q) > k)
+        # spot-check 200 random positions of the image against the scalar oracle
+        o = orc.Oracle(k, e); o.set_coder(cc)
+        words = image.view(np.uint32)
+        rng = np.random.default_rng(3)
+        at = 300
+        for q in _contigs(fa):
+            if len(q) <= k:
+                continue
+            assert words[at] == len(q)
+            for j in rng.integers(0, len(q) - k + 1, 10):
+                h, _ = o.hash_seq(q[j:j + k])
+                assert np.array_equal(words[at + 1 + j * e: at + 1 + (j + 1) * e], h[0])
+            at += 1 + (len(q) - k + 1) * e
+        s.reads_upload(0, b1); s.reads_upload(1, b2)
+        assert s.reads_records(0) == s.reads_records(1) == big.n_pairs
+        assert s.reads_seq_bases(0) == big.n_pairs * 150
+        s.set_sampling(100.0)
+        assert s.s1_count(0, len(b1)) == big.n_pairs
+        assert s.s1_count(1, len(b1)) == big.n_pairs
+        n_peaks = s.s2_peaks()
+        s.s3_pairs()
+        text = s.intervals()
+        loci, filt = s.peaks()
+        # peaks are strictly ordered by (contig, position) and one per 50-bp bucket (E:288-301)
+        key = loci[:, 0].astype(np.int64) * (1 << 32) + loci[:, 1]
+        assert np.all(np.diff(key) > 0)
+        bucket = loci[:, 0].astype(np.int64) * (1 << 32) + loci[:, 1] // 50
+        assert len(np.unique(bucket)) == n_peaks
+        # every planted junction on a recipient lies strictly inside an emitted interval (evaluation.py:64-76)
+        ivs = [tuple(map(int, ln.split("\t"))) for ln in text.decode().splitlines()]
+        names = [ln[1:].split()[0] for ln in fa.decode().splitlines() if ln.startswith(">")]
+        long_names = [n for n, q in zip(names, _contigs(fa)) if len(q) > k]
+        found = 0
+        for ev in big.truth:
+            ordinal = long_names.index(names[ev.recipient]) + 1
+            found += any(c == ordinal and a + 50 < ev.r_pos < b - 50 for c, a, b in ivs)
+        assert found >= 0.75 * len(big.truth), (found, len(big.truth))
+        # idempotence: the same sample again after reset -> identical text; uploading the image instead of building -> identical
+        s.reset()
+        s.index_upload(image)
+        s.set_sampling(100.0)
+        s.s1_count(0, len(b1)); s.s1_count(1, len(b1))
+        assert s.s2_peaks() == n_peaks
+        s.s3_pairs()
+        assert s.intervals() == text
+        # counting is commutative and saturating: mates in the other order give the same table checksum
+        tab = s.count_table()
+        s.reset(); s.set_sampling(100.0)
+        s.s1_count(1, len(b1)); s.s1_count(0, len(b1))
+        assert np.array_equal(np.bincount(tab, minlength=4), np.bincount(s.count_table(), minlength=4))
+
+
+def _contigs(fa: bytes):
+    out, cur = [], []
+    for ln in fa.split(b"\n"):
+        if ln.startswith(b">"):
+            out.append(b"".join(cur))         # first append is the (empty) text before the first header
+            cur = []
+        else:
+            cur.append(ln)
+    out.append(b"".join(cur))
+    return out[1:]
+
+
+@pytest.mark.slow
+def test_large_run_matches_reference_binary_on_this_box(big, tmp_path):
+    """k=32 end to end against the real reference executable (needs ~21 GB host RAM, ~2-3 min)."""
+    if not os.path.exists(orc.REF_BIN_Z):
+        pytest.skip("oracle/_ref/extract_ref_z not present")
+    n = 40000
+    lines = 4 * n
+    def head(src, dst):
+        with open(src, "rb") as f, open(dst, "wb") as g:
+            for _ in range(lines):
+                g.write(f.readline())
+    d = str(tmp_path)
+    fq1, fq2 = os.path.join(d, "h.1.fq"), os.path.join(d, "h.2.fq")
+    head(big.fq1, fq1); head(big.fq2, fq2)
+    fa_r, fa_g = os.path.join(d, "r", "ref.fa"), os.path.join(d, "g", "ref.fa")
+    os.makedirs(os.path.dirname(fa_r)); os.makedirs(os.path.dirname(fa_g))
+    shutil.copy(big.ref_fa, fa_r); shutil.copy(big.ref_fa, fa_g)
+    orc.run_reference(fq1, fq2, fa_r, os.path.join(d, "r.txt"), k=32, e=3, seed=1, sample=0.9, max_peak=2000000, timeout=1500)
+    api.extract_ref(fq1, fq2, fa_g, os.path.join(d, "g.txt"), k=32, e=3, seed=1, sample=0.9, max_peak=2000000)
+    assert fixtures.sha256(fa_r + ".k32.h3.index.dat") == fixtures.sha256(fa_g + ".k32.h3.index.dat")
+    assert _read(fa_r + ".genome.len.txt") == _read(fa_g + ".genome.len.txt")
+    assert _read(os.path.join(d, "r.txt")) == _read(os.path.join(d, "g.txt"))
