@@ -107,6 +107,7 @@ int      lhgt_reads_upload(lhgt_ctx* c, int mate, const uint8_t* fq, uint64_t n)
 int      lhgt_reads_attach_device(lhgt_ctx* c, int mate, const void* dev_fq, uint64_t n);
 long     lhgt_reads_records(const lhgt_ctx* c, int mate);
 uint64_t lhgt_reads_seq_bases(const lhgt_ctx* c, int mate);   /* sum of sequence-line lengths */
+uint64_t lhgt_reads_bytes(const lhgt_ctx* c, int mate);       /* size of the resident FASTQ image */
 
 /* down_sam_ratio in percent (E:1392-1398, cal_sam_ratio E:1244-1270); needs fq1 uploaded when
  * sample_arg > 1. */
@@ -114,6 +115,10 @@ double lhgt_sample_ratio(lhgt_ctx* c, double sample_arg);
 /* Fixes the sampling rule `random_array[ordinal % 50M] < ratio` (E:1037-1044, 413-419) where
  * random_array is drawn from srand(seed) after rand_skip earlier draws (get_random, E:1332-1340). */
 int    lhgt_set_sampling(lhgt_ctx* c, double ratio_percent, unsigned seed, long rand_skip);
+/* Multi-GPU: this context holds records [base, base+n) of the whole sample, so the sampling ordinal
+ * of its record r is base + r (the reference's `lines/4`, E:1037-1044 / E:413-419, counted over the
+ * whole file).  Call before lhgt_set_sampling.  Default 0. */
+int    lhgt_set_ordinal_base(lhgt_ctx* c, uint64_t base);
 
 /* ------------------------------------------------------------------ stages */
 
@@ -153,8 +158,9 @@ void*    lhgt_dev_peak_filter(lhgt_ctx* c, uint64_t* bytes);
 /* count := min(3, count + other) field-wise on packed tables (other: device pointer, same size). */
 int      lhgt_count_merge(lhgt_ctx* c, const void* dev_other, uint64_t bytes, uint64_t word_offset);
 
-/* Device time of the last call of each stage, measured with CUDA events on the context's stream:
- * [0] reads index (newline scan)  [1] S1  [2] S2 gather  [3] S2 finish  [4] S3  [5] IB kernel. */
+/* Device time spent in each stage since the previous lhgt_stage_ms call (read-and-clear), measured
+ * with CUDA events on the context's stream:
+ * [0] FASTQ record scan  [1] S1  [2] S2 gather  [3] S2 finish  [4] S3  [5] IB kernel. */
 int  lhgt_stage_ms(const lhgt_ctx* c, float* ms6);
 /* Kernels launched by this context since creation. */
 long lhgt_launch_count(const lhgt_ctx* c);

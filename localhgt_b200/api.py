@@ -68,8 +68,10 @@ SYMBOLS = {
     "lhgt_reads_attach_device": (_i, [_vp, _i, _vp, _u64]),
     "lhgt_reads_records": (_l, [_vp, _i]),
     "lhgt_reads_seq_bases": (_u64, [_vp, _i]),
+    "lhgt_reads_bytes": (_u64, [_vp, _i]),
     "lhgt_sample_ratio": (_d, [_vp, _d]),
     "lhgt_set_sampling": (_i, [_vp, _d, _u, _l]),
+    "lhgt_set_ordinal_base": (_i, [_vp, _u64]),
     "lhgt_s1_count": (_l, [_vp, _i, _u64]),
     "lhgt_s2_peaks": (_l, [_vp, _f, _f, _l]),
     "lhgt_s3_pairs": (_l, [_vp, _l, _l]),
@@ -228,6 +230,9 @@ class Screen:
         buf = np.frombuffer(image, dtype=np.uint8)
         _check(self._L.lhgt_index_upload(self._h, _ptr(buf), len(buf)))
 
+    def index_upload_ptr(self, host_ptr: int, n: int) -> None:
+        _check(self._L.lhgt_index_upload(self._h, host_ptr, n))
+
     def index_build_file(self, fasta: str, index_path: str, len_path: str) -> None:
         _check(self._L.lhgt_index_build_file(self._h, fasta.encode(), index_path.encode(), len_path.encode()))
 
@@ -248,6 +253,7 @@ class Screen:
 
     def reads_records(self, mate: int) -> int: return int(self._L.lhgt_reads_records(self._h, mate))
     def reads_seq_bases(self, mate: int) -> int: return int(self._L.lhgt_reads_seq_bases(self._h, mate))
+    def reads_bytes(self, mate: int) -> int: return int(self._L.lhgt_reads_bytes(self._h, mate))
 
     def sample_ratio(self, sample_arg: float) -> float:
         r = self._L.lhgt_sample_ratio(self._h, sample_arg)
@@ -257,6 +263,9 @@ class Screen:
 
     def set_sampling(self, ratio_percent: float, seed: int = 1, rand_skip: int = 0) -> None:
         _check(self._L.lhgt_set_sampling(self._h, ratio_percent, seed, rand_skip))
+
+    def set_ordinal_base(self, base: int) -> None:
+        _check(self._L.lhgt_set_ordinal_base(self._h, base))
 
     # ---- stages
     def s1_count(self, mate: int, byte_budget: int) -> int:

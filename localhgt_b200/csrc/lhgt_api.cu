@@ -110,6 +110,7 @@ struct lhgt_ctx {
     Reads reads[2];
 
     uint32_t* d_sample_bits = nullptr; bool sampling_set = false; double ratio = 100.0;
+    uint64_t ordinal_base = 0;               // records that precede this context's shard in the whole sample
 
     uint32_t* d_cands = nullptr; int32_t* d_tally = nullptr; S3Scratch scratch{};
 
@@ -144,7 +145,14 @@ struct Span {
         if (cudaEventCreate(&a) == cudaSuccess && cudaEventCreate(&b) == cudaSuccess) cudaEventRecord(a, c->st);
     }
     ~Span() {
-        if (a && b) { cudaEventRecord(b, c->st); c->spans.push_back({stage, a, b}); }
+        if (a && b) {
+            cudaEventRecord(b, c->st);
+            if (c->spans.size() >= 4096) {                          // nobody is reading them: keep the newest
+                cudaEventDestroy(c->spans.front().a); cudaEventDestroy(c->spans.front().b);
+                c->spans.erase(c->spans.begin());
+            }
+            c->spans.push_back({stage, a, b});
+        }
     }
 };
 
@@ -707,6 +715,7 @@ extern "C" int lhgt_reads_attach_device(lhgt_ctx* c, int mate, const void* dev_f
 }
 
 extern "C" long lhgt_reads_records(const lhgt_ctx* c, int mate) { return c && mate >= 0 && mate <= 1 ? (long)c->reads[mate].nrec : 0; }
+extern "C" uint64_t lhgt_reads_bytes(const lhgt_ctx* c, int mate) { return c && mate >= 0 && mate <= 1 ? c->reads[mate].n : 0; }
 extern "C" uint64_t lhgt_reads_seq_bases(const lhgt_ctx* c, int mate) { return c && mate >= 0 && mate <= 1 ? c->reads[mate].seq_bases : 0; }
 
 extern "C" double lhgt_sample_ratio(lhgt_ctx* c, double sample_arg) {
@@ -723,7 +732,7 @@ extern "C" int lhgt_set_sampling(lhgt_ctx* c, double ratio, unsigned seed, long 
     c->sampling_set = true;
     dev_free(c->d_sample_bits);
     if (ratio >= 100) return 0;                                    // every drawn value is <= 99.999 (E:1336)
-    uint64_t need = std::max(c->reads[0].nrec, c->reads[1].nrec);
+    uint64_t need = std::max(c->reads[0].nrec, c->reads[1].nrec) + c->ordinal_base;
     need = std::min<uint64_t>(need, kRandomArray);
     size_t words = (size_t)(kRandomArray + 31) / 32;
     std::vector<uint32_t> bits(words, 0u);
@@ -737,6 +746,13 @@ extern "C" int lhgt_set_sampling(lhgt_ctx* c, double ratio, unsigned seed, long 
     if (rc) return rc;
     CU(cudaMemcpyAsync(c->d_sample_bits, bits.data(), words * 4, cudaMemcpyHostToDevice, c->st));
     CU(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+extern "C" int lhgt_set_ordinal_base(lhgt_ctx* c, uint64_t base) {
+    if (!c) return fail(LHGT_E_ARG, "null ctx");
+    c->ordinal_base = base;
+    c->sampling_set = false;                                       // the sampled subset depends on it
     return 0;
 }
 
@@ -756,8 +772,8 @@ extern "C" long lhgt_s1_count(lhgt_ctx* c, int mate, uint64_t byte_budget) {
     CU(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->st));
     {
         Span sp(c, 1);
-        c->launches += launch_s1(r.d_fq, r.d_start, r.d_end, r.nrec, byte_budget, c->d_sample_bits, c->hp, c->d_count,
-                                 c->d_counter, c->d_err, c->st);
+        c->launches += launch_s1(r.d_fq, r.d_start, r.d_end, r.nrec, byte_budget, c->d_sample_bits, c->ordinal_base, c->hp,
+                                 c->d_count, c->d_counter, c->d_err, c->st);
     }
     unsigned long long sampled = 0; int flag = 0;
     CU(cudaMemcpyAsync(&sampled, c->d_counter, sizeof sampled, cudaMemcpyDeviceToHost, c->st));
@@ -871,7 +887,7 @@ extern "C" long lhgt_s3_pairs(lhgt_ctx* c, long first, long count) {
     if (c->n_peaks > 0) {
         Span sp(c, 4);
         c->launches += launch_s3(a.d_fq, a.d_start, a.d_end, a.nrec, b.d_fq, b.d_start, b.d_end, b.nrec, b.tail_start, b.tail_len,
-                                 (uint64_t)first, cnt, c->d_sample_bits, c->hp, c->d_prefilter, c->d_peak_kmer, c->d_loci,
+                                 (uint64_t)first, cnt, c->d_sample_bits, c->ordinal_base, c->hp, c->d_prefilter, c->d_peak_kmer, c->d_loci,
                                  c->d_filter, c->scratch, s3_grid_blocks(c->device), c->d_counter, c->d_err, c->st);
     }
     unsigned long long sampled = 0; int flag = 0;
@@ -932,7 +948,6 @@ extern "C" int lhgt_reset(lhgt_ctx* c) {
     CU(cudaMemsetAsync(c->d_count, 0, c->count_words * 4, c->st));
     c->n_peaks = -1; c->n_flagged = 0; c->gathered = false;
     CU(cudaStreamSynchronize(c->st));
-    free_spans(c);
     return 0;
 }
 
@@ -1010,6 +1025,7 @@ extern "C" int lhgt_stage_ms(const lhgt_ctx* cc, float* ms6) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess && s.stage >= 0 && s.stage < 6) ms6[s.stage] += ms;
     }
+    free_spans(c);                                                  // read-and-clear
     return 0;
 }
 

@@ -370,8 +370,8 @@ __device__ __forceinline__ bool is_sampled(const uint32_t* __restrict__ sample_b
 template <int E>
 __global__ void __launch_bounds__(kS1Warps * 32, 4) s1_count_kernel(
     const uint8_t* __restrict__ fq, const uint64_t* __restrict__ rec_start, const uint64_t* __restrict__ rec_end,
-    uint64_t nrec, uint64_t budget, const uint32_t* __restrict__ sample_bits, HashP hp, uint32_t* __restrict__ count,
-    unsigned long long* __restrict__ n_sampled, int* __restrict__ err) {
+    uint64_t nrec, uint64_t budget, const uint32_t* __restrict__ sample_bits, uint64_t ordinal_base, HashP hp,
+    uint32_t* __restrict__ count, unsigned long long* __restrict__ n_sampled, int* __restrict__ err) {
     __shared__ uint32_t planes_all[kS1Warps][4 * kReadPlane];
     const int e = E ? E : hp.e;
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(kS1Warps * 32, 4) s1_count_kernel(
     for (uint64_t r = (uint64_t)blockIdx.x * kS1Warps + warp; r < nrec; r += stride) {
         uint64_t start = rec_start[r];
         if (start > budget) continue;                       // Q15 (E:1022-1025 with end = size(fq1))
-        if (!is_sampled(sample_bits, r)) continue;
+        if (!is_sampled(sample_bits, r + ordinal_base)) continue;
         uint64_t len64 = rec_end[r] - start;
         if (len64 > (uint64_t)kMaxReadLen) { if (lane == 0) atomicExch(err, 1); continue; }
         int len = (int)len64;
@@ -421,23 +421,23 @@ __global__ void __launch_bounds__(kS1Warps * 32, 4) s1_count_kernel(
 
 template <int E>
 static void s1_launch(const uint8_t* fq, const uint64_t* rs, const uint64_t* re, uint64_t nrec, uint64_t budget,
-                      const uint32_t* sb, const HashP& hp, uint32_t* count, unsigned long long* ns, int* err,
+                      const uint32_t* sb, uint64_t ob, const HashP& hp, uint32_t* count, unsigned long long* ns, int* err,
                       cudaStream_t st) {
     uint64_t want = (nrec + kS1Warps - 1) / kS1Warps;
     unsigned grid = (unsigned)(want < (uint64_t)kSMs * 4 ? want : (uint64_t)kSMs * 4);
-    s1_count_kernel<E><<<grid, kS1Warps * 32, 0, st>>>(fq, rs, re, nrec, budget, sb, hp, count, ns, err);
+    s1_count_kernel<E><<<grid, kS1Warps * 32, 0, st>>>(fq, rs, re, nrec, budget, sb, ob, hp, count, ns, err);
 }
 
 int launch_s1(const uint8_t* fq, const uint64_t* rec_start, const uint64_t* rec_end, uint64_t nrec, uint64_t budget,
-              const uint32_t* sample_bits, const HashP& hp, uint32_t* count, unsigned long long* n_sampled, int* err,
-              cudaStream_t st) {
+              const uint32_t* sample_bits, uint64_t ordinal_base, const HashP& hp, uint32_t* count,
+              unsigned long long* n_sampled, int* err, cudaStream_t st) {
     if (nrec == 0) return 0;
     switch (hp.e) {
-        case 1: s1_launch<1>(fq, rec_start, rec_end, nrec, budget, sample_bits, hp, count, n_sampled, err, st); break;
-        case 2: s1_launch<2>(fq, rec_start, rec_end, nrec, budget, sample_bits, hp, count, n_sampled, err, st); break;
-        case 3: s1_launch<3>(fq, rec_start, rec_end, nrec, budget, sample_bits, hp, count, n_sampled, err, st); break;
-        case 4: s1_launch<4>(fq, rec_start, rec_end, nrec, budget, sample_bits, hp, count, n_sampled, err, st); break;
-        default: s1_launch<0>(fq, rec_start, rec_end, nrec, budget, sample_bits, hp, count, n_sampled, err, st); break;
+        case 1: s1_launch<1>(fq, rec_start, rec_end, nrec, budget, sample_bits, ordinal_base, hp, count, n_sampled, err, st); break;
+        case 2: s1_launch<2>(fq, rec_start, rec_end, nrec, budget, sample_bits, ordinal_base, hp, count, n_sampled, err, st); break;
+        case 3: s1_launch<3>(fq, rec_start, rec_end, nrec, budget, sample_bits, ordinal_base, hp, count, n_sampled, err, st); break;
+        case 4: s1_launch<4>(fq, rec_start, rec_end, nrec, budget, sample_bits, ordinal_base, hp, count, n_sampled, err, st); break;
+        default: s1_launch<0>(fq, rec_start, rec_end, nrec, budget, sample_bits, ordinal_base, hp, count, n_sampled, err, st); break;
     }
     return 1;
 }
@@ -845,7 +845,7 @@ __global__ void __launch_bounds__(kS3Warps * 32, 4) s3_pairs_kernel(
     const uint8_t* __restrict__ fq1, const uint64_t* __restrict__ s1, const uint64_t* __restrict__ e1, uint64_t nrec1,
     const uint8_t* __restrict__ fq2, const uint64_t* __restrict__ s2, const uint64_t* __restrict__ e2, uint64_t nrec2,
     uint64_t tail_start, uint64_t tail_len, uint64_t first, uint64_t count, const uint32_t* __restrict__ sample_bits,
-    HashP hp, const uint32_t* __restrict__ prefilter, const uint32_t* __restrict__ peak_kmer,
+    uint64_t ordinal_base, HashP hp, const uint32_t* __restrict__ prefilter, const uint32_t* __restrict__ peak_kmer,
     const int32_t* __restrict__ loci, uint8_t* __restrict__ peak_filter, S3Scratch scratch,
     unsigned long long* __restrict__ n_sampled, int* __restrict__ err) {
     __shared__ uint32_t planes_all[kS3Warps][4 * kReadPlane];
@@ -859,7 +859,7 @@ __global__ void __launch_bounds__(kS3Warps * 32, 4) s3_pairs_kernel(
     uint64_t stride = (uint64_t)gridDim.x * kS3Warps;
     uint64_t last = first + count < nrec1 ? first + count : nrec1;
     for (uint64_t r = first + gwarp; r < last; r += stride) {
-        if (!is_sampled(sample_bits, r)) continue;
+        if (!is_sampled(sample_bits, r + ordinal_base)) continue;
         uint64_t a0 = s1[r], l1 = e1[r] - a0, b0, l2;
         if (r < nrec2) { b0 = s2[r]; l2 = e2[r] - b0; }
         else { b0 = tail_start; l2 = tail_len; }            // fq2 exhausted: std::getline leaves its last string
@@ -878,13 +878,14 @@ __global__ void __launch_bounds__(kS3Warps * 32, 4) s3_pairs_kernel(
 
 int launch_s3(const uint8_t* fq1, const uint64_t* s1, const uint64_t* e1, uint64_t nrec1, const uint8_t* fq2,
               const uint64_t* s2, const uint64_t* e2, uint64_t nrec2, uint64_t tail_start, uint64_t tail_len,
-              uint64_t first, uint64_t count, const uint32_t* sample_bits, const HashP& hp, const uint32_t* prefilter,
+              uint64_t first, uint64_t count, const uint32_t* sample_bits, uint64_t ordinal_base, const HashP& hp,
+              const uint32_t* prefilter,
               const uint32_t* peak_kmer, const int32_t* loci, uint8_t* peak_filter, S3Scratch scratch, int grid_blocks,
               unsigned long long* n_sampled, int* err, cudaStream_t st) {
     if (count == 0 || nrec1 == 0) return 0;
 #define LHGT_S3(EE)                                                                                                   \
     s3_pairs_kernel<EE><<<grid_blocks, kS3Warps * 32, 0, st>>>(fq1, s1, e1, nrec1, fq2, s2, e2, nrec2, tail_start,    \
-                                                               tail_len, first, count, sample_bits, hp, prefilter,   \
+                                                               tail_len, first, count, sample_bits, ordinal_base, hp, prefilter,   \
                                                                peak_kmer, loci, peak_filter, scratch, n_sampled, err)
     switch (hp.e) {
         case 1: LHGT_S3(1); break;

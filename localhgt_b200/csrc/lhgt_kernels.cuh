@@ -52,7 +52,7 @@ int launch_index_build(const uint8_t* seq, const Contig* contigs, const Tile* ti
                        const HashP& hp, uint32_t* image, uint8_t* valid_out, cudaStream_t st);
 
 int launch_s1(const uint8_t* fq, const uint64_t* rec_start, const uint64_t* rec_end, uint64_t nrec,
-              uint64_t budget, const uint32_t* sample_bits, const HashP& hp, uint32_t* count,
+              uint64_t budget, const uint32_t* sample_bits, uint64_t ordinal_base, const HashP& hp, uint32_t* count,
               unsigned long long* n_sampled, int* err, cudaStream_t st);
 
 int launch_s2_gather(const uint32_t* image, const Contig* contigs, const Tile* tiles, uint64_t tile_begin,
@@ -73,7 +73,7 @@ int launch_s2_register(const uint32_t* image, const Contig* contigs, const Tile*
 int launch_s3(const uint8_t* fq1, const uint64_t* s1, const uint64_t* e1, uint64_t nrec1,
               const uint8_t* fq2, const uint64_t* s2, const uint64_t* e2, uint64_t nrec2,
               uint64_t mate2_tail_start, uint64_t mate2_tail_len,
-              uint64_t first, uint64_t count, const uint32_t* sample_bits, const HashP& hp,
+              uint64_t first, uint64_t count, const uint32_t* sample_bits, uint64_t ordinal_base, const HashP& hp,
               const uint32_t* prefilter, const uint32_t* peak_kmer, const int32_t* loci,
               uint8_t* peak_filter, S3Scratch scratch, int grid_blocks, unsigned long long* n_sampled,
               int* err, cudaStream_t st);

@@ -1,0 +1,187 @@
+"""One process per GPU: the screen of one sample whose read pairs are partitioned across ranks.
+
+What is sharded and what is exchanged:
+
+  S1   each rank counts the k-mers of ITS record range into its own 2^k table; the tables are then
+       combined field-wise with min(3, a+b) — exact because min(3, sum) == min(3, sum of min(3, .)).
+       Exchange: all-to-all of table slices (rank r receives slice r of every table), local merge,
+       all-gather of the merged slices.  2 x table bytes per rank instead of (N-1) x.
+  S2   the table gather (the HBM-bound part) is sharded over reference tiles; the per-position hit bits
+       (2 bits per reference base) are exchanged; the cheap scans/peak registration then run replicated,
+       so every rank ends with identical peak ids and an identical peak_kmer table without moving it.
+  S3   each rank confirms peaks with its own pairs; only `peak_filter >= 1` is consumed (E:526), so the
+       verdict bytes are max-reduced.
+  OUT  identical on every rank; rank 0's text is the result.
+
+Result = the reference's `-t 1` run over the concatenation of the shards in rank order: sampling
+ordinals are offset by the records of the preceding shards and the fq2 byte budget (quirk Q15) is
+translated into shard-local offsets.
+
+The collectives are torch.distributed (NCCL on GPUs; gloo in the CPU test).  The engine underneath is
+liblhgt through api.Screen; tests/test_multi_gloo.py substitutes the oracle to exercise this file's
+logic on CPU.
+"""
+from __future__ import annotations
+
+import time
+from typing import Optional
+
+import numpy as np
+
+
+class _DevMem:
+    """Exposes a raw device pointer through __cuda_array_interface__ so torch can wrap it (no copy)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def split_range(n: int, parts: int, i: int):
+    """Contiguous near-equal split of range(n): part i of `parts`."""
+    base, extra = divmod(n, parts)
+    lo = i * base + min(i, extra)
+    return lo, lo + base + (1 if i < extra else 0)
+
+
+class GpuEngine:
+    """api.Screen seen through the few operations the sharded plan needs."""
+
+    sharded_s2 = True
+
+    def __init__(self, scr, torch):
+        self.scr, self.torch = scr, torch
+
+    def _wrap(self, ptr_n):
+        ptr, n = ptr_n
+        return self.torch.as_tensor(_DevMem(ptr, n), device=f"cuda:{self.scr.device}") if ptr and n else None
+
+    def table(self):
+        return self._wrap(self.scr.dev_count_table())
+
+    def merge_into(self, byte_offset: int, other) -> None:
+        self.scr.count_merge(other.data_ptr(), other.numel(), byte_offset // 4)
+
+    def hit_bits(self, which: int):
+        return self._wrap(self.scr.dev_hit_bits(which))
+
+    def tile_bytes(self) -> int:
+        return 128                                   # 1024 positions, one bit each
+
+    def peak_filter(self):
+        return self._wrap(self.scr.dev_peak_filter())
+
+    def sync(self):
+        self.scr.sync()
+
+    def __getattr__(self, name):                      # everything else is the Screen's own method
+        return getattr(self.scr, name)
+
+
+class Shard:
+    def __init__(self, scr, rank: int = 0, world: int = 1, dist=None, torch=None, engine=None):
+        self.rank, self.world, self.dist, self.torch = rank, world, dist, torch
+        self.eng = engine if engine is not None else GpuEngine(scr, torch)
+        self.last_stage_ms = np.zeros(8)
+        self.last_peaks = 0
+        self.last_counts = {}
+
+    # ---- collectives on small host scalars
+    def _all_gather_ints(self, vals):
+        if self.world == 1:
+            return [list(vals)]
+        t = self.torch.tensor(list(vals), dtype=self.torch.int64, device=self._dev())
+        out = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return [[int(x) for x in o.tolist()] for o in out]
+
+    def _dev(self):
+        tab = self.eng.table()
+        return tab.device
+
+    def _fence(self, t) -> None:
+        """The engine's kernels run on its own stream: make the host wait for the collective (which torch
+        orders after the current stream) before the next engine call touches the buffer."""
+        if t is not None and t.is_cuda:
+            self.torch.cuda.current_stream(t.device).synchronize()
+
+    # ---- exchanges
+    def exchange_counts(self) -> None:
+        """count := min(3, sum over ranks), on every rank."""
+        tab = self.eng.table()
+        n = tab.numel()
+        w = self.world
+        if n % (4 * w):
+            raise ValueError("count table does not split into word-aligned slices")
+        chunk = n // w
+        recv = self.torch.empty_like(tab)
+        self.dist.all_to_all_single(recv, tab)                 # recv[j] = rank j's slice `rank`
+        self._fence(recv)
+        lo = self.rank * chunk
+        for j in range(w):
+            if j != self.rank:
+                self.eng.merge_into(lo, recv[j * chunk:(j + 1) * chunk])
+        self.eng.sync()
+        mine = tab[lo:lo + chunk].clone()
+        self.dist.all_gather_into_tensor(tab, mine)
+        self._fence(tab)
+
+    def exchange_hit_bits(self, ntiles: int) -> None:
+        tb = self.eng.tile_bytes()
+        for which in (0, 1):
+            bits = self.eng.hit_bits(which)
+            for r in range(self.world):
+                lo, hi = split_range(ntiles, self.world, r)
+                if hi > lo:
+                    self.dist.broadcast(bits[lo * tb:hi * tb], src=r)
+            self._fence(bits)
+
+    # ---- the pass
+    def screen(self, *, size1: int, sample_arg: float, seed: int, rand_skip: int, hit: float, match: float,
+               max_peak: int) -> bytes:
+        """Reads must already be resident (reads_upload / reads_attach_device) and the index loaded."""
+        eng, w = self.eng, self.world
+        ms = np.zeros(8)
+        t0 = time.perf_counter()
+        eng.reset()
+        nrec1, nrec2 = eng.reads_records(0), eng.reads_records(1)
+        info = self._all_gather_ints([nrec1, eng.reads_seq_bases(0), size1, eng.reads_bytes(1)])
+        base = sum(r[0] for r in info[: self.rank])
+        if sample_arg <= 1:
+            ratio = 100 * sample_arg                                   # E:1392-1394
+        else:
+            ratio = 100 * sample_arg / float(2 * sum(r[1] for r in info))   # E:1258-1265 over the whole fq1
+        size1_total = sum(r[2] for r in info)
+        fq2_before = sum(r[3] for r in info[: self.rank])
+        budget2 = size1_total - fq2_before if w > 1 else size1         # Q15 in shard-local byte offsets
+        eng.set_ordinal_base(base)
+        eng.set_sampling(ratio, seed, rand_skip)
+        ms[7] = 1000 * (time.perf_counter() - t0)
+        n1 = eng.s1_count(0, size1_total)                              # fq1 records never start beyond size(fq1)
+        n2 = eng.s1_count(1, budget2) if budget2 >= 0 else 0
+        t1 = time.perf_counter()
+        if w > 1:
+            self.exchange_counts()
+        if w > 1 and eng.sharded_s2:
+            nt = eng.s2_tiles()
+            lo, hi = split_range(nt, w, self.rank)
+            eng.s2_gather(lo, hi)
+            eng.sync()
+            self.exchange_hit_bits(nt)
+            n_peaks = eng.s2_finish(hit, match, max_peak)
+        else:
+            n_peaks = eng.s2_peaks(hit, match, max_peak)
+        t2 = time.perf_counter()
+        n3 = eng.s3_pairs()
+        if w > 1 and n_peaks > 0:
+            eng.sync()
+            filt = eng.peak_filter()
+            self.dist.all_reduce(filt, op=self.dist.ReduceOp.MAX)
+            self._fence(filt)
+        text = eng.intervals()
+        st = eng.stage_ms()
+        ms[:6] = st[:6]
+        ms[6] = 1000 * (t2 - t1) - st[2] - st[3] if w > 1 else 0.0
+        self.last_stage_ms = ms
+        self.last_peaks = int(n_peaks)
+        self.last_counts = {"s1": (int(n1), int(n2)), "s3": int(n3), "ratio": ratio, "ordinal_base": base}
+        return text
