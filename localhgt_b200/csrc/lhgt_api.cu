@@ -233,6 +233,14 @@ extern "C" int lhgt_create(lhgt_ctx** out, int device, int k, int e) {
         return fail(LHGT_E_CUDA, "no CUDA device: liblhgt has no CPU fallback");
     if (device < 0 || device >= ndev) return fail(LHGT_E_ARG, "device %d out of range (%d visible)", device, ndev);
     CU(cudaSetDevice(device));
+    {
+        // The screen's hot loads are 4-byte gathers from 2^k-entry tables far larger than L2: ask L2 to fetch
+        // single 32-byte sectors from HBM instead of promoting every miss to a wider line.
+        const char* g = getenv("LHGT_L2_FETCH");
+        size_t gran = g ? (size_t)atoi(g) : 32;
+        if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+        cudaGetLastError();
+    }
     lhgt_ctx* c = new lhgt_ctx();
     c->device = device; c->k = k; c->e = e;
     for (int i = 0; i < LHGT_CODER_SLOTS; ++i) c->cc[i] = 100;
