@@ -73,6 +73,7 @@ SYMBOLS = {
     "lhgt_set_sampling": (_i, [_vp, _d, _u, _l]),
     "lhgt_set_ordinal_base": (_i, [_vp, _u64]),
     "lhgt_s1_count": (_l, [_vp, _i, _u64]),
+    "lhgt_set_s1_mode": (_i, [_vp, _i]),
     "lhgt_s2_peaks": (_l, [_vp, _f, _f, _l]),
     "lhgt_s3_pairs": (_l, [_vp, _l, _l]),
     "lhgt_intervals": (_i, [_vp, _vp, _sz, C.POINTER(_sz)]),
@@ -89,6 +90,7 @@ SYMBOLS = {
     "lhgt_dev_peak_filter": (_vp, [_vp, C.POINTER(_u64)]),
     "lhgt_count_merge": (_i, [_vp, _vp, _u64, _u64]),
     "lhgt_stage_ms": (_i, [_vp, _vp]),
+    "lhgt_stage_ms_ex": (_i, [_vp, _vp, _i]),
     "lhgt_launch_count": (_l, [_vp]),
     "lhgt_extract_ref": (_i, [C.POINTER(Args), C.POINTER(Stats)]),
     "lhgt_main": (_i, [_i, C.POINTER(_s)]),
@@ -271,6 +273,10 @@ class Screen:
     def s1_count(self, mate: int, byte_budget: int) -> int:
         return _check(self._L.lhgt_s1_count(self._h, mate, byte_budget))
 
+    def set_s1_mode(self, mode: int) -> None:
+        """0 auto, 1 direct probes, 2 hash streams (identical counts; see include/lhgt.h)."""
+        _check(self._L.lhgt_set_s1_mode(self._h, mode))
+
     def s2_peaks(self, hit_ratio: float = 0.1, match_ratio: float = 0.08, max_peak: int = 300000000) -> int:
         return _check(self._L.lhgt_s2_peaks(self._h, hit_ratio, match_ratio, max_peak))
 
@@ -337,8 +343,10 @@ class Screen:
         _check(self._L.lhgt_count_merge(self._h, dev_other, nbytes, word_offset))
 
     def stage_ms(self) -> np.ndarray:
-        ms = np.zeros(6, dtype=np.float32)
-        _check(self._L.lhgt_stage_ms(self._h, _ptr(ms)))
+        """Device ms per stage since the last call: [0] FASTQ record scan [1] S1 [2] S2 gather [3] S2 finish [4] S3
+        [5] IB [6] S1 hash-stream kernel [7] S1 stream-apply kernels."""
+        ms = np.zeros(8, dtype=np.float32)
+        _check(self._L.lhgt_stage_ms_ex(self._h, _ptr(ms), 8))
         return ms
 
     def launch_count(self) -> int: return int(self._L.lhgt_launch_count(self._h))

@@ -19,6 +19,8 @@
 
 using namespace lhgt;
 
+static const int kBinWarpsHost = 8;   // warps per CTA of s1_bin_kernel
+
 // ------------------------------------------------------------------------------------------------ errors
 static thread_local char g_err[512] = "";
 
@@ -113,6 +115,9 @@ struct lhgt_ctx {
     uint64_t ordinal_base = 0;               // records that precede this context's shard in the whole sample
 
     uint32_t* d_cands = nullptr; int32_t* d_tally = nullptr; S3Scratch scratch{};
+
+    int s1_mode = 0;                         // 0 auto, 1 direct probes, 2 binned streams (lhgt_set_s1_mode)
+    uint32_t* d_bin_pool = nullptr; uint64_t bin_pool_entries = 0; uint32_t* d_bin_cursor = nullptr;
 
     unsigned long long* d_counter = nullptr; int* d_err = nullptr;
 
@@ -295,6 +300,7 @@ extern "C" void lhgt_destroy(lhgt_ctx* c) {
     dev_free(c->d_count); dev_free(c->d_peak_kmer); dev_free(c->d_prefilter);
     dev_free(c->d_loci); dev_free(c->d_filter); dev_free(c->d_sample_bits);
     dev_free(c->d_cands); dev_free(c->d_tally); dev_free(c->d_counter); dev_free(c->d_err);
+    dev_free(c->d_bin_pool); dev_free(c->d_bin_cursor);
     if (c->own) cudaStreamDestroy(c->own);
     delete c;
 }
@@ -770,6 +776,71 @@ static int check_err_flag(lhgt_ctx* c, int* flag) {
     return 0;
 }
 
+// S1 plan: tables beyond this size are counted through hash streams so that each table slice is L2-resident
+// while it is updated; smaller tables are probed directly (they sit in L2 anyway).
+static const uint64_t kSliceBytes = (uint64_t)64 << 20;
+
+extern "C" int lhgt_set_s1_mode(lhgt_ctx* c, int mode) {
+    if (!c || mode < 0 || mode > 2) return fail(LHGT_E_ARG, "lhgt_set_s1_mode: mode is 0 (auto), 1 (direct) or 2 (binned)");
+    if (mode == 2 && c->k < 8) return fail(LHGT_E_ARG, "binned counting needs k >= 8");
+    c->s1_mode = mode;
+    return 0;
+}
+
+static uint64_t bin_pool_limit_entries() {
+    const char* g = getenv("LHGT_BIN_POOL_MB");                      // test knob: forces several chunks
+    uint64_t mb = g ? (uint64_t)atol(g) : (uint64_t)12 << 10;
+    if (mb < 1) mb = 1;
+    return (mb << 20) / 4;
+}
+
+static int s1_binned(lhgt_ctx* c, Reads& r, uint64_t byte_budget) {
+    uint64_t table_bytes = c->count_words * 4;
+    BinP bp{};
+    bp.log2 = 0;
+    while (bp.log2 < 4 && (table_bytes >> bp.log2) > kSliceBytes) ++bp.log2;
+    if (c->s1_mode == 2) bp.log2 = 4;                                // forced (tests at small k)
+    bp.shift = c->k - bp.log2;
+    int nbins = 1 << bp.log2;
+    bp.bucket_cap = (uint32_t)(2 * kBinWarpsHost * 128 * c->e / nbins);   // twice the expected fill of one round
+    // hashes one record contributes on average (sampled fraction included), +12.5 % for skew between streams
+    double avg_len = r.nrec ? (double)r.seq_bases / (double)r.nrec : 0.0;
+    double per_rec = std::max(1.0, avg_len - c->k + 1) * c->e * std::min(1.0, c->d_sample_bits ? c->ratio / 100.0 : 1.0);
+    uint64_t want = (uint64_t)(per_rec * (double)r.nrec * 1.125) + (uint64_t)nbins * 4096;
+    uint64_t limit = bin_pool_limit_entries();
+    uint64_t total = std::min(want, limit);
+    uint64_t cap = (total / nbins + 7) & ~(uint64_t)7;
+    if (cap > 0xfffffff8ull / 2) cap = 0xfffffff8ull / 2;            // cursors are 32-bit and may run past cap
+    if (c->bin_pool_entries < cap * nbins) {
+        dev_free(c->d_bin_pool);
+        c->bin_pool_entries = 0;
+        int rc = dev_alloc(&c->d_bin_pool, cap * nbins);
+        if (rc) return rc;
+        c->bin_pool_entries = cap * nbins;
+    }
+    if (!c->d_bin_cursor) { int rc = dev_alloc(&c->d_bin_cursor, kMaxBins); if (rc) return rc; }
+    bp.pool = c->d_bin_pool; bp.cursor = c->d_bin_cursor; bp.cap = (uint32_t)cap;
+    uint64_t per_chunk = std::max<uint64_t>(1, (uint64_t)((double)cap * nbins / 1.125 / per_rec));
+    for (uint64_t lo = 0; lo < r.nrec; lo += per_chunk) {
+        uint64_t hi = std::min(r.nrec, lo + per_chunk);
+        CU(cudaMemsetAsync(c->d_bin_cursor, 0, kMaxBins * sizeof(uint32_t), c->st));
+        int n;
+        {
+            Span sp(c, 6);
+            n = launch_s1_binned(r.d_fq, r.d_start, r.d_end, lo, hi, byte_budget, c->d_sample_bits, c->ordinal_base, c->hp, bp,
+                                 c->d_count, c->d_counter, c->d_err, 0, c->st);
+        }
+        if (n < 0) return fail(LHGT_E_CUDA, "S1 stream kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        c->launches += n;
+        {
+            Span sp(c, 7);
+            c->launches += launch_s1_binned(r.d_fq, r.d_start, r.d_end, lo, hi, byte_budget, c->d_sample_bits, c->ordinal_base, c->hp, bp,
+                                            c->d_count, c->d_counter, c->d_err, 1, c->st);
+        }
+    }
+    return 0;
+}
+
 extern "C" long lhgt_s1_count(lhgt_ctx* c, int mate, uint64_t byte_budget) {
     if (!c || mate < 0 || mate > 1) return fail(LHGT_E_ARG, "bad argument");
     Reads& r = c->reads[mate];
@@ -778,10 +849,16 @@ extern "C" long lhgt_s1_count(lhgt_ctx* c, int mate, uint64_t byte_budget) {
     CU(cudaSetDevice(c->device));
     CU(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), c->st));
     CU(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->st));
+    bool binned = c->s1_mode == 2 || (c->s1_mode == 0 && c->count_words * 4 > kSliceBytes);
     {
         Span sp(c, 1);
-        c->launches += launch_s1(r.d_fq, r.d_start, r.d_end, r.nrec, byte_budget, c->d_sample_bits, c->ordinal_base, c->hp,
-                                 c->d_count, c->d_counter, c->d_err, c->st);
+        if (binned) {
+            int rc = s1_binned(c, r, byte_budget);
+            if (rc) return rc;
+        } else {
+            c->launches += launch_s1(r.d_fq, r.d_start, r.d_end, r.nrec, byte_budget, c->d_sample_bits, c->ordinal_base, c->hp,
+                                     c->d_count, c->d_counter, c->d_err, c->st);
+        }
     }
     unsigned long long sampled = 0; int flag = 0;
     CU(cudaMemcpyAsync(&sampled, c->d_counter, sizeof sampled, cudaMemcpyDeviceToHost, c->st));
@@ -1024,14 +1101,23 @@ extern "C" int lhgt_count_merge(lhgt_ctx* c, const void* dev_other, uint64_t byt
 }
 
 extern "C" int lhgt_stage_ms(const lhgt_ctx* cc, float* ms6) {
+    float ms8[LHGT_STAGES];
+    int rc = lhgt_stage_ms_ex(cc, ms8, LHGT_STAGES);
+    if (rc) return rc;
+    if (!ms6) return fail(LHGT_E_ARG, "null pointer");
+    for (int i = 0; i < 6; ++i) ms6[i] = ms8[i];
+    return 0;
+}
+
+extern "C" int lhgt_stage_ms_ex(const lhgt_ctx* cc, float* ms6, int n_stages) {
     lhgt_ctx* c = const_cast<lhgt_ctx*>(cc);
-    if (!c || !ms6) return fail(LHGT_E_ARG, "null pointer");
+    if (!c || !ms6 || n_stages < 1) return fail(LHGT_E_ARG, "null pointer");
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->st));
-    for (int i = 0; i < 6; ++i) ms6[i] = 0.f;
+    for (int i = 0; i < n_stages; ++i) ms6[i] = 0.f;
     for (auto& s : c->spans) {
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess && s.stage >= 0 && s.stage < 6) ms6[s.stage] += ms;
+        if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess && s.stage >= 0 && s.stage < n_stages) ms6[s.stage] += ms;
     }
     free_spans(c);                                                  // read-and-clear
     return 0;

@@ -443,6 +443,172 @@ int launch_s1(const uint8_t* fq, const uint64_t* rec_start, const uint64_t* rec_
 }
 
 // ------------------------------------------------------------------------------------------------
+// S1, binned form.  A 2^k-entry table far larger than L2 makes every direct probe a
+// 128-byte DRAM fill (profiles/r01_probe_bench_*: 43 G probes/s), while a table slice that fits L2
+// sustains 290 G probes/s.  So counting runs in two phases:
+//   A  s1_bin_kernel: hash the sampled reads and append every hash to one of 2^bin_log2 streams
+//      chosen by its top bits (per-CTA shared-memory buckets, flushed as coalesced runs);
+//   B  s1_apply_kernel, once per stream: the 64 MiB table slice the stream addresses stays L2-resident
+//      while the stream is read back sequentially and applied with the same load + CAS update.
+// Saturating increments commute, so the table is bit-identical to the direct form's.  A stream that
+// would overflow its region (pathological, low-complexity input) applies the surplus directly.
+// ------------------------------------------------------------------------------------------------
+constexpr int kBinWarps = 8;
+
+__device__ __forceinline__ void bump_direct(uint32_t* count, uint32_t h) {
+    bump(count, h, ld_table(count + (h >> 4)));
+}
+
+template <int E>
+__global__ void __launch_bounds__(kBinWarps * 32, 3) s1_bin_kernel(
+    const uint8_t* __restrict__ fq, const uint64_t* __restrict__ rec_start, const uint64_t* __restrict__ rec_end,
+    uint64_t rec_lo, uint64_t rec_hi, uint64_t budget, const uint32_t* __restrict__ sample_bits, uint64_t ordinal_base,
+    HashP hp, BinP bp, uint32_t* __restrict__ count, unsigned long long* __restrict__ n_sampled, int* __restrict__ err) {
+    extern __shared__ uint32_t dyn[];
+    __shared__ uint32_t planes_all[kBinWarps][4 * kReadPlane];
+    __shared__ uint32_t cnt[kMaxBins];
+    uint32_t* buckets = dyn;                                  // [nbins][bucket_cap]
+    const int e = E ? E : hp.e;
+    const int nbins = 1 << bp.log2;
+    const uint32_t bcap = bp.bucket_cap;
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* planes = planes_all[warp];
+    if (threadIdx.x < kMaxBins) cnt[threadIdx.x] = 0;
+    unsigned long long mine = 0;
+    uint64_t stride = (uint64_t)gridDim.x * kBinWarps;
+    uint64_t r = rec_lo + (uint64_t)blockIdx.x * kBinWarps + warp;
+    int np = 0, j0 = 0;
+    bool have = false;
+    for (;;) {
+        while (!have && r < rec_hi) {                         // next read of this warp that has k-mers to count
+            uint64_t start = rec_start[r];
+            bool take = start <= budget && is_sampled(sample_bits, r + ordinal_base);   // Q15
+            if (take) {
+                uint64_t len64 = rec_end[r] - start;
+                if (len64 > (uint64_t)kMaxReadLen) { if (lane == 0) atomicExch(err, 1); take = false; }
+                else {
+                    ++mine;
+                    np = (int)len64 - hp.k + 1;
+                    if (np > 0) { warp_pack<kReadPlane>(fq + start, (int)len64, planes, lane); have = true; j0 = 0; }
+                }
+            }
+            if (!have) r += stride;
+        }
+        if (!__syncthreads_or(have)) break;                   // also: buckets and cnt are free again
+        if (have) {
+#pragma unroll
+            for (int u = 0; u < kS1Unroll; ++u) {
+                int j = j0 + u * 32 + lane;
+                bool ok = j < np;
+                KmerWin kw = make_win<kReadPlane>(planes, ok ? j : 0, hp);
+                ok = ok && kw.valid;
+#pragma unroll
+                for (int i = 0; i < (E ? E : kMaxE); ++i)
+                    if (i < e && ok) {
+                        uint32_t h = hash_of(kw, hp, i);
+                        uint32_t b = h >> bp.shift;
+                        uint32_t slot = atomicAdd(&cnt[b], 1u);
+                        if (slot < bcap) buckets[b * bcap + slot] = h;
+                        else bump_direct(count, h);           // bucket full: rare, exact either way
+                    }
+            }
+            j0 += 32 * kS1Unroll;
+            if (j0 >= np) { have = false; r += stride; }
+        }
+        __syncthreads();
+        for (int b = warp; b < nbins; b += kBinWarps) {       // flush: one coalesced run per stream
+            uint32_t n = min(cnt[b], bcap);
+            if (n) {
+                uint32_t g = 0;
+                if (lane == 0) g = atomicAdd(bp.cursor + b, n);
+                g = __shfl_sync(kFull, g, 0);
+                uint32_t* dst = bp.pool + (size_t)b * bp.cap;
+                for (uint32_t x = lane; x < n; x += 32) {
+                    uint32_t h = buckets[b * bcap + x];
+                    if (g + x < bp.cap) dst[g + x] = h;
+                    else bump_direct(count, h);               // stream region full
+                }
+            }
+            __syncwarp();
+            if (lane == 0) cnt[b] = 0;
+        }
+    }
+    if (lane == 0 && mine) atomicAdd(n_sampled, mine);
+}
+
+__device__ __forceinline__ void ld_stream8(const uint32_t* p, uint32_t v[8]) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(p));
+}
+
+constexpr int kApplyThreads = 256, kApplyVec = 2;            // 16 probes in flight per thread
+
+__global__ void __launch_bounds__(kApplyThreads) s1_apply_kernel(const uint32_t* __restrict__ stream,
+                                                                 const uint32_t* __restrict__ cursor, uint32_t cap,
+                                                                 uint32_t* __restrict__ count) {
+    uint32_t n = min(*cursor, cap);
+    uint32_t n8 = n >> 3;
+    uint32_t tid = blockIdx.x * kApplyThreads + threadIdx.x, nthreads = gridDim.x * kApplyThreads;
+    for (uint32_t base = tid; base < n8; base += nthreads * kApplyVec) {
+        uint32_t h[kApplyVec][8], seen[kApplyVec][8];
+        bool ok[kApplyVec];
+#pragma unroll
+        for (int v = 0; v < kApplyVec; ++v) {
+            uint32_t at = base + v * nthreads;
+            ok[v] = at < n8;
+            if (ok[v]) ld_stream8(stream + (size_t)at * 8, h[v]);
+        }
+#pragma unroll
+        for (int v = 0; v < kApplyVec; ++v)
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (ok[v]) seen[v][q] = ld_table(count + (h[v][q] >> 4));
+#pragma unroll
+        for (int v = 0; v < kApplyVec; ++v)
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (ok[v]) bump(count, h[v][q], seen[v][q]);
+    }
+    if (tid < (n & 7u)) bump_direct(count, stream[(n8 << 3) + tid]);
+}
+
+size_t s1_bin_smem_bytes(const BinP& bp) { return ((size_t)bp.bucket_cap << bp.log2) * sizeof(uint32_t); }
+
+template <int E>
+static cudaError_t s1_bin_launch(const uint8_t* fq, const uint64_t* rs, const uint64_t* re, uint64_t lo, uint64_t hi, uint64_t budget,
+                                 const uint32_t* sb, uint64_t ob, const HashP& hp, const BinP& bp, uint32_t* count,
+                                 unsigned long long* ns, int* err, cudaStream_t st) {
+    size_t smem = s1_bin_smem_bytes(bp);
+    cudaError_t rc = cudaFuncSetAttribute(s1_bin_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (rc != cudaSuccess) return rc;
+    uint64_t want = (hi - lo + kBinWarps - 1) / kBinWarps;
+    unsigned grid = (unsigned)(want < (uint64_t)kSMs * 3 ? want : (uint64_t)kSMs * 3);
+    s1_bin_kernel<E><<<grid, kBinWarps * 32, smem, st>>>(fq, rs, re, lo, hi, budget, sb, ob, hp, bp, count, ns, err);
+    return cudaGetLastError();
+}
+
+int launch_s1_binned(const uint8_t* fq, const uint64_t* rec_start, const uint64_t* rec_end, uint64_t rec_lo, uint64_t rec_hi,
+                     uint64_t budget, const uint32_t* sample_bits, uint64_t ordinal_base, const HashP& hp, const BinP& bp,
+                     uint32_t* count, unsigned long long* n_sampled, int* err, int phase, cudaStream_t st) {
+    if (rec_hi <= rec_lo) return 0;
+    int nbins = 1 << bp.log2;
+    if (phase == 1) {
+        for (int b = 0; b < nbins; ++b)
+            s1_apply_kernel<<<kSMs * 8, kApplyThreads, 0, st>>>(bp.pool + (size_t)b * bp.cap, bp.cursor + b, bp.cap, count);
+        return nbins;
+    }
+    cudaError_t rc;
+    switch (hp.e) {
+        case 1: rc = s1_bin_launch<1>(fq, rec_start, rec_end, rec_lo, rec_hi, budget, sample_bits, ordinal_base, hp, bp, count, n_sampled, err, st); break;
+        case 2: rc = s1_bin_launch<2>(fq, rec_start, rec_end, rec_lo, rec_hi, budget, sample_bits, ordinal_base, hp, bp, count, n_sampled, err, st); break;
+        case 3: rc = s1_bin_launch<3>(fq, rec_start, rec_end, rec_lo, rec_hi, budget, sample_bits, ordinal_base, hp, bp, count, n_sampled, err, st); break;
+        case 4: rc = s1_bin_launch<4>(fq, rec_start, rec_end, rec_lo, rec_hi, budget, sample_bits, ordinal_base, hp, bp, count, n_sampled, err, st); break;
+        default: rc = s1_bin_launch<0>(fq, rec_start, rec_end, rec_lo, rec_hi, budget, sample_bits, ordinal_base, hp, bp, count, n_sampled, err, st); break;
+    }
+    return rc != cudaSuccess ? -1 : 1;
+}
+
+// ------------------------------------------------------------------------------------------------
 // S2 (E:888-979 + E:550-725 + E:239-301) as five data-parallel passes over 1024-position tiles.
 // Bit arrays are little-endian in bit order: tile t, local position x -> word t*32 + x/32, bit x%32.
 // ------------------------------------------------------------------------------------------------

@@ -32,6 +32,17 @@ struct Contig {
     uint32_t tile0;                    // first tile
 };
 
+constexpr int kMaxBins = 16;           // S1 hash streams (table slices of 2^k / 4 / nbins bytes)
+
+struct BinP {                          // S1, binned form
+    uint32_t* pool;                    // [1 << log2][cap] hashes
+    uint32_t* cursor;                  // [1 << log2] entries appended so far (may run past cap: surplus was applied directly)
+    uint32_t cap;                      // entries per stream, multiple of 8
+    uint32_t bucket_cap;               // shared-memory bucket entries per stream per CTA
+    int log2;                          // streams = 1 << log2 <= kMaxBins
+    int shift;                         // stream of hash h = h >> shift  (k - log2)
+};
+
 struct S3Scratch {                     // per resident warp
     uint32_t* cands;                   // [2*(kMaxReadLen)] * e
     int32_t* tally;                    // [3 * 2*kMaxReadLen]
@@ -54,6 +65,14 @@ int launch_index_build(const uint8_t* seq, const Contig* contigs, const Tile* ti
 int launch_s1(const uint8_t* fq, const uint64_t* rec_start, const uint64_t* rec_end, uint64_t nrec,
               uint64_t budget, const uint32_t* sample_bits, uint64_t ordinal_base, const HashP& hp, uint32_t* count,
               unsigned long long* n_sampled, int* err, cudaStream_t st);
+
+// phase 0: stream the hashes of records [rec_lo, rec_hi) (cursors must be zero on entry);
+// phase 1: one apply launch per stream
+int launch_s1_binned(const uint8_t* fq, const uint64_t* rec_start, const uint64_t* rec_end, uint64_t rec_lo,
+                     uint64_t rec_hi, uint64_t budget, const uint32_t* sample_bits, uint64_t ordinal_base,
+                     const HashP& hp, const BinP& bp, uint32_t* count, unsigned long long* n_sampled, int* err,
+                     int phase, cudaStream_t st);
+size_t s1_bin_smem_bytes(const BinP& bp);
 
 int launch_s2_gather(const uint32_t* image, const Contig* contigs, const Tile* tiles, uint64_t tile_begin,
                      uint64_t tile_end, const HashP& hp, const uint32_t* count, uint32_t* single,

@@ -81,7 +81,7 @@ class Shard:
     def __init__(self, scr, rank: int = 0, world: int = 1, dist=None, torch=None, engine=None):
         self.rank, self.world, self.dist, self.torch = rank, world, dist, torch
         self.eng = engine if engine is not None else GpuEngine(scr, torch)
-        self.last_stage_ms = np.zeros(8)
+        self.last_stage_ms = np.zeros(10)
         self.last_peaks = 0
         self.last_counts = {}
 
@@ -140,7 +140,7 @@ class Shard:
                max_peak: int) -> bytes:
         """Reads must already be resident (reads_upload / reads_attach_device) and the index loaded."""
         eng, w = self.eng, self.world
-        ms = np.zeros(8)
+        ms = np.zeros(10)
         t0 = time.perf_counter()
         eng.reset()
         nrec1, nrec2 = eng.reads_records(0), eng.reads_records(1)
@@ -180,6 +180,8 @@ class Shard:
         text = eng.intervals()
         st = eng.stage_ms()
         ms[:6] = st[:6]
+        if len(st) >= 8:
+            ms[8:10] = st[6:8]                                          # S1 split: hash-stream kernel, stream-apply kernels
         ms[6] = 1000 * (t2 - t1) - st[2] - st[3] if w > 1 else 0.0
         self.last_stage_ms = ms
         self.last_peaks = int(n_peaks)

@@ -122,6 +122,72 @@ def test_stages_match_oracle(case, manifest, workdir):
     o.close()
 
 
+# ------------------------------------------------------------------ S1: direct probes vs hash streams
+def _low_complexity_fastq(path, rng, n_random=3000):
+    """Reads that defeat uniform hashing: homopolymers and short tandem repeats put every k-mer of a read
+    (and of thousands of reads) into ONE stream, overflowing the shared-memory buckets and a small stream region."""
+    seqs = []
+    for i in range(1500):
+        seqs.append(b"A" * 150)
+        seqs.append((b"AC" * 80)[: 100 + i % 50])
+        seqs.append((b"GATTACA" * 30)[:150])
+        seqs.append(b"T" * 40 + b"N" + b"T" * 60)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    for _ in range(n_random):
+        seqs.append(acgt[rng.integers(0, 4, int(rng.integers(20, 250)))].tobytes())
+    order = rng.permutation(len(seqs))
+    seqs = [seqs[i] for i in order]
+    synth.write_fastq_ragged(path, [b"r%d/1" % i for i in range(len(seqs))], seqs)
+    return len(seqs)
+
+
+@pytest.mark.parametrize("k,e", [(24, 3), (16, 5), (27, 10)])
+def test_s1_streams_equal_direct_and_oracle(k, e, workdir, monkeypatch):
+    rng = np.random.default_rng(k * 100 + e)
+    fq = os.path.join(workdir, f"lowc_{k}_{e}.fq")
+    n = _low_complexity_fastq(fq, rng)
+    raw = _read(fq)
+    o = orc.Oracle(k, e); o.srand(3); cc = o.random_coder()
+    o.fill_random(n + 8)
+    ratio = 80.0
+    want_n = o.s1_count(fq, len(raw), ratio)
+    want = o.count_table().copy()
+    o.close()
+    for mode, pool_mb in ((1, None), (2, None), (2, "1")):
+        if pool_mb:
+            monkeypatch.setenv("LHGT_BIN_POOL_MB", pool_mb)      # 16 K entries per stream: many chunks + full regions
+        else:
+            monkeypatch.delenv("LHGT_BIN_POOL_MB", raising=False)
+        with api.Screen(k, e) as s:
+            s.set_coder(cc)
+            s.set_s1_mode(mode)
+            s.reads_upload(0, raw)
+            s.set_sampling(ratio, 3, k * (e // 3 + 1))
+            assert s.s1_count(0, len(raw)) == want_n
+            got = s.count_table()
+            assert np.array_equal(got, want), (mode, pool_mb, int((got != want).sum()))
+            s.s1_count(0, len(raw))                               # counting again only saturates further
+            assert np.array_equal(s.count_table(), np.minimum(3, 2 * want.astype(np.int32)))
+
+
+@pytest.mark.parametrize("case", [fixtures.BY_NAME[n] for n in ("base_k24", "noisy", "shorts_bp", "fq2_longer")], ids=lambda c: c.name)
+def test_streamed_s1_whole_run(case, manifest, workdir):
+    """The full pass with S1 forced through the stream path reproduces the reference's interval text."""
+    gold = manifest[case.name]
+    fa, fq1, fq2, o, s, idx, lenp, skip = _stage_run(case, workdir)
+    o.close()
+    with s:
+        s.set_s1_mode(2)
+        b1, b2 = _read(fq1), _read(fq2)
+        s.reads_upload(0, b1); s.reads_upload(1, b2)
+        s.set_sampling(s.sample_ratio(case.sample), case.seed, skip)
+        n1, n2 = s.s1_count(0, len(b1)), s.s1_count(1, len(b1))
+        assert (n1 + n2) // 2 == gold["ref_pairs_s1"]
+        assert s.s2_peaks(case.hit, case.match, case.max_peak) == gold["ref_raw_peaks"]
+        assert s.s3_pairs() == gold["ref_pairs_s3"]
+        assert s.intervals().decode() == gold["interval_text"]
+
+
 # ------------------------------------------------------------------ the whole program, file level
 @pytest.mark.parametrize("case", fixtures.CASES, ids=lambda c: c.name)
 def test_extract_ref_matches_reference_binary(case, manifest, workdir):
