@@ -72,12 +72,40 @@ struct GlibcRand {
 };
 
 // ------------------------------------------------------------------------------------------------ context
+template <class T>
+static int dev_alloc(T** p, size_t count) {
+    *p = nullptr;
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+    if (e != cudaSuccess) return fail(LHGT_E_NOMEM, "cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+    return 0;
+}
+template <class T>
+static void dev_free(T*& p) { if (p) cudaFree((void*)p); p = nullptr; }
+
+// Grow-only device buffer: cudaMalloc/cudaFree synchronise the device and cost milliseconds at these sizes, so a
+// context that screens sample after sample keeps its buffers and only ever enlarges them.
+template <class T>
+struct DevBuf {
+    T* p = nullptr; size_t cap = 0;
+    int reserve(size_t n) {
+        if (n <= cap && p) return 0;
+        release();
+        int rc = dev_alloc(&p, n);
+        if (!rc) cap = n ? n : 1;
+        return rc;
+    }
+    void release() { dev_free(p); cap = 0; }
+};
+
 struct Reads {
     const uint8_t* d_fq = nullptr;
     bool owned = false;
     uint64_t n = 0, nrec = 0, seq_bases = 0;
-    uint64_t* d_start = nullptr;
+    uint64_t* d_start = nullptr;               // = start_buf.p / end_buf.p once located
     uint64_t* d_end = nullptr;
+    DevBuf<uint8_t> fq_buf;                    // backing store of an uploaded image (owned)
+    DevBuf<uint64_t> start_buf, end_buf;
     uint64_t tail_start = 0, tail_len = 0;   // what std::getline leaves behind once the file is exhausted
     bool ready = false;
 };
@@ -95,6 +123,9 @@ struct lhgt_ctx {
     uint32_t* d_prefilter = nullptr;
 
     uint32_t* d_image = nullptr; uint64_t image_words = 0; bool image_owned = true;
+    DevBuf<uint32_t> image_buf, single_buf, trio_buf, good_buf, flagged_buf, tile_new_buf, tile_base_buf, scan_tmp_buf;
+    DevBuf<uint32_t> fq_cnt_buf, fq_base_buf, fq_tmp_buf;    // FASTQ newline-scan temporaries
+    DevBuf<Contig> contigs_buf; DevBuf<Tile> tiles_buf;
     std::vector<Contig> contigs; std::vector<Tile> tiles;
     Contig* d_contigs = nullptr; Tile* d_tiles = nullptr;
     uint64_t index_bases = 0;
@@ -166,16 +197,6 @@ static void free_spans(lhgt_ctx* c) {
     c->spans.clear();
 }
 
-template <class T>
-static int dev_alloc(T** p, size_t count) {
-    *p = nullptr;
-    if (count == 0) count = 1;
-    cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
-    if (e != cudaSuccess) return fail(LHGT_E_NOMEM, "cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
-    return 0;
-}
-template <class T>
-static void dev_free(T*& p) { if (p) cudaFree((void*)p); p = nullptr; }
 
 // ------------------------------------------------------------------------------------------------ small ABI
 extern "C" int lhgt_abi_version(void) { return LHGT_ABI_VERSION; }
@@ -274,18 +295,22 @@ extern "C" int lhgt_create(lhgt_ctx** out, int device, int k, int e) {
     return 0;
 }
 
-static void drop_reads(Reads& r) {
-    if (r.owned) { uint8_t* p = const_cast<uint8_t*>(r.d_fq); dev_free(p); }
-    dev_free(r.d_start); dev_free(r.d_end);
-    r = Reads();
+static void drop_reads(Reads& r, bool release = false) {      // forgets the sample, keeps the buffers
+    if (release) { r.fq_buf.release(); r.start_buf.release(); r.end_buf.release(); }
+    r.d_fq = nullptr; r.owned = false; r.n = r.nrec = r.seq_bases = 0;
+    r.d_start = r.d_end = nullptr; r.tail_start = r.tail_len = 0; r.ready = false;
 }
 
-static void drop_index(lhgt_ctx* c) {
-    if (c->image_owned) dev_free(c->d_image);
+static void drop_index(lhgt_ctx* c, bool release = false) {     // forgets the index, keeps the buffers
+    if (release) {
+        c->image_buf.release(); c->single_buf.release(); c->trio_buf.release(); c->good_buf.release(); c->flagged_buf.release();
+        c->tile_new_buf.release(); c->tile_base_buf.release(); c->scan_tmp_buf.release(); c->contigs_buf.release(); c->tiles_buf.release();
+        c->fq_cnt_buf.release(); c->fq_base_buf.release(); c->fq_tmp_buf.release();
+    }
     c->d_image = nullptr; c->image_owned = true; c->image_words = 0;
-    dev_free(c->d_contigs); dev_free(c->d_tiles);
-    dev_free(c->d_single); dev_free(c->d_trio); dev_free(c->d_good); dev_free(c->d_flagged);
-    dev_free(c->d_tile_new); dev_free(c->d_tile_base); dev_free(c->d_scan_tmp);
+    c->d_contigs = nullptr; c->d_tiles = nullptr;
+    c->d_single = c->d_trio = c->d_good = c->d_flagged = nullptr;
+    c->d_tile_new = c->d_tile_base = c->d_scan_tmp = nullptr;
     c->contigs.clear(); c->tiles.clear(); c->len_text.clear();
     c->index_ready = false; c->gathered = false; c->index_bases = 0;
 }
@@ -295,8 +320,8 @@ extern "C" void lhgt_destroy(lhgt_ctx* c) {
     cudaSetDevice(c->device);
     if (c->st) cudaStreamSynchronize(c->st);
     free_spans(c);
-    drop_reads(c->reads[0]); drop_reads(c->reads[1]);
-    drop_index(c);
+    drop_reads(c->reads[0], true); drop_reads(c->reads[1], true);
+    drop_index(c, true);
     dev_free(c->d_count); dev_free(c->d_peak_kmer); dev_free(c->d_prefilter);
     dev_free(c->d_loci); dev_free(c->d_filter); dev_free(c->d_sample_bits);
     dev_free(c->d_cands); dev_free(c->d_tally); dev_free(c->d_counter); dev_free(c->d_err);
@@ -347,13 +372,14 @@ static int finish_index_tables(lhgt_ctx* c) {
     }
     size_t nt = c->tiles.size();
     int rc = 0;
-    if ((rc = dev_alloc(&c->d_contigs, c->contigs.size()))) return rc;
-    if ((rc = dev_alloc(&c->d_tiles, nt))) return rc;
     size_t bw = nt * kTileWords;
-    if ((rc = dev_alloc(&c->d_single, bw)) || (rc = dev_alloc(&c->d_trio, bw)) || (rc = dev_alloc(&c->d_good, bw)) ||
-        (rc = dev_alloc(&c->d_flagged, bw)) || (rc = dev_alloc(&c->d_tile_new, nt)) || (rc = dev_alloc(&c->d_tile_base, nt)) ||
-        (rc = dev_alloc(&c->d_scan_tmp, scan_tmp_words(nt))))
+    if ((rc = c->contigs_buf.reserve(c->contigs.size())) || (rc = c->tiles_buf.reserve(nt)) || (rc = c->single_buf.reserve(bw)) ||
+        (rc = c->trio_buf.reserve(bw)) || (rc = c->good_buf.reserve(bw)) || (rc = c->flagged_buf.reserve(bw)) ||
+        (rc = c->tile_new_buf.reserve(nt)) || (rc = c->tile_base_buf.reserve(nt)) || (rc = c->scan_tmp_buf.reserve(scan_tmp_words(nt))))
         return rc;
+    c->d_contigs = c->contigs_buf.p; c->d_tiles = c->tiles_buf.p;
+    c->d_single = c->single_buf.p; c->d_trio = c->trio_buf.p; c->d_good = c->good_buf.p; c->d_flagged = c->flagged_buf.p;
+    c->d_tile_new = c->tile_new_buf.p; c->d_tile_base = c->tile_base_buf.p; c->d_scan_tmp = c->scan_tmp_buf.p;
     CU(cudaMemcpyAsync(c->d_contigs, c->contigs.data(), c->contigs.size() * sizeof(Contig), cudaMemcpyHostToDevice, c->st));
     CU(cudaMemcpyAsync(c->d_tiles, c->tiles.data(), nt * sizeof(Tile), cudaMemcpyHostToDevice, c->st));
     CU(cudaStreamSynchronize(c->st));
@@ -419,9 +445,9 @@ static void parse_fasta(const uint8_t* fa, size_t n, int k, int e, ParsedFasta& 
 }
 
 static int alloc_image(lhgt_ctx* c, uint64_t words) {
-    int rc = dev_alloc(&c->d_image, words);
+    int rc = c->image_buf.reserve(words);
     if (rc) return rc;
-    c->image_words = words; c->image_owned = true;
+    c->d_image = c->image_buf.p; c->image_words = words; c->image_owned = true;
     return 0;
 }
 
@@ -640,13 +666,11 @@ static int index_reads(lhgt_ctx* c, Reads& r, int last_byte, uint64_t tail_start
     uint64_t tiles = fastq_index_tiles(r.n);
     r.nrec = 0; r.seq_bases = 0;
     if (r.n == 0) { r.ready = true; return 0; }
-    uint32_t *d_cnt = nullptr, *d_base = nullptr, *d_tmp = nullptr;
     int rc = 0;
-    if ((rc = dev_alloc(&d_cnt, tiles)) || (rc = dev_alloc(&d_base, tiles)) || (rc = dev_alloc(&d_tmp, scan_tmp_words(tiles)))) {
-        dev_free(d_cnt); dev_free(d_base); dev_free(d_tmp);
+    if ((rc = c->fq_cnt_buf.reserve(tiles)) || (rc = c->fq_base_buf.reserve(tiles)) || (rc = c->fq_tmp_buf.reserve(scan_tmp_words(tiles))))
         return rc;
-    }
-    auto cleanup = [&]() { dev_free(d_cnt); dev_free(d_base); dev_free(d_tmp); };
+    uint32_t *d_cnt = c->fq_cnt_buf.p, *d_base = c->fq_base_buf.p, *d_tmp = c->fq_tmp_buf.p;
+    auto cleanup = [&]() {};
     {
         Span sp(c, 0);
         c->launches += launch_fastq_index(r.d_fq, r.n, d_cnt, d_base, d_tmp, nullptr, nullptr, 0, 0, c->st);
@@ -660,7 +684,8 @@ static int index_reads(lhgt_ctx* c, Reads& r, int last_byte, uint64_t tail_start
     bool open_tail = last_byte != '\n';
     uint64_t lines = newlines + (open_tail ? 1 : 0);
     r.nrec = (lines + 2) / 4;                                      // lines 1, 5, 9, ... are sequences
-    if ((rc = dev_alloc(&r.d_start, r.nrec)) || (rc = dev_alloc(&r.d_end, r.nrec))) { cleanup(); return rc; }
+    if ((rc = r.start_buf.reserve(r.nrec)) || (rc = r.end_buf.reserve(r.nrec))) { cleanup(); return rc; }
+    r.d_start = r.start_buf.p; r.d_end = r.end_buf.p;
     cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), c->st);
     {
         Span sp(c, 0);
@@ -692,9 +717,9 @@ extern "C" int lhgt_reads_upload(lhgt_ctx* c, int mate, const uint8_t* fq, uint6
     CU(cudaSetDevice(c->device));
     Reads& r = c->reads[mate];
     drop_reads(r);
-    uint8_t* d = nullptr;
-    int rc = dev_alloc(&d, n + 64);
+    int rc = r.fq_buf.reserve(n + 64);
     if (rc) return rc;
+    uint8_t* d = r.fq_buf.p;
     r.d_fq = d; r.owned = true; r.n = n;
     if (n) CU(cudaMemcpyAsync(d, fq, n, cudaMemcpyHostToDevice, c->st));
     uint64_t tail = 0;
@@ -794,6 +819,10 @@ static uint64_t bin_pool_limit_entries() {
     return (mb << 20) / 4;
 }
 
+// A canonical hash is the smaller of two (forward, reverse-complement) near-uniform 32-bit values, so its
+// density falls linearly: the stream of the b-th of n equal table slices receives (2(n-b)-1)/n^2 of the hashes.
+static double stream_share(int b, int nbins) { return (2.0 * (nbins - b) - 1.0) / ((double)nbins * nbins); }
+
 static int s1_binned(lhgt_ctx* c, Reads& r, uint64_t byte_budget) {
     uint64_t table_bytes = c->count_words * 4;
     BinP bp{};
@@ -802,25 +831,35 @@ static int s1_binned(lhgt_ctx* c, Reads& r, uint64_t byte_budget) {
     if (c->s1_mode == 2) bp.log2 = 4;                                // forced (tests at small k)
     bp.shift = c->k - bp.log2;
     int nbins = 1 << bp.log2;
-    bp.bucket_cap = (uint32_t)(2 * kBinWarpsHost * 128 * c->e / nbins);   // twice the expected fill of one round
-    // hashes one record contributes on average (sampled fraction included), +12.5 % for skew between streams
+    // shared-memory buckets: one round of a CTA hashes kBinWarpsHost x 128 positions; 1.5x the expected share + 64
+    double round_hashes = (double)kBinWarpsHost * 128 * c->e;
+    bp.boff[0] = 0;
+    for (int b = 0; b < kMaxBins; ++b)
+        bp.boff[b + 1] = bp.boff[b] + (b < nbins ? (uint32_t)(1.5 * round_hashes * stream_share(b, nbins)) + 64 : 0);
+    // hashes one record contributes on average (sampled fraction included)
     double avg_len = r.nrec ? (double)r.seq_bases / (double)r.nrec : 0.0;
     double per_rec = std::max(1.0, avg_len - c->k + 1) * c->e * std::min(1.0, c->d_sample_bits ? c->ratio / 100.0 : 1.0);
-    uint64_t want = (uint64_t)(per_rec * (double)r.nrec * 1.125) + (uint64_t)nbins * 4096;
-    uint64_t limit = bin_pool_limit_entries();
-    uint64_t total = std::min(want, limit);
-    uint64_t cap = (total / nbins + 7) & ~(uint64_t)7;
-    if (cap > 0xfffffff8ull / 2) cap = 0xfffffff8ull / 2;            // cursors are 32-bit and may run past cap
-    if (c->bin_pool_entries < cap * nbins) {
+    const double slack = 1.0625;                                     // on top of each stream's expected share
+    uint64_t want = (uint64_t)(per_rec * (double)r.nrec * slack) + (uint64_t)nbins * 8192;
+    uint64_t total = std::min(want, bin_pool_limit_entries());
+    if (total > 0xf0000000ull) total = 0xf0000000ull;                // offsets and cursors are 32-bit
+    if (total < (uint64_t)nbins * 16384) total = (uint64_t)nbins * 16384;
+    if (c->bin_pool_entries < total) {
         dev_free(c->d_bin_pool);
         c->bin_pool_entries = 0;
-        int rc = dev_alloc(&c->d_bin_pool, cap * nbins);
+        int rc = dev_alloc(&c->d_bin_pool, total + 8 * kMaxBins);
         if (rc) return rc;
-        c->bin_pool_entries = cap * nbins;
+        c->bin_pool_entries = total;
     }
     if (!c->d_bin_cursor) { int rc = dev_alloc(&c->d_bin_cursor, kMaxBins); if (rc) return rc; }
-    bp.pool = c->d_bin_pool; bp.cursor = c->d_bin_cursor; bp.cap = (uint32_t)cap;
-    uint64_t per_chunk = std::max<uint64_t>(1, (uint64_t)((double)cap * nbins / 1.125 / per_rec));
+    bp.pool = c->d_bin_pool; bp.cursor = c->d_bin_cursor;
+    uint64_t usable = total - (uint64_t)nbins * 8192;
+    bp.off[0] = 0;
+    for (int b = 0; b < kMaxBins; ++b) {
+        uint64_t region = b < nbins ? ((uint64_t)((double)usable * stream_share(b, nbins)) + 8192) & ~(uint64_t)7 : 0;
+        bp.off[b + 1] = (uint32_t)(bp.off[b] + region);
+    }
+    uint64_t per_chunk = std::max<uint64_t>(1, (uint64_t)((double)usable / slack / per_rec));
     for (uint64_t lo = 0; lo < r.nrec; lo += per_chunk) {
         uint64_t hi = std::min(r.nrec, lo + per_chunk);
         CU(cudaMemsetAsync(c->d_bin_cursor, 0, kMaxBins * sizeof(uint32_t), c->st));

@@ -55,25 +55,49 @@ __device__ __forceinline__ uint32_t hash_of(const KmerWin& kw, const HashP& hp, 
     return min(f, r);
 }
 
-// One warp turns `len` ASCII bytes into four plane arrays of `nw+1` words (last one zero).
-template <int STRIDE>
-__device__ __forceinline__ void warp_pack(const uint8_t* __restrict__ src, int len, uint32_t* planes, int lane) {
-    int nw = (len + 31) >> 5;
-    for (int w = 0; w < nw; ++w) {
-        int p = w * 32 + lane;
-        uint32_t bits = p < len ? base_bits(src[p]) : 0u;
-        uint32_t b0 = __brev(__ballot_sync(kFull, bits & 1u));
-        uint32_t b1 = __brev(__ballot_sync(kFull, bits & 2u));
-        uint32_t b2 = __brev(__ballot_sync(kFull, bits & 4u));
-        uint32_t b3 = __brev(__ballot_sync(kFull, bits & 8u));
-        if (lane == 0) {
-            planes[w] = b0; planes[STRIDE + w] = b1; planes[2 * STRIDE + w] = b2; planes[3 * STRIDE + w] = b3;
-        }
-    }
-    if (lane == 0) {
-        planes[nw] = 0; planes[STRIDE + nw] = 0; planes[2 * STRIDE + nw] = 0; planes[3 * STRIDE + nw] = 0;
-    }
-    __syncwarp();
+// ---- rolling pack + hash: no shared-memory planes ------------------------------------------------------------
+// A warp walks a read 32 bases at a time.  Word w of the four planes (bit p%32 of word p/32 = position p: ballots
+// deliver exactly that) lives in four warp-uniform registers; the 32-position chunk c needs words c and c+1, and
+// lane l's window (positions 32c+l ...) is one funnel shift.  In this little-endian window position j+z sits at
+// bit z, which is the form the reverse-complement hash wants; one BREV per plane gives the forward form
+// (the two use the same masks).  Positions whose window runs past the read see validity bits 0.
+struct Planes { uint32_t p0, p1, p2, pv; };
+
+__device__ __forceinline__ void fill_base_lut(uint8_t* lut) {           // call with all threads, then __syncthreads
+    for (int c = threadIdx.x; c < 256; c += blockDim.x) lut[c] = (uint8_t)base_bits((uint32_t)c);
+}
+
+__device__ __forceinline__ Planes pack_word(uint32_t ch, const uint8_t* lut) {
+    uint32_t bits = lut[ch];
+    Planes w;
+    w.p0 = __ballot_sync(kFull, bits & 1u);
+    w.p1 = __ballot_sync(kFull, bits & 2u);
+    w.p2 = __ballot_sync(kFull, bits & 4u);
+    w.pv = __ballot_sync(kFull, bits & 8u);
+    return w;
+}
+
+struct LeWin {                       // per-lane k-mer window, both orientations
+    uint32_t w2, wx0, wx1;           // forward:   W2, W0^W2, W1^W2   (base z at bit k-1-z)
+    uint32_t n2, nx0, x1;            // mirrored: ~L2, ~(L0^L2), L1^L2 (base z at bit z; masked by kmask at the end)
+    bool valid;
+};
+
+__device__ __forceinline__ LeWin le_window(const Planes& lo, const Planes& hi, int lane, const HashP& hp) {
+    uint32_t l0 = __funnelshift_r(lo.p0, hi.p0, lane), l1 = __funnelshift_r(lo.p1, hi.p1, lane);
+    uint32_t l2 = __funnelshift_r(lo.p2, hi.p2, lane), lv = __funnelshift_r(lo.pv, hi.pv, lane);
+    LeWin k;
+    k.valid = (lv & hp.kmask) == hp.kmask;
+    uint32_t x0 = l0 ^ l2, x1 = l1 ^ l2;
+    k.n2 = ~l2; k.nx0 = ~x0; k.x1 = x1;
+    k.w2 = __brev(l2) >> hp.shr; k.wx0 = __brev(x0) >> hp.shr; k.wx1 = __brev(x1) >> hp.shr;
+    return k;
+}
+
+__device__ __forceinline__ uint32_t le_hash(const LeWin& k, const HashP& hp, int i) {
+    uint32_t f = k.w2 ^ (k.wx0 & hp.m0[i]) ^ (k.wx1 & hp.m1[i]);
+    uint32_t r = (k.n2 ^ (k.nx0 & hp.m0[i]) ^ (k.x1 & hp.m1[i])) & hp.kmask;
+    return min(f, r);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -99,6 +123,22 @@ __device__ __forceinline__ void bump(uint32_t* count, uint32_t h, uint32_t seen)
         if (old == seen) break;
         seen = old;
     }
+}
+
+// One increment attempt for each of N probes, all compare-and-swaps issued before any result is looked at (a
+// dependent CAS loop per probe would serialise N L2 round trips); the rare losers finish in bump()'s loop.
+template <int N>
+__device__ __forceinline__ void bump_batch(uint32_t* count, const uint32_t (&h)[N], uint32_t (&seen)[N], const bool (&ok)[N]) {
+    uint32_t got[N];
+#pragma unroll
+    for (int q = 0; q < N; ++q) {
+        int sh = (h[q] & 15u) * 2;
+        got[q] = seen[q];
+        if (ok[q] && ((seen[q] >> sh) & 3u) < 3u) got[q] = atomicCAS(count + (h[q] >> 4), seen[q], seen[q] + (1u << sh));
+    }
+#pragma unroll
+    for (int q = 0; q < N; ++q)
+        if (got[q] != seen[q]) bump(count, h[q], got[q]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -358,7 +398,6 @@ int launch_index_build(const uint8_t* seq, const Contig* contigs, const Tile* ti
 // packed into shared memory by ballots; each lane hashes positions lane, lane+32, ... and issues all
 // its table loads before the first compare-and-swap so ~12 independent sectors per lane are in flight.
 // ------------------------------------------------------------------------------------------------
-constexpr int kReadPlane = (kMaxReadLen + 31) / 32 + 2;   // 18 words
 constexpr int kS1Warps = 8, kS1Unroll = 4;
 
 __device__ __forceinline__ bool is_sampled(const uint32_t* __restrict__ sample_bits, uint64_t ordinal) {
@@ -372,10 +411,11 @@ __global__ void __launch_bounds__(kS1Warps * 32, 4) s1_count_kernel(
     const uint8_t* __restrict__ fq, const uint64_t* __restrict__ rec_start, const uint64_t* __restrict__ rec_end,
     uint64_t nrec, uint64_t budget, const uint32_t* __restrict__ sample_bits, uint64_t ordinal_base, HashP hp,
     uint32_t* __restrict__ count, unsigned long long* __restrict__ n_sampled, int* __restrict__ err) {
-    __shared__ uint32_t planes_all[kS1Warps][4 * kReadPlane];
+    __shared__ uint8_t lut[256];
     const int e = E ? E : hp.e;
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t* planes = planes_all[warp];
+    fill_base_lut(lut);
+    __syncthreads();
     unsigned long long mine = 0;
     uint64_t stride = (uint64_t)gridDim.x * kS1Warps;
     for (uint64_t r = (uint64_t)blockIdx.x * kS1Warps + warp; r < nrec; r += stride) {
@@ -388,33 +428,27 @@ __global__ void __launch_bounds__(kS1Warps * 32, 4) s1_count_kernel(
         ++mine;
         int np = len - hp.k + 1;
         if (np <= 0) continue;
-        warp_pack<kReadPlane>(fq + start, len, planes, lane);
-        for (int j0 = 0; j0 < np; j0 += 32 * kS1Unroll) {
-            uint32_t h[kS1Unroll][E ? E : kMaxE];
-            uint32_t seen[kS1Unroll][E ? E : kMaxE];
-            bool ok[kS1Unroll];
+        const uint8_t* src = fq + start;
+        int nch = (np + 31) >> 5;
+        Planes prev = pack_word(lane < len ? src[lane] : 0u, lut);
+        uint32_t chn = 32 + lane < len ? src[32 + lane] : 0u;
+        for (int w = 1; w <= nch; ++w) {
+            Planes cur = pack_word(chn, lut);
+            int pn = (w + 1) * 32 + lane;
+            chn = pn < len ? src[pn] : 0u;
+            LeWin kw = le_window(prev, cur, lane, hp);
+            prev = cur;
+            uint32_t h[E ? E : kMaxE], seen[E ? E : kMaxE];
+            bool ok[E ? E : kMaxE];
 #pragma unroll
-            for (int u = 0; u < kS1Unroll; ++u) {
-                int j = j0 + u * 32 + lane;
-                ok[u] = j < np;
-                KmerWin kw = make_win<kReadPlane>(planes, ok[u] ? j : 0, hp);
-                ok[u] = ok[u] && kw.valid;
-#pragma unroll
-                for (int i = 0; i < (E ? E : kMaxE); ++i)
-                    if (i < e) h[u][i] = hash_of(kw, hp, i);
+            for (int i = 0; i < (E ? E : kMaxE); ++i) {
+                ok[i] = i < e && kw.valid;
+                h[i] = i < e ? le_hash(kw, hp, i) : 0u;
+                seen[i] = 0u;
+                if (ok[i]) seen[i] = ld_table(count + (h[i] >> 4));
             }
-#pragma unroll
-            for (int u = 0; u < kS1Unroll; ++u)
-#pragma unroll
-                for (int i = 0; i < (E ? E : kMaxE); ++i)
-                    if (i < e && ok[u]) seen[u][i] = ld_table(count + (h[u][i] >> 4));
-#pragma unroll
-            for (int u = 0; u < kS1Unroll; ++u)
-#pragma unroll
-                for (int i = 0; i < (E ? E : kMaxE); ++i)
-                    if (i < e && ok[u]) bump(count, h[u][i], seen[u][i]);
+            bump_batch<(E ? E : kMaxE)>(count, h, seen, ok);
         }
-        __syncwarp();
     }
     if (lane == 0 && mine) atomicAdd(n_sampled, mine);
 }
@@ -465,68 +499,107 @@ __global__ void __launch_bounds__(kBinWarps * 32, 3) s1_bin_kernel(
     uint64_t rec_lo, uint64_t rec_hi, uint64_t budget, const uint32_t* __restrict__ sample_bits, uint64_t ordinal_base,
     HashP hp, BinP bp, uint32_t* __restrict__ count, unsigned long long* __restrict__ n_sampled, int* __restrict__ err) {
     extern __shared__ uint32_t dyn[];
-    __shared__ uint32_t planes_all[kBinWarps][4 * kReadPlane];
     __shared__ uint32_t cnt[kMaxBins];
-    uint32_t* buckets = dyn;                                  // [nbins][bucket_cap]
+    __shared__ uint2 bnd[kMaxBins];                           // bucket b = dyn[bnd[b].x .. bnd[b].y)
+    __shared__ uint8_t lut[256];
+    uint32_t* buckets = dyn;
     const int e = E ? E : hp.e;
     const int nbins = 1 << bp.log2;
-    const uint32_t bcap = bp.bucket_cap;
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t* planes = planes_all[warp];
-    if (threadIdx.x < kMaxBins) cnt[threadIdx.x] = 0;
+    if (threadIdx.x < kMaxBins) { bnd[threadIdx.x] = make_uint2(bp.boff[threadIdx.x], bp.boff[threadIdx.x + 1]); cnt[threadIdx.x] = 0; }
+    fill_base_lut(lut);
+    __syncthreads();
     unsigned long long mine = 0;
-    uint64_t stride = (uint64_t)gridDim.x * kBinWarps;
-    uint64_t r = rec_lo + (uint64_t)blockIdx.x * kBinWarps + warp;
-    int np = 0, j0 = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * kBinWarps;
+    auto next_sampled = [&](uint64_t q) {                     // warp-uniform
+        while (q < rec_hi && !is_sampled(sample_bits, q + ordinal_base)) q += stride;
+        return q;
+    };
+    // The candidate record (next sampled one of this warp) is always one step ahead: its offsets are loaded when the
+    // current read is accepted, its first 64 bases after the current read's first chunk, so a warp never sits
+    // through the start -> end -> bytes load chain between reads.
+    uint64_t r = next_sampled(rec_lo + (uint64_t)blockIdx.x * kBinWarps + warp);
+    uint64_t cs = 0, ce = 0;
+    if (r < rec_hi) { cs = rec_start[r]; ce = rec_end[r]; }
+    uint32_t pb0 = 0, pb1 = 0;
+    bool pb_ready = false;
+    const uint8_t* src = fq;
+    int len = 0, w = 0, nch = 0;                              // current read: length, next word to pack, hash chunks
+    uint32_t chn = 0;                                         // this lane's byte of word w, loaded one chunk ahead
+    Planes prev{0, 0, 0, 0};
     bool have = false;
     for (;;) {
-        while (!have && r < rec_hi) {                         // next read of this warp that has k-mers to count
-            uint64_t start = rec_start[r];
-            bool take = start <= budget && is_sampled(sample_bits, r + ordinal_base);   // Q15
-            if (take) {
-                uint64_t len64 = rec_end[r] - start;
-                if (len64 > (uint64_t)kMaxReadLen) { if (lane == 0) atomicExch(err, 1); take = false; }
-                else {
-                    ++mine;
-                    np = (int)len64 - hp.k + 1;
-                    if (np > 0) { warp_pack<kReadPlane>(fq + start, (int)len64, planes, lane); have = true; j0 = 0; }
-                }
-            }
-            if (!have) r += stride;
+        while (!have && r < rec_hi) {                         // turn the candidate into the current read
+            uint64_t start = cs, len64 = ce - cs;
+            uint32_t b0 = pb0, b1 = pb1;
+            bool fetched = pb_ready;
+            r = next_sampled(r + stride);
+            if (r < rec_hi) { cs = rec_start[r]; ce = rec_end[r]; }
+            pb_ready = false;
+            if (start > budget) continue;                     // Q15
+            if (len64 > (uint64_t)kMaxReadLen) { if (lane == 0) atomicExch(err, 1); continue; }
+            ++mine;
+            len = (int)len64;
+            int np = len - hp.k + 1;
+            if (np <= 0) continue;
+            src = fq + start;
+            if (!fetched) { b0 = lane < len ? src[lane] : 0u; b1 = 32 + lane < len ? src[32 + lane] : 0u; }
+            nch = (np + 31) >> 5;
+            prev = pack_word(b0, lut);
+            chn = b1;
+            w = 1;
+            have = true;
         }
         if (!__syncthreads_or(have)) break;                   // also: buckets and cnt are free again
-        if (have) {
-#pragma unroll
-            for (int u = 0; u < kS1Unroll; ++u) {
-                int j = j0 + u * 32 + lane;
-                bool ok = j < np;
-                KmerWin kw = make_win<kReadPlane>(planes, ok ? j : 0, hp);
-                ok = ok && kw.valid;
+#pragma unroll 1
+        for (int it = 0; it < kS1Unroll && have; ++it) {      // chunk w-1 = words w-1 (prev) and w (cur)
+            Planes cur = pack_word(chn, lut);
+            int pn = (w + 1) * 32 + lane;
+            chn = pn < len ? src[pn] : 0u;
+            LeWin kw = le_window(prev, cur, lane, hp);
+            if (kw.valid) {
 #pragma unroll
                 for (int i = 0; i < (E ? E : kMaxE); ++i)
-                    if (i < e && ok) {
-                        uint32_t h = hash_of(kw, hp, i);
+                    if (i < e) {
+                        uint32_t h = le_hash(kw, hp, i);
                         uint32_t b = h >> bp.shift;
-                        uint32_t slot = atomicAdd(&cnt[b], 1u);
-                        if (slot < bcap) buckets[b * bcap + slot] = h;
+                        uint2 lim = bnd[b];
+                        uint32_t slot = lim.x + atomicAdd(&cnt[b], 1u);
+                        if (slot < lim.y) buckets[slot] = h;
                         else bump_direct(count, h);           // bucket full: rare, exact either way
                     }
             }
-            j0 += 32 * kS1Unroll;
-            if (j0 >= np) { have = false; r += stride; }
+            prev = cur;
+            if (++w > nch) { have = false; }
+            if (!pb_ready && r < rec_hi) {                    // candidate's first two words, consumed a read later
+                uint64_t nlen = ce - cs;
+                const uint8_t* nsrc = fq + cs;
+                pb0 = (uint64_t)lane < nlen ? nsrc[lane] : 0u;
+                pb1 = (uint64_t)(32 + lane) < nlen ? nsrc[32 + lane] : 0u;
+                pb_ready = true;
+            }
         }
         __syncthreads();
-        for (int b = warp; b < nbins; b += kBinWarps) {       // flush: one coalesced run per stream
-            uint32_t n = min(cnt[b], bcap);
+        for (int q = 0; q < 2; ++q) {                         // flush: one coalesced run per stream; streams b and
+            int b = q == 0 ? warp : nbins - 1 - warp;         // nbins-1-b together carry an equal share (stream_share)
+            if (b >= nbins || (q == 1 && b < kBinWarps)) continue;
+            uint32_t b0 = bnd[b].x;
+            uint32_t n = min(cnt[b], bnd[b].y - b0);
             if (n) {
                 uint32_t g = 0;
                 if (lane == 0) g = atomicAdd(bp.cursor + b, n);
                 g = __shfl_sync(kFull, g, 0);
-                uint32_t* dst = bp.pool + (size_t)b * bp.cap;
-                for (uint32_t x = lane; x < n; x += 32) {
-                    uint32_t h = buckets[b * bcap + x];
-                    if (g + x < bp.cap) dst[g + x] = h;
-                    else bump_direct(count, h);               // stream region full
+                uint32_t* dst = bp.pool + bp.off[b];
+                uint32_t cap = bp.off[b + 1] - bp.off[b];
+                if (g + n <= cap) {
+                    dst += g;
+                    for (uint32_t x = lane; x < n; x += 32) dst[x] = buckets[b0 + x];
+                } else {
+                    for (uint32_t x = lane; x < n; x += 32) {
+                        uint32_t h = buckets[b0 + x];
+                        if (g + x < cap) dst[g + x] = h;
+                        else bump_direct(count, h);           // stream region full
+                    }
                 }
             }
             __syncwarp();
@@ -536,43 +609,96 @@ __global__ void __launch_bounds__(kBinWarps * 32, 3) s1_bin_kernel(
     if (lane == 0 && mine) atomicAdd(n_sampled, mine);
 }
 
-__device__ __forceinline__ void ld_stream8(const uint32_t* p, uint32_t v[8]) {
-    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(p));
+// ---- TMA (cp.async.bulk) + mbarrier plumbing for the stream reader ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LHGT_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LHGT_DONE;\n"
+        "bra LHGT_WAIT;\n"
+        "LHGT_DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on `bar`; the stream is read once: evict-first in L2
+__device__ __forceinline__ void bulk_load_evict_first(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
 }
 
-constexpr int kApplyThreads = 256, kApplyVec = 2;            // 16 probes in flight per thread
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
-__global__ void __launch_bounds__(kApplyThreads) s1_apply_kernel(const uint32_t* __restrict__ stream,
-                                                                 const uint32_t* __restrict__ cursor, uint32_t cap,
-                                                                 uint32_t* __restrict__ count) {
-    uint32_t n = min(*cursor, cap);
-    uint32_t n8 = n >> 3;
-    uint32_t tid = blockIdx.x * kApplyThreads + threadIdx.x, nthreads = gridDim.x * kApplyThreads;
-    for (uint32_t base = tid; base < n8; base += nthreads * kApplyVec) {
-        uint32_t h[kApplyVec][8], seen[kApplyVec][8];
-        bool ok[kApplyVec];
+// Phase B.  A CTA walks tiles of 2048 hashes of one stream.  An elected thread keeps a ring of TMA bulk copies in
+// flight (UBLKCP; "full" mbarriers count the bytes landed, "empty" mbarriers count the warps done with a slot), so
+// the stream never occupies load scoreboards and every thread spends its own on the 8 table probes it issues per
+// tile.  No CTA-wide barrier inside the loop.
+constexpr int kApplyThreads = 256, kApplyPer = 8, kApplyTile = kApplyThreads * kApplyPer, kApplyStages = 4;
+constexpr size_t kApplySmem = (size_t)kApplyStages * kApplyTile * sizeof(uint32_t) + 2 * kApplyStages * sizeof(uint64_t);
+
+__global__ void __launch_bounds__(kApplyThreads, 4) s1_apply_kernel(const uint32_t* __restrict__ stream,
+                                                                    const uint32_t* __restrict__ cursor, uint32_t cap,
+                                                                    uint32_t* __restrict__ count) {
+    extern __shared__ __align__(128) uint32_t apply_smem[];
+    uint32_t* tiles = apply_smem;                                              // [kApplyStages][kApplyTile]
+    uint64_t* full = reinterpret_cast<uint64_t*>(apply_smem + kApplyStages * kApplyTile);
+    uint64_t* empty = full + kApplyStages;
+    const uint32_t n = min(*cursor, cap);
+    const uint32_t ntiles = (n + kApplyTile - 1) / kApplyTile;
+    if (blockIdx.x >= ntiles) return;
+    const uint32_t mine = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;    // tiles blockIdx.x + i * gridDim.x
+    const int lane = threadIdx.x & 31;
+    auto issue = [&](uint32_t j) {                                             // thread 0 only
+        uint32_t stg = j % kApplyStages;
+        if (j >= (uint32_t)kApplyStages) mbar_wait(&empty[stg], ((j / kApplyStages) - 1u) & 1u);   // previous tenant drained
+        uint32_t first = (blockIdx.x + j * gridDim.x) * kApplyTile;
+        uint32_t bytes = (min((uint32_t)kApplyTile, n - first) * 4u + 15u) & ~15u;   // regions are multiples of 8 entries
+        mbar_expect_tx(&full[stg], bytes);
+        bulk_load_evict_first(tiles + stg * kApplyTile, stream + first, bytes, &full[stg]);
+    };
+    if (threadIdx.x == 0) {
+        for (int s2 = 0; s2 < kApplyStages; ++s2) { mbar_init(&full[s2], 1); mbar_init(&empty[s2], kApplyThreads / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (uint32_t j = 0; j < min(mine, (uint32_t)kApplyStages - 1); ++j) issue(j);
+    }
+    __syncthreads();
+    for (uint32_t i = 0; i < mine; ++i) {
+        if (threadIdx.x == 0 && i + kApplyStages - 1 < mine) issue(i + kApplyStages - 1);
+        uint32_t stg = i % kApplyStages;
+        mbar_wait(&full[stg], (i / kApplyStages) & 1u);
+        uint32_t first = (blockIdx.x + i * gridDim.x) * kApplyTile;
+        uint32_t valid = min((uint32_t)kApplyTile, n - first);
+        const uint32_t* tile = tiles + stg * kApplyTile;
+        uint32_t h[kApplyPer], seen[kApplyPer];
+        bool ok[kApplyPer];
 #pragma unroll
-        for (int v = 0; v < kApplyVec; ++v) {
-            uint32_t at = base + v * nthreads;
-            ok[v] = at < n8;
-            if (ok[v]) ld_stream8(stream + (size_t)at * 8, h[v]);
+        for (int q = 0; q < kApplyPer; ++q) {
+            uint32_t x = threadIdx.x + q * kApplyThreads;
+            ok[q] = x < valid;
+            h[q] = tile[x];
         }
 #pragma unroll
-        for (int v = 0; v < kApplyVec; ++v)
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-                if (ok[v]) seen[v][q] = ld_table(count + (h[v][q] >> 4));
-#pragma unroll
-        for (int v = 0; v < kApplyVec; ++v)
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-                if (ok[v]) bump(count, h[v][q], seen[v][q]);
+        for (int q = 0; q < kApplyPer; ++q)
+            if (ok[q]) seen[q] = ld_table(count + (h[q] >> 4));
+        __syncwarp();                                                          // every lane's tile words are in registers
+        if (lane == 0) mbar_arrive(&empty[stg]);
+        bump_batch<kApplyPer>(count, h, seen, ok);
     }
-    if (tid < (n & 7u)) bump_direct(count, stream[(n8 << 3) + tid]);
 }
 
-size_t s1_bin_smem_bytes(const BinP& bp) { return ((size_t)bp.bucket_cap << bp.log2) * sizeof(uint32_t); }
+size_t s1_bin_smem_bytes(const BinP& bp) { return (size_t)bp.boff[1 << bp.log2] * sizeof(uint32_t); }
 
 template <int E>
 static cudaError_t s1_bin_launch(const uint8_t* fq, const uint64_t* rs, const uint64_t* re, uint64_t lo, uint64_t hi, uint64_t budget,
@@ -593,8 +719,9 @@ int launch_s1_binned(const uint8_t* fq, const uint64_t* rec_start, const uint64_
     if (rec_hi <= rec_lo) return 0;
     int nbins = 1 << bp.log2;
     if (phase == 1) {
+        if (cudaFuncSetAttribute(s1_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kApplySmem) != cudaSuccess) return -1;
         for (int b = 0; b < nbins; ++b)
-            s1_apply_kernel<<<kSMs * 8, kApplyThreads, 0, st>>>(bp.pool + (size_t)b * bp.cap, bp.cursor + b, bp.cap, count);
+            s1_apply_kernel<<<kSMs * 4, kApplyThreads, kApplySmem, st>>>(bp.pool + bp.off[b], bp.cursor + b, bp.off[b + 1] - bp.off[b], count);
         return nbins;
     }
     cudaError_t rc;
@@ -930,25 +1057,30 @@ int s3_warps_per_block() { return kS3Warps; }
 int s3_grid_blocks(int) { return kSMs * 4; }
 
 template <int E>
-__device__ __forceinline__ int s3_scan_mate(const uint8_t* __restrict__ src, int len, uint32_t* planes, const HashP& hp,
+__device__ __forceinline__ int s3_scan_mate(const uint8_t* __restrict__ src, int len, const uint8_t* lut, const HashP& hp,
                                             const uint32_t* __restrict__ prefilter, const uint32_t* __restrict__ peak_kmer,
                                             uint32_t* __restrict__ cands, int n_listed, int lane) {
     const int e = E ? E : hp.e;
     int np = len - hp.k + 1;
     if (np <= 0) return n_listed;
-    warp_pack<kReadPlane>(src, len, planes, lane);
-    for (int j0 = 0; j0 < np; j0 += 32) {
-        int j = j0 + lane;
-        bool ok = j < np;
-        KmerWin kw = make_win<kReadPlane>(planes, ok ? j : 0, hp);
-        ok = ok && kw.valid;
+    int nch = (np + 31) >> 5;
+    Planes prev = pack_word(lane < len ? src[lane] : 0u, lut);
+    uint32_t c1 = 32 + lane < len ? src[32 + lane] : 0u;      // bytes run two words ahead of the hashing
+    uint32_t c2 = 64 + lane < len ? src[64 + lane] : 0u;
+    for (int w = 1; w <= nch; ++w) {                          // chunk w-1: positions 32(w-1) + lane, ascending
+        Planes cur = pack_word(c1, lut);
+        c1 = c2;
+        int pn = (w + 2) * 32 + lane;
+        c2 = pn < len ? src[pn] : 0u;
+        LeWin kw = le_window(prev, cur, lane, hp);
+        prev = cur;
         uint32_t h[E ? E : kMaxE], pk[E ? E : kMaxE], fw[E ? E : kMaxE];
 #pragma unroll
         for (int i = 0; i < (E ? E : kMaxE); ++i)
             if (i < e) {
-                h[i] = hash_of(kw, hp, i);
+                h[i] = le_hash(kw, hp, i);
                 uint32_t slot = prefilter_slot(h[i]);
-                fw[i] = ok ? __ldg(prefilter + (slot >> 5)) >> (slot & 31) : 0u;
+                fw[i] = kw.valid ? __ldg(prefilter + (slot >> 5)) >> (slot & 31) : 0u;
             }
         bool any = false;
 #pragma unroll
@@ -1014,10 +1146,11 @@ __global__ void __launch_bounds__(kS3Warps * 32, 4) s3_pairs_kernel(
     uint64_t ordinal_base, HashP hp, const uint32_t* __restrict__ prefilter, const uint32_t* __restrict__ peak_kmer,
     const int32_t* __restrict__ loci, uint8_t* __restrict__ peak_filter, S3Scratch scratch,
     unsigned long long* __restrict__ n_sampled, int* __restrict__ err) {
-    __shared__ uint32_t planes_all[kS3Warps][4 * kReadPlane];
+    __shared__ uint8_t lut[256];
     const int e = E ? E : hp.e;
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t* planes = planes_all[warp];
+    fill_base_lut(lut);
+    __syncthreads();
     uint64_t gwarp = (uint64_t)blockIdx.x * kS3Warps + warp;
     uint32_t* cands = scratch.cands + gwarp * scratch.cands_stride;
     int32_t* tally = scratch.tally + gwarp * scratch.tally_stride;
@@ -1031,8 +1164,8 @@ __global__ void __launch_bounds__(kS3Warps * 32, 4) s3_pairs_kernel(
         else { b0 = tail_start; l2 = tail_len; }            // fq2 exhausted: std::getline leaves its last string
         if (l1 > (uint64_t)kMaxReadLen || l2 > (uint64_t)kMaxReadLen) { if (lane == 0) atomicExch(err, 1); continue; }
         ++mine;
-        int n_listed = s3_scan_mate<E>(fq1 + a0, (int)l1, planes, hp, prefilter, peak_kmer, cands, 0, lane);
-        n_listed = s3_scan_mate<E>(fq2 + b0, (int)l2, planes, hp, prefilter, peak_kmer, cands, n_listed, lane);
+        int n_listed = s3_scan_mate<E>(fq1 + a0, (int)l1, lut, hp, prefilter, peak_kmer, cands, 0, lane);
+        n_listed = s3_scan_mate<E>(fq2 + b0, (int)l2, lut, hp, prefilter, peak_kmer, cands, n_listed, lane);
         if (n_listed >= 6) {                                 // base_hits >= MIN_BASE_NUM (E:496)
             __syncwarp();
             if (lane == 0) s3_vote(cands, n_listed, e, loci, tally, peak_filter);

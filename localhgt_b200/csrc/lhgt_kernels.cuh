@@ -35,10 +35,10 @@ struct Contig {
 constexpr int kMaxBins = 16;           // S1 hash streams (table slices of 2^k / 4 / nbins bytes)
 
 struct BinP {                          // S1, binned form
-    uint32_t* pool;                    // [1 << log2][cap] hashes
-    uint32_t* cursor;                  // [1 << log2] entries appended so far (may run past cap: surplus was applied directly)
-    uint32_t cap;                      // entries per stream, multiple of 8
-    uint32_t bucket_cap;               // shared-memory bucket entries per stream per CTA
+    uint32_t* pool;                    // stream b occupies pool[off[b] .. off[b+1])
+    uint32_t* cursor;                  // [1 << log2] entries appended so far (may run past the region: surplus was applied directly)
+    uint32_t off[kMaxBins + 1];        // multiples of 8 entries
+    uint32_t boff[kMaxBins + 1];       // shared-memory bucket b of a CTA occupies dyn[boff[b] .. boff[b+1])
     int log2;                          // streams = 1 << log2 <= kMaxBins
     int shift;                         // stream of hash h = h >> shift  (k - log2)
 };

@@ -10,6 +10,11 @@ nproc >> $O/gpu.txt; free -g >> $O/gpu.txt
 for w in $what; do case $w in
 tests)
   timeout 1500 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu.log; tail -5 $O/pytest_gpu.log;;
+quick)
+  timeout 900 python -m pytest tests -m gpu -x -q -k "${TESTK:-s1 or streamed or k32 or large_run_properties}" > $O/pytest_quick.log 2>&1; echo "pytest rc=$?" >> $O/pytest_quick.log; tail -5 $O/pytest_quick.log;;
+benchq)
+  timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu ${BENCHARGS:-} > $O/bench_quick.json 2> $O/bench_quick.err; echo "bench rc=$?"; python -c "
+import json;d=json.load(open('$O/bench_quick.json'));print(d['value'],d['ms_per_step'],d['e2e']['value'],d['roofline']['stage_ms_per_step'])"; tail -5 $O/bench_quick.err;;
 smoke)
   timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke rc=$?" >> $O/smoke.log; tail -3 $O/smoke.log;;
 bench)
