@@ -401,7 +401,9 @@ def ours(args) -> None:
                 "what": "pinned host FASTQ x2 + index image -> HBM -> S1,S2,S3 -> interval text on host, through the C ABI"},
         "gpu_launches": int(launches), "roofline": roofline, "index_build": index_build,
         "result": {"interval_lines": len(text_resident.splitlines()), "interval_sha256": hashlib.sha256(text_resident).hexdigest()[:16],
-                   "planted_recovered": recovered(text_resident, meta), "peaks": shard.last_peaks},
+                   "planted_recovered": recovered(text_resident, meta), "peaks": shard.last_peaks,
+                   "sampled": shard.last_counts},
+        "host_wall_ms_last_step": {k: round(v, 3) for k, v in shard.last_wall_ms.items()},
     }
     if world == 1 and not args.no_cpu:
         try:

@@ -142,7 +142,9 @@ struct lhgt_ctx {
 
     Reads reads[2];
 
-    uint32_t* d_sample_bits = nullptr; bool sampling_set = false; double ratio = 100.0;
+    uint32_t* d_sample_bits = nullptr; bool sampling_set = false, sample_bits_on = false; double ratio = 100.0;
+    GlibcRand* rand_gen = nullptr; unsigned rand_seed = 0; long rand_skip = 0; uint64_t rand_filled = 0;
+    DevBuf<uint32_t> rand_m_buf;                 // rand() % 100000 of draws skip .. skip + rand_filled - 1
     uint64_t ordinal_base = 0;               // records that precede this context's shard in the whole sample
 
     uint32_t* d_cands = nullptr; int32_t* d_tally = nullptr; S3Scratch scratch{};
@@ -324,6 +326,7 @@ extern "C" void lhgt_destroy(lhgt_ctx* c) {
     drop_index(c, true);
     dev_free(c->d_count); dev_free(c->d_peak_kmer); dev_free(c->d_prefilter);
     dev_free(c->d_loci); dev_free(c->d_filter); dev_free(c->d_sample_bits);
+    c->rand_m_buf.release(); delete c->rand_gen;
     dev_free(c->d_cands); dev_free(c->d_tally); dev_free(c->d_counter); dev_free(c->d_err);
     dev_free(c->d_bin_pool); dev_free(c->d_bin_cursor);
     if (c->own) cudaStreamDestroy(c->own);
@@ -769,22 +772,47 @@ extern "C" int lhgt_set_sampling(lhgt_ctx* c, double ratio, unsigned seed, long 
     CU(cudaSetDevice(c->device));
     c->ratio = ratio;
     c->sampling_set = true;
-    dev_free(c->d_sample_bits);
+    c->sample_bits_on = false;
     if (ratio >= 100) return 0;                                    // every drawn value is <= 99.999 (E:1336)
     uint64_t need = std::max(c->reads[0].nrec, c->reads[1].nrec) + c->ordinal_base;
     need = std::min<uint64_t>(need, kRandomArray);
-    size_t words = (size_t)(kRandomArray + 31) / 32;
-    std::vector<uint32_t> bits(words, 0u);
-    GlibcRand g(seed);
-    for (long i = 0; i < rand_skip; ++i) g.next();
-    for (uint64_t i = 0; i < need; ++i) {
-        float r = (float)((g.next() % 100000) / 1000.0);           // E:1336-1337
-        if ((double)r < ratio) bits[i >> 5] |= 1u << (i & 31);     // E:1044, 419
+    // get_random (E:1332-1340) draws r = (float)((rand() % 100000) / 1000.0).  The draws depend on the seed only, so
+    // m = rand() % 100000 is kept on the device per (seed, skip) and extended on demand; the per-sample part -- the
+    // comparison with this sample's ratio (E:1044, 419) -- is one small kernel.
+    if (!c->rand_gen || c->rand_seed != seed || c->rand_skip != rand_skip) {
+        delete c->rand_gen;
+        c->rand_gen = new GlibcRand(seed);
+        for (long i = 0; i < rand_skip; ++i) c->rand_gen->next();
+        c->rand_seed = seed; c->rand_skip = rand_skip; c->rand_filled = 0;
     }
-    int rc = dev_alloc(&c->d_sample_bits, words);
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(c->d_sample_bits, bits.data(), words * 4, cudaMemcpyHostToDevice, c->st));
-    CU(cudaStreamSynchronize(c->st));
+    if (c->rand_filled < need) {
+        if (c->rand_m_buf.cap < need) {                             // grow: keep what is already there
+            DevBuf<uint32_t> bigger;
+            uint64_t cap = std::min<uint64_t>(kRandomArray, std::max<uint64_t>(need, 2 * c->rand_m_buf.cap));
+            int rc = bigger.reserve(cap);
+            if (rc) return rc;
+            if (c->rand_filled) CU(cudaMemcpyAsync(bigger.p, c->rand_m_buf.p, c->rand_filled * 4, cudaMemcpyDeviceToDevice, c->st));
+            CU(cudaStreamSynchronize(c->st));
+            c->rand_m_buf.release();
+            c->rand_m_buf = bigger;
+        }
+        std::vector<uint32_t> m(need - c->rand_filled);
+        for (auto& v : m) v = (uint32_t)(c->rand_gen->next() % 100000);
+        CU(cudaMemcpyAsync(c->rand_m_buf.p + c->rand_filled, m.data(), m.size() * 4, cudaMemcpyHostToDevice, c->st));
+        CU(cudaStreamSynchronize(c->st));
+        c->rand_filled = need;
+    }
+    // r(m) = (float)(m / 1000.0) never decreases with m, so  r(m) < ratio  <=>  m < m_star
+    uint32_t lo = 0, hi = 100000;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) / 2;
+        float r = (float)(mid / 1000.0);
+        if ((double)r < ratio) lo = mid + 1; else hi = mid;
+    }
+    size_t words = (size_t)(kRandomArray + 31) / 32;
+    if (!c->d_sample_bits) { int rc = dev_alloc(&c->d_sample_bits, words); if (rc) return rc; }
+    c->launches += launch_sample_bits(c->rand_m_buf.p, need, lo, c->d_sample_bits, words, c->st);
+    c->sample_bits_on = true;
     return 0;
 }
 
@@ -838,7 +866,7 @@ static int s1_binned(lhgt_ctx* c, Reads& r, uint64_t byte_budget) {
         bp.boff[b + 1] = bp.boff[b] + (b < nbins ? (uint32_t)(1.5 * round_hashes * stream_share(b, nbins)) + 64 : 0);
     // hashes one record contributes on average (sampled fraction included)
     double avg_len = r.nrec ? (double)r.seq_bases / (double)r.nrec : 0.0;
-    double per_rec = std::max(1.0, avg_len - c->k + 1) * c->e * std::min(1.0, c->d_sample_bits ? c->ratio / 100.0 : 1.0);
+    double per_rec = std::max(1.0, avg_len - c->k + 1) * c->e * std::min(1.0, c->sample_bits_on ? c->ratio / 100.0 : 1.0);
     const double slack = 1.0625;                                     // on top of each stream's expected share
     uint64_t want = (uint64_t)(per_rec * (double)r.nrec * slack) + (uint64_t)nbins * 8192;
     uint64_t total = std::min(want, bin_pool_limit_entries());
@@ -866,14 +894,14 @@ static int s1_binned(lhgt_ctx* c, Reads& r, uint64_t byte_budget) {
         int n;
         {
             Span sp(c, 6);
-            n = launch_s1_binned(r.d_fq, r.d_start, r.d_end, lo, hi, byte_budget, c->d_sample_bits, c->ordinal_base, c->hp, bp,
+            n = launch_s1_binned(r.d_fq, r.d_start, r.d_end, lo, hi, byte_budget, c->sample_bits_on ? c->d_sample_bits : nullptr, c->ordinal_base, c->hp, bp,
                                  c->d_count, c->d_counter, c->d_err, 0, c->st);
         }
         if (n < 0) return fail(LHGT_E_CUDA, "S1 stream kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         c->launches += n;
         {
             Span sp(c, 7);
-            c->launches += launch_s1_binned(r.d_fq, r.d_start, r.d_end, lo, hi, byte_budget, c->d_sample_bits, c->ordinal_base, c->hp, bp,
+            c->launches += launch_s1_binned(r.d_fq, r.d_start, r.d_end, lo, hi, byte_budget, c->sample_bits_on ? c->d_sample_bits : nullptr, c->ordinal_base, c->hp, bp,
                                             c->d_count, c->d_counter, c->d_err, 1, c->st);
         }
     }
@@ -895,7 +923,7 @@ extern "C" long lhgt_s1_count(lhgt_ctx* c, int mate, uint64_t byte_budget) {
             int rc = s1_binned(c, r, byte_budget);
             if (rc) return rc;
         } else {
-            c->launches += launch_s1(r.d_fq, r.d_start, r.d_end, r.nrec, byte_budget, c->d_sample_bits, c->ordinal_base, c->hp,
+            c->launches += launch_s1(r.d_fq, r.d_start, r.d_end, r.nrec, byte_budget, c->sample_bits_on ? c->d_sample_bits : nullptr, c->ordinal_base, c->hp,
                                      c->d_count, c->d_counter, c->d_err, c->st);
         }
     }
@@ -1011,7 +1039,7 @@ extern "C" long lhgt_s3_pairs(lhgt_ctx* c, long first, long count) {
     if (c->n_peaks > 0) {
         Span sp(c, 4);
         c->launches += launch_s3(a.d_fq, a.d_start, a.d_end, a.nrec, b.d_fq, b.d_start, b.d_end, b.nrec, b.tail_start, b.tail_len,
-                                 (uint64_t)first, cnt, c->d_sample_bits, c->ordinal_base, c->hp, c->d_prefilter, c->d_peak_kmer, c->d_loci,
+                                 (uint64_t)first, cnt, c->sample_bits_on ? c->d_sample_bits : nullptr, c->ordinal_base, c->hp, c->d_prefilter, c->d_peak_kmer, c->d_loci,
                                  c->d_filter, c->scratch, s3_grid_blocks(c->device), c->d_counter, c->d_err, c->st);
     }
     unsigned long long sampled = 0; int flag = 0;

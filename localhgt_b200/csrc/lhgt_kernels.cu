@@ -125,20 +125,28 @@ __device__ __forceinline__ void bump(uint32_t* count, uint32_t h, uint32_t seen)
     }
 }
 
-// One increment attempt for each of N probes, all compare-and-swaps issued before any result is looked at (a
-// dependent CAS loop per probe would serialise N L2 round trips); the rare losers finish in bump()'s loop.
+// Saturating increment of N counters whose words were loaded into seen[].  Every round issues the compare-and-swaps
+// of all still-pending probes back to back and only then looks at the results, so a round costs one L2 round trip
+// however many probes it carries; a probe that lost its word to a neighbour (16 counters share a word) re-decides on
+// the value the failed CAS returned and goes again in the next round.
 template <int N>
 __device__ __forceinline__ void bump_batch(uint32_t* count, const uint32_t (&h)[N], uint32_t (&seen)[N], const bool (&ok)[N]) {
-    uint32_t got[N];
-#pragma unroll
-    for (int q = 0; q < N; ++q) {
-        int sh = (h[q] & 15u) * 2;
-        got[q] = seen[q];
-        if (ok[q] && ((seen[q] >> sh) & 3u) < 3u) got[q] = atomicCAS(count + (h[q] >> 4), seen[q], seen[q] + (1u << sh));
-    }
+    uint32_t pend = 0;
 #pragma unroll
     for (int q = 0; q < N; ++q)
-        if (got[q] != seen[q]) bump(count, h[q], got[q]);
+        if (ok[q] && ((seen[q] >> ((h[q] & 15u) * 2)) & 3u) < 3u) pend |= 1u << q;
+    while (pend) {
+        uint32_t got[N];
+#pragma unroll
+        for (int q = 0; q < N; ++q)
+            if (pend & (1u << q)) got[q] = atomicCAS(count + (h[q] >> 4), seen[q], seen[q] + (1u << ((h[q] & 15u) * 2)));
+#pragma unroll
+        for (int q = 0; q < N; ++q)
+            if (pend & (1u << q)) {
+                if (got[q] == seen[q] || ((got[q] >> ((h[q] & 15u) * 2)) & 3u) == 3u) pend &= ~(1u << q);
+                seen[q] = got[q];
+            }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -644,59 +652,85 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // flight (UBLKCP; "full" mbarriers count the bytes landed, "empty" mbarriers count the warps done with a slot), so
 // the stream never occupies load scoreboards and every thread spends its own on the 8 table probes it issues per
 // tile.  No CTA-wide barrier inside the loop.
-constexpr int kApplyThreads = 256, kApplyPer = 8, kApplyTile = kApplyThreads * kApplyPer, kApplyStages = 4;
-constexpr size_t kApplySmem = (size_t)kApplyStages * kApplyTile * sizeof(uint32_t) + 2 * kApplyStages * sizeof(uint64_t);
+constexpr int kApplyThreads = 256;
+template <int PER, int STAGES> constexpr size_t apply_smem_bytes() {
+    return (size_t)STAGES * kApplyThreads * PER * sizeof(uint32_t) + 2 * STAGES * sizeof(uint64_t);
+}
 
-__global__ void __launch_bounds__(kApplyThreads, 4) s1_apply_kernel(const uint32_t* __restrict__ stream,
-                                                                    const uint32_t* __restrict__ cursor, uint32_t cap,
-                                                                    uint32_t* __restrict__ count) {
+// MODE 0: the product.  Other modes exist for tools/apply_bench.cu only (cost probes): 1 = probes without updates.
+template <int PER, int STAGES, int MIN_CTAS, int MODE>
+__global__ void __launch_bounds__(kApplyThreads, MIN_CTAS) s1_apply_kernel(const uint32_t* __restrict__ stream,
+                                                                           const uint32_t* __restrict__ cursor, uint32_t cap,
+                                                                           uint32_t* __restrict__ count) {
+    constexpr int kTileN = kApplyThreads * PER;
     extern __shared__ __align__(128) uint32_t apply_smem[];
-    uint32_t* tiles = apply_smem;                                              // [kApplyStages][kApplyTile]
-    uint64_t* full = reinterpret_cast<uint64_t*>(apply_smem + kApplyStages * kApplyTile);
-    uint64_t* empty = full + kApplyStages;
+    uint32_t* tiles = apply_smem;                                              // [STAGES][kTileN]
+    uint64_t* full = reinterpret_cast<uint64_t*>(apply_smem + STAGES * kTileN);
+    uint64_t* empty = full + STAGES;
     const uint32_t n = min(*cursor, cap);
-    const uint32_t ntiles = (n + kApplyTile - 1) / kApplyTile;
+    const uint32_t ntiles = (n + kTileN - 1) / kTileN;
     if (blockIdx.x >= ntiles) return;
     const uint32_t mine = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;    // tiles blockIdx.x + i * gridDim.x
     const int lane = threadIdx.x & 31;
     auto issue = [&](uint32_t j) {                                             // thread 0 only
-        uint32_t stg = j % kApplyStages;
-        if (j >= (uint32_t)kApplyStages) mbar_wait(&empty[stg], ((j / kApplyStages) - 1u) & 1u);   // previous tenant drained
-        uint32_t first = (blockIdx.x + j * gridDim.x) * kApplyTile;
-        uint32_t bytes = (min((uint32_t)kApplyTile, n - first) * 4u + 15u) & ~15u;   // regions are multiples of 8 entries
+        uint32_t stg = j % STAGES;
+        if (j >= (uint32_t)STAGES) mbar_wait(&empty[stg], ((j / STAGES) - 1u) & 1u);   // previous tenant drained
+        uint32_t first = (blockIdx.x + j * gridDim.x) * kTileN;
+        uint32_t bytes = (min((uint32_t)kTileN, n - first) * 4u + 15u) & ~15u;  // regions are multiples of 8 entries
         mbar_expect_tx(&full[stg], bytes);
-        bulk_load_evict_first(tiles + stg * kApplyTile, stream + first, bytes, &full[stg]);
+        bulk_load_evict_first(tiles + stg * kTileN, stream + first, bytes, &full[stg]);
     };
     if (threadIdx.x == 0) {
-        for (int s2 = 0; s2 < kApplyStages; ++s2) { mbar_init(&full[s2], 1); mbar_init(&empty[s2], kApplyThreads / 32); }
+        for (int s2 = 0; s2 < STAGES; ++s2) { mbar_init(&full[s2], 1); mbar_init(&empty[s2], kApplyThreads / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        for (uint32_t j = 0; j < min(mine, (uint32_t)kApplyStages - 1); ++j) issue(j);
+        for (uint32_t j = 0; j < min(mine, (uint32_t)STAGES - 1); ++j) issue(j);
     }
     __syncthreads();
+    uint32_t sink = 0;
     for (uint32_t i = 0; i < mine; ++i) {
-        if (threadIdx.x == 0 && i + kApplyStages - 1 < mine) issue(i + kApplyStages - 1);
-        uint32_t stg = i % kApplyStages;
-        mbar_wait(&full[stg], (i / kApplyStages) & 1u);
-        uint32_t first = (blockIdx.x + i * gridDim.x) * kApplyTile;
-        uint32_t valid = min((uint32_t)kApplyTile, n - first);
-        const uint32_t* tile = tiles + stg * kApplyTile;
-        uint32_t h[kApplyPer], seen[kApplyPer];
-        bool ok[kApplyPer];
+        if (threadIdx.x == 0 && i + STAGES - 1 < mine) issue(i + STAGES - 1);
+        uint32_t stg = i % STAGES;
+        mbar_wait(&full[stg], (i / STAGES) & 1u);
+        uint32_t first = (blockIdx.x + i * gridDim.x) * kTileN;
+        uint32_t valid = min((uint32_t)kTileN, n - first);
+        const uint32_t* tile = tiles + stg * kTileN;
+        uint32_t h[PER], seen[PER];
+        bool ok[PER];
 #pragma unroll
-        for (int q = 0; q < kApplyPer; ++q) {
+        for (int q = 0; q < PER; ++q) {
             uint32_t x = threadIdx.x + q * kApplyThreads;
             ok[q] = x < valid;
             h[q] = tile[x];
         }
 #pragma unroll
-        for (int q = 0; q < kApplyPer; ++q)
+        for (int q = 0; q < PER; ++q)
             if (ok[q]) seen[q] = ld_table(count + (h[q] >> 4));
         __syncwarp();                                                          // every lane's tile words are in registers
         if (lane == 0) mbar_arrive(&empty[stg]);
-        bump_batch<kApplyPer>(count, h, seen, ok);
+        if (MODE == 0) bump_batch<PER>(count, h, seen, ok);
+        else if (MODE == 1) {
+#pragma unroll
+            for (int q = 0; q < PER; ++q) if (ok[q]) sink += seen[q];
+        } else {                                                               // cost probes, NOT exact: tools/apply_bench.cu
+#pragma unroll
+            for (int q = 0; q < PER; ++q) {
+                int sh = (h[q] & 15u) * 2;
+                if (ok[q] && ((seen[q] >> sh) & 3u) < 3u) {
+                    uint32_t* addr = count + (h[q] >> 4);
+                    if (MODE == 2) sink += atomicAdd(addr, 1u << sh);          // returning add
+                    else if (MODE == 3) atomicAdd(addr, 1u << sh);             // fire-and-forget (RED)
+                    else if (MODE == 4) atomicOr(addr, 1u << sh);              // RED.OR
+                    else if (MODE == 5) atomicCAS(addr, seen[q], seen[q] + (1u << sh));   // CAS, result dropped
+                }
+            }
+        }
     }
+    if (MODE != 0 && sink == 0x9e3779b9u) count[0] = sink;
 }
+
+constexpr int kApplyPer = 8, kApplyStages = 4, kApplyMinCtas = 4;
+constexpr size_t kApplySmem = apply_smem_bytes<kApplyPer, kApplyStages>();
 
 size_t s1_bin_smem_bytes(const BinP& bp) { return (size_t)bp.boff[1 << bp.log2] * sizeof(uint32_t); }
 
@@ -719,9 +753,10 @@ int launch_s1_binned(const uint8_t* fq, const uint64_t* rec_start, const uint64_
     if (rec_hi <= rec_lo) return 0;
     int nbins = 1 << bp.log2;
     if (phase == 1) {
-        if (cudaFuncSetAttribute(s1_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kApplySmem) != cudaSuccess) return -1;
+        auto kern = s1_apply_kernel<kApplyPer, kApplyStages, kApplyMinCtas, 0>;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kApplySmem) != cudaSuccess) return -1;
         for (int b = 0; b < nbins; ++b)
-            s1_apply_kernel<<<kSMs * 4, kApplyThreads, kApplySmem, st>>>(bp.pool + bp.off[b], bp.cursor + b, bp.off[b + 1] - bp.off[b], count);
+            kern<<<kSMs * kApplyMinCtas, kApplyThreads, kApplySmem, st>>>(bp.pool + bp.off[b], bp.cursor + b, bp.off[b + 1] - bp.off[b], count);
         return nbins;
     }
     cudaError_t rc;
@@ -1194,6 +1229,25 @@ int launch_s3(const uint8_t* fq1, const uint64_t* s1, const uint64_t* e1, uint64
         default: LHGT_S3(0); break;
     }
 #undef LHGT_S3
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// sampling decisions (E:1037-1044 / E:413-419 with random_array reduced to its integer part, see lhgt_set_sampling)
+// ------------------------------------------------------------------------------------------------
+__global__ void sample_bits_kernel(const uint32_t* __restrict__ m, uint64_t n, uint32_t m_star, uint32_t* __restrict__ bits,
+                                   uint64_t words) {
+    int lane = threadIdx.x & 31;
+    uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t w = warp; w < words; w += nwarps) {
+        uint64_t o = w * 32 + lane;
+        uint32_t word = __ballot_sync(kFull, o < n && m[o] < m_star);
+        if (lane == 0) bits[w] = word;
+    }
+}
+
+int launch_sample_bits(const uint32_t* m, uint64_t n, uint32_t m_star, uint32_t* bits, uint64_t words, cudaStream_t st) {
+    sample_bits_kernel<<<kSMs * 8, 256, 0, st>>>(m, n, m_star, bits, words);
     return 1;
 }
 

@@ -99,6 +99,8 @@ int launch_s3(const uint8_t* fq1, const uint64_t* s1, const uint64_t* e1, uint64
 int s3_grid_blocks(int device);
 int s3_warps_per_block();
 
+// bit o of `bits` := o < n && m[o] < m_star (the sampling decision of ordinal o); the other bits of the 50 M-bit array := 0
+int launch_sample_bits(const uint32_t* m, uint64_t n, uint32_t m_star, uint32_t* bits, uint64_t words, cudaStream_t st);
 int launch_count_unpack(const uint32_t* count, uint64_t entries, uint8_t* out, cudaStream_t st);
 int launch_count_merge(uint32_t* count, const uint32_t* other, uint64_t words, cudaStream_t st);
 

@@ -84,6 +84,7 @@ class Shard:
         self.last_stage_ms = np.zeros(10)
         self.last_peaks = 0
         self.last_counts = {}
+        self.last_wall_ms = {}
 
     # ---- collectives on small host scalars
     def _all_gather_ints(self, vals):
@@ -141,10 +142,19 @@ class Shard:
         """Reads must already be resident (reads_upload / reads_attach_device) and the index loaded."""
         eng, w = self.eng, self.world
         ms = np.zeros(10)
+        wall = {}
         t0 = time.perf_counter()
+
+        def lap(name, since):
+            now = time.perf_counter()
+            wall[name] = wall.get(name, 0.0) + 1000 * (now - since)
+            return now
+
         eng.reset()
         nrec1, nrec2 = eng.reads_records(0), eng.reads_records(1)
+        t = lap("reset", t0)
         info = self._all_gather_ints([nrec1, eng.reads_seq_bases(0), size1, eng.reads_bytes(1)])
+        t = lap("gather_sizes", t)
         base = sum(r[0] for r in info[: self.rank])
         if sample_arg <= 1:
             ratio = 100 * sample_arg                                   # E:1392-1394
@@ -155,29 +165,39 @@ class Shard:
         budget2 = size1_total - fq2_before if w > 1 else size1         # Q15 in shard-local byte offsets
         eng.set_ordinal_base(base)
         eng.set_sampling(ratio, seed, rand_skip)
+        t = lap("set_sampling", t)
         ms[7] = 1000 * (time.perf_counter() - t0)
         n1 = eng.s1_count(0, size1_total)                              # fq1 records never start beyond size(fq1)
         n2 = eng.s1_count(1, budget2) if budget2 >= 0 else 0
-        t1 = time.perf_counter()
+        t = t1 = lap("s1", t)
         if w > 1:
             self.exchange_counts()
+            t = lap("exchange_counts", t)
         if w > 1 and eng.sharded_s2:
             nt = eng.s2_tiles()
             lo, hi = split_range(nt, w, self.rank)
             eng.s2_gather(lo, hi)
             eng.sync()
+            t = lap("s2_gather", t)
             self.exchange_hit_bits(nt)
+            t = lap("exchange_hit_bits", t)
             n_peaks = eng.s2_finish(hit, match, max_peak)
+            t = lap("s2_finish", t)
         else:
             n_peaks = eng.s2_peaks(hit, match, max_peak)
+            t = lap("s2", t)
         t2 = time.perf_counter()
         n3 = eng.s3_pairs()
+        t = lap("s3", t)
         if w > 1 and n_peaks > 0:
             eng.sync()
             filt = eng.peak_filter()
             self.dist.all_reduce(filt, op=self.dist.ReduceOp.MAX)
             self._fence(filt)
+            t = lap("reduce_filter", t)
         text = eng.intervals()
+        t = lap("intervals", t)
+        self.last_wall_ms = wall
         st = eng.stage_ms()
         ms[:6] = st[:6]
         if len(st) >= 8:
