@@ -336,11 +336,16 @@ def ours(args) -> None:
                                 max_peak=MAX_PEAK)
 
         def step_e2e():
-            scr.index_upload_ptr(himg.data_ptr(), himg.numel())
+            # all three host->device copies are queued on the copy stream up front, in the order the stages need them;
+            # each stage adopts its input when it gets there (fq2 lands behind S1 of fq1, the index behind S1 of fq2)
+            scr.reads_prefetch_ptr(0, h1.data_ptr(), h1.numel())
+            scr.reads_prefetch_ptr(1, h2.data_ptr(), h2.numel())
+            scr.index_prefetch_ptr(himg.data_ptr(), himg.numel())
             scr.reads_upload_ptr(0, h1.data_ptr(), h1.numel())
-            scr.reads_upload_ptr(1, h2.data_ptr(), h2.numel())
-            return shard.screen(size1=h1.numel(), sample_arg=SAMPLE, seed=SEED, rand_skip=0, hit=HIT, match=MATCH,
-                                max_peak=MAX_PEAK)
+            return shard.screen(size1=h1.numel(), size2=h2.numel(), sample_arg=SAMPLE, seed=SEED, rand_skip=0, hit=HIT, match=MATCH,
+                                max_peak=MAX_PEAK,
+                                before_mate2=lambda: scr.reads_upload_ptr(1, h2.data_ptr(), h2.numel()),
+                                before_s2=lambda: scr.index_upload_ptr(himg.data_ptr(), himg.numel()))
 
         def timed(fn, steps, warm, sampler=None):
             for _ in range(warm):
@@ -398,7 +403,8 @@ def ours(args) -> None:
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "pairs/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(h1.numel() + h2.numel() + himg.numel()), "d2h_bytes_per_step": len(text_resident) + 64,
-                "what": "pinned host FASTQ x2 + index image -> HBM -> S1,S2,S3 -> interval text on host, through the C ABI"},
+                "what": "pinned host FASTQ x2 + index image -> HBM (copy stream, overlapping S1) -> S1,S2,S3 -> interval text on host, "
+                        "through the C ABI; every byte crosses PCIe inside the timed region"},
         "gpu_launches": int(launches), "roofline": roofline, "index_build": index_build,
         "result": {"interval_lines": len(text_resident.splitlines()), "interval_sha256": hashlib.sha256(text_resident).hexdigest()[:16],
                    "planted_recovered": recovered(text_resident, meta), "peaks": shard.last_peaks,

@@ -93,6 +93,13 @@ int      lhgt_index_len_text(const lhgt_ctx* c, char* dst, size_t cap, size_t* n
 /* Makes an existing image HBM-resident (read_index's input, E:888-979) and adopts its coder
  * (E:1417).  lhgt_index_attach_device uses an image that already lives on this device. */
 int      lhgt_index_upload(lhgt_ctx* c, const uint8_t* image, uint64_t n);
+/* Overlap of the host->device copies with the stages (the reference reads its inputs from disk stage by stage,
+ * E:1426-1507; here the bytes cross PCIe once, and may do so while an earlier stage computes).  A prefetch starts
+ * the copy of a host buffer (pinned memory for a truly asynchronous copy) on the context's copy stream and
+ * returns; the later lhgt_reads_upload / lhgt_index_upload call with the SAME pointer and size adopts the copy
+ * instead of repeating it.  The host buffer must stay valid and unchanged until that call returns. */
+int      lhgt_reads_prefetch(lhgt_ctx* c, int mate, const uint8_t* fq, uint64_t n);
+int      lhgt_index_prefetch(lhgt_ctx* c, const uint8_t* image, uint64_t n);
 /* File-level forms (what main() does at E:1401-1417). */
 int      lhgt_index_build_file(lhgt_ctx* c, const char* fasta_path, const char* index_path,
                                const char* len_path);

@@ -65,6 +65,8 @@ SYMBOLS = {
     "lhgt_index_build_file": (_i, [_vp, _s, _s, _s]),
     "lhgt_index_load_file": (_i, [_vp, _s]),
     "lhgt_reads_upload": (_i, [_vp, _i, _vp, _u64]),
+    "lhgt_reads_prefetch": (_i, [_vp, _i, _vp, _u64]),
+    "lhgt_index_prefetch": (_i, [_vp, _vp, _u64]),
     "lhgt_reads_attach_device": (_i, [_vp, _i, _vp, _u64]),
     "lhgt_reads_records": (_l, [_vp, _i]),
     "lhgt_reads_seq_bases": (_u64, [_vp, _i]),
@@ -246,6 +248,13 @@ class Screen:
         """fq: bytes / numpy uint8 / anything exposing a host pointer via numpy."""
         buf = fq if isinstance(fq, np.ndarray) else np.frombuffer(fq, dtype=np.uint8)
         _check(self._L.lhgt_reads_upload(self._h, mate, _ptr(buf) if len(buf) else None, len(buf)))
+
+    def reads_prefetch_ptr(self, mate: int, host_ptr: int, n: int) -> None:
+        """Starts the H2D copy on the copy stream; reads_upload_ptr(mate, same ptr, same n) adopts it later."""
+        _check(self._L.lhgt_reads_prefetch(self._h, mate, host_ptr, n))
+
+    def index_prefetch_ptr(self, host_ptr: int, n: int) -> None:
+        _check(self._L.lhgt_index_prefetch(self._h, host_ptr, n))
 
     def reads_upload_ptr(self, mate: int, host_ptr: int, n: int) -> None:
         _check(self._L.lhgt_reads_upload(self._h, mate, host_ptr, n))

@@ -117,6 +117,9 @@ struct lhgt_ctx {
     int16_t cc[LHGT_CODER_SLOTS];
     HashP hp;
     cudaStream_t own = nullptr, st = nullptr;
+    cudaStream_t copy_st = nullptr;              // host->device prefetches run here, beside the kernels on `st`
+    struct Prefetch { const void* host = nullptr; uint64_t n = 0; cudaEvent_t done = nullptr; bool active = false; };
+    Prefetch pf_reads[2], pf_index;
 
     uint32_t* d_count = nullptr; uint64_t count_words = 0;
     uint32_t* d_peak_kmer = nullptr;
@@ -277,6 +280,7 @@ extern "C" int lhgt_create(lhgt_ctx** out, int device, int k, int e) {
     int rc = 0;
     if (cudaStreamCreateWithFlags(&c->own, cudaStreamNonBlocking) != cudaSuccess) rc = fail(LHGT_E_CUDA, "stream create failed");
     c->st = c->own;
+    if (!rc && cudaStreamCreateWithFlags(&c->copy_st, cudaStreamNonBlocking) != cudaSuccess) rc = fail(LHGT_E_CUDA, "stream create failed");
     uint64_t entries = 1ull << k;
     c->count_words = std::max<uint64_t>(1, entries / 16);
     if (!rc) rc = dev_alloc(&c->d_count, c->count_words);
@@ -303,7 +307,10 @@ static void drop_reads(Reads& r, bool release = false) {      // forgets the sam
     r.d_start = r.d_end = nullptr; r.tail_start = r.tail_len = 0; r.ready = false;
 }
 
+static int clear_peak_tables(lhgt_ctx* c);
+
 static void drop_index(lhgt_ctx* c, bool release = false) {     // forgets the index, keeps the buffers
+    clear_peak_tables(c);                                       // un-writing the peak tables needs the index that wrote them
     if (release) {
         c->image_buf.release(); c->single_buf.release(); c->trio_buf.release(); c->good_buf.release(); c->flagged_buf.release();
         c->tile_new_buf.release(); c->tile_base_buf.release(); c->scan_tmp_buf.release(); c->contigs_buf.release(); c->tiles_buf.release();
@@ -313,6 +320,7 @@ static void drop_index(lhgt_ctx* c, bool release = false) {     // forgets the i
     c->d_contigs = nullptr; c->d_tiles = nullptr;
     c->d_single = c->d_trio = c->d_good = c->d_flagged = nullptr;
     c->d_tile_new = c->d_tile_base = c->d_scan_tmp = nullptr;
+    c->n_peaks = -1; c->n_flagged = 0;
     c->contigs.clear(); c->tiles.clear(); c->len_text.clear();
     c->index_ready = false; c->gathered = false; c->index_bases = 0;
 }
@@ -329,6 +337,8 @@ extern "C" void lhgt_destroy(lhgt_ctx* c) {
     c->rand_m_buf.release(); delete c->rand_gen;
     dev_free(c->d_cands); dev_free(c->d_tally); dev_free(c->d_counter); dev_free(c->d_err);
     dev_free(c->d_bin_pool); dev_free(c->d_bin_cursor);
+    if (c->copy_st) { cudaStreamSynchronize(c->copy_st); cudaStreamDestroy(c->copy_st); }
+    for (lhgt_ctx::Prefetch* p : {&c->pf_reads[0], &c->pf_reads[1], &c->pf_index}) if (p->done) cudaEventDestroy(p->done);
     if (c->own) cudaStreamDestroy(c->own);
     delete c;
 }
@@ -564,6 +574,48 @@ static int adopt_image_layout(lhgt_ctx* c, const uint32_t* words, uint64_t nword
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ prefetch
+// Starts the host->device copy on the copy stream; the matching upload call later adopts it (waits on the event
+// from the compute stream) instead of copying.  The destination is a buffer no kernel in flight reads: uploads of
+// one sample follow its own stage order (fq1, S1, fq2, S1, index, S2, S3).
+static int start_prefetch(lhgt_ctx* c, lhgt_ctx::Prefetch& p, void* dst, const void* host, uint64_t n) {
+    if (!p.done) CU(cudaEventCreateWithFlags(&p.done, cudaEventDisableTiming));
+    CU(cudaEventRecord(p.done, c->st));                          // whatever still reads the destination on the compute stream
+    CU(cudaStreamWaitEvent(c->copy_st, p.done, 0));
+    if (n) CU(cudaMemcpyAsync(dst, host, n, cudaMemcpyHostToDevice, c->copy_st));
+    CU(cudaEventRecord(p.done, c->copy_st));
+    p.host = host; p.n = n; p.active = true;
+    return 0;
+}
+
+// true when `host`/`n` is exactly what was prefetched: the compute stream then waits for that copy
+static bool adopt_prefetch(lhgt_ctx* c, lhgt_ctx::Prefetch& p, const void* host, uint64_t n) {
+    if (!p.active) return false;
+    p.active = false;
+    if (p.host != host || p.n != n) { cudaEventSynchronize(p.done); return false; }   // stale: let it land, then overwrite
+    return cudaStreamWaitEvent(c->st, p.done, 0) == cudaSuccess;
+}
+
+extern "C" int lhgt_reads_prefetch(lhgt_ctx* c, int mate, const uint8_t* fq, uint64_t n) {
+    if (!c || mate < 0 || mate > 1 || (!fq && n)) return fail(LHGT_E_ARG, "lhgt_reads_prefetch: bad argument");
+    CU(cudaSetDevice(c->device));
+    Reads& r = c->reads[mate];
+    drop_reads(r);
+    int rc = r.fq_buf.reserve(n + 64);
+    if (rc) return rc;
+    return start_prefetch(c, c->pf_reads[mate], r.fq_buf.p, fq, n);
+}
+
+extern "C" int lhgt_index_prefetch(lhgt_ctx* c, const uint8_t* image, uint64_t n) {
+    if (!c || !image) return fail(LHGT_E_ARG, "null pointer");
+    if (n % 4) return fail(LHGT_E_FORMAT, "index image size is not a multiple of 4");
+    CU(cudaSetDevice(c->device));
+    drop_index(c);
+    int rc = c->image_buf.reserve(n / 4);
+    if (rc) return rc;
+    return start_prefetch(c, c->pf_index, c->image_buf.p, image, n);
+}
+
 extern "C" int lhgt_index_upload(lhgt_ctx* c, const uint8_t* image, uint64_t n) {
     if (!c || !image) return fail(LHGT_E_ARG, "null pointer");
     if (n % 4) return fail(LHGT_E_FORMAT, "index image size is not a multiple of 4");
@@ -572,7 +624,7 @@ extern "C" int lhgt_index_upload(lhgt_ctx* c, const uint8_t* image, uint64_t n) 
     int rc = adopt_image_layout(c, (const uint32_t*)image, n / 4);
     if (rc) return rc;
     if ((rc = alloc_image(c, n / 4))) return rc;
-    CU(cudaMemcpyAsync(c->d_image, image, n, cudaMemcpyHostToDevice, c->st));
+    if (!adopt_prefetch(c, c->pf_index, image, n)) CU(cudaMemcpyAsync(c->d_image, image, n, cudaMemcpyHostToDevice, c->st));
     return finish_index_tables(c);
 }
 
@@ -581,7 +633,7 @@ struct HostFile {
     uint8_t* p = nullptr; size_t n = 0; bool pinned = false;
     ~HostFile() { release(); }
     void release() {
-        if (p) { if (pinned) cudaFreeHost(p); else free(p); }
+        if (p) { if (pinned) { cudaDeviceSynchronize(); cudaFreeHost(p); } else free(p); }   // no copy may still read it
         p = nullptr; n = 0;
     }
 };
@@ -724,7 +776,7 @@ extern "C" int lhgt_reads_upload(lhgt_ctx* c, int mate, const uint8_t* fq, uint6
     if (rc) return rc;
     uint8_t* d = r.fq_buf.p;
     r.d_fq = d; r.owned = true; r.n = n;
-    if (n) CU(cudaMemcpyAsync(d, fq, n, cudaMemcpyHostToDevice, c->st));
+    if (!adopt_prefetch(c, c->pf_reads[mate], fq, n) && n) CU(cudaMemcpyAsync(d, fq, n, cudaMemcpyHostToDevice, c->st));
     uint64_t tail = 0;
     int last = '\n';
     if (n) {
@@ -1210,13 +1262,13 @@ extern "C" int lhgt_extract_ref(const lhgt_args* a, lhgt_stats* stats) {
     if (rc) return rc;
     struct Guard { lhgt_ctx* c; ~Guard() { lhgt_destroy(c); } } guard{c};
 
-    // inputs: both FASTQ images go to HBM once and stay there for S1 and S3
+    // inputs: both FASTQ images cross PCIe once and stay in HBM for S1 and S3.  The copies run on the copy stream:
+    // fq1's while fq2 is still being read from disk, fq2's and the index image's behind S1 of fq1.
     t = now_s();
-    {
-        HostFile f1, f2;
-        if ((rc = slurp(a->fq1, f1, true)) || (rc = lhgt_reads_upload(c, 0, f1.p, f1.n))) return rc;
-        if ((rc = slurp(a->fq2, f2, true)) || (rc = lhgt_reads_upload(c, 1, f2.p, f2.n))) return rc;
-    }
+    HostFile f1, f2, fidx;
+    if ((rc = slurp(a->fq1, f1, true)) || (rc = lhgt_reads_prefetch(c, 0, f1.p, f1.n))) return rc;
+    if ((rc = slurp(a->fq2, f2, true)) || (rc = lhgt_reads_prefetch(c, 1, f2.p, f2.n))) return rc;
+    if ((rc = lhgt_reads_upload(c, 0, f1.p, f1.n))) return rc;
     st.seconds[1] = now_s() - t;
     uint64_t size1 = c->reads[0].n;                                       // E:1419
 
@@ -1233,6 +1285,7 @@ extern "C" int lhgt_extract_ref(const lhgt_args* a, lhgt_stats* stats) {
     std::string index_path = std::string(a->fasta) + ".k" + std::to_string(a->k) + ".h" + std::to_string(a->e) + ".index.dat";
     std::string len_path = std::string(a->fasta) + ".genome.len.txt";
     long rand_skip = 0;
+    bool index_pending = false;
     if (!file_exists(index_path.c_str())) {
         if (say) printf("Reference index not detected, start index...\n");
         int16_t cc[LHGT_CODER_SLOTS];
@@ -1244,7 +1297,8 @@ extern "C" int lhgt_extract_ref(const lhgt_args* a, lhgt_stats* stats) {
         st.index_built = 1;
     } else {
         if (say) printf("Reference index is detected.\n");
-        if ((rc = lhgt_index_load_file(c, index_path.c_str()))) return rc;
+        if ((rc = slurp(index_path.c_str(), fidx, true)) || (rc = lhgt_index_prefetch(c, fidx.p, fidx.n))) return rc;
+        index_pending = true;
     }
     st.seconds[2] = now_s() - t;
     if (say) printf("Start extract HGT-related segments...\n");
@@ -1255,10 +1309,20 @@ extern "C" int lhgt_extract_ref(const lhgt_args* a, lhgt_stats* stats) {
     long n;
     if ((n = lhgt_s1_count(c, 0, size1)) < 0) return (int)n;
     st.reads_s1[0] = n;
+    if ((rc = lhgt_reads_upload(c, 1, f2.p, f2.n))) return rc;
+    if ((rc = lhgt_set_sampling(c, ratio, a->seed, rand_skip))) return rc;   // fq2 may hold more records than fq1
     if ((n = lhgt_s1_count(c, 1, size1)) < 0) return (int)n;               // Q15: fq1's size bounds fq2 too
     st.reads_s1[1] = n;
+    f1.release(); f2.release();
     st.seconds[3] = now_s() - t;
     if (say) printf("K-mer counting is finished.\nconsidered read pair num in kmer counting:%ld\n", (st.reads_s1[0] + st.reads_s1[1]) / 2);
+
+    if (index_pending) {
+        double t2 = now_s();
+        if ((rc = lhgt_index_upload(c, fidx.p, fidx.n))) return rc;
+        fidx.release();
+        st.seconds[2] += now_s() - t2;
+    }
 
     t = now_s();
     if ((n = lhgt_s2_peaks(c, (float)a->hit_ratio, (float)a->match_ratio, a->max_peak)) < 0) return (int)n;

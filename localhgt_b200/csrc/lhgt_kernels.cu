@@ -502,21 +502,26 @@ __device__ __forceinline__ void bump_direct(uint32_t* count, uint32_t h) {
 }
 
 template <int E>
-__global__ void __launch_bounds__(kBinWarps * 32, 3) s1_bin_kernel(
+__global__ void __launch_bounds__(kBinWarps * 32, 4) s1_bin_kernel(
     const uint8_t* __restrict__ fq, const uint64_t* __restrict__ rec_start, const uint64_t* __restrict__ rec_end,
     uint64_t rec_lo, uint64_t rec_hi, uint64_t budget, const uint32_t* __restrict__ sample_bits, uint64_t ordinal_base,
     HashP hp, BinP bp, uint32_t* __restrict__ count, unsigned long long* __restrict__ n_sampled, int* __restrict__ err) {
-    extern __shared__ uint32_t dyn[];
-    __shared__ uint32_t cnt[kMaxBins];
-    __shared__ uint2 bnd[kMaxBins];                           // bucket b = dyn[bnd[b].x .. bnd[b].y)
+    extern __shared__ uint32_t dyn[];                         // two bucket sets: one fills while the other drains
+    __shared__ uint32_t cnt[2][kMaxBins];
+    __shared__ uint2 bnd[kMaxBins];                           // bucket b of a set = set base + [bnd[b].x, bnd[b].y)
     __shared__ uint8_t lut[256];
-    uint32_t* buckets = dyn;
     const int e = E ? E : hp.e;
     const int nbins = 1 << bp.log2;
+    const uint32_t set_entries = bp.boff[kMaxBins];
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x < kMaxBins) { bnd[threadIdx.x] = make_uint2(bp.boff[threadIdx.x], bp.boff[threadIdx.x + 1]); cnt[threadIdx.x] = 0; }
+    if (threadIdx.x < kMaxBins) {
+        bnd[threadIdx.x] = make_uint2(bp.boff[threadIdx.x], bp.boff[threadIdx.x + 1]);
+        cnt[0][threadIdx.x] = 0; cnt[1][threadIdx.x] = 0;
+    }
     fill_base_lut(lut);
     __syncthreads();
+    // the two streams this warp drains: b and nbins-1-b together carry an equal share of the hashes (stream_share)
+    int mine_b[2] = {warp < nbins ? warp : -1, nbins - 1 - warp >= kBinWarps ? nbins - 1 - warp : -1};
     unsigned long long mine = 0;
     const uint64_t stride = (uint64_t)gridDim.x * kBinWarps;
     auto next_sampled = [&](uint64_t q) {                     // warp-uniform
@@ -536,7 +541,8 @@ __global__ void __launch_bounds__(kBinWarps * 32, 3) s1_bin_kernel(
     uint32_t chn = 0;                                         // this lane's byte of word w, loaded one chunk ahead
     Planes prev{0, 0, 0, 0};
     bool have = false;
-    for (;;) {
+    int set = 0;                                              // the set this round fills; set^1 drains
+    for (bool first_round = true;; first_round = false) {
         while (!have && r < rec_hi) {                         // turn the candidate into the current read
             uint64_t start = cs, len64 = ce - cs;
             uint32_t b0 = pb0, b1 = pb1;
@@ -558,61 +564,81 @@ __global__ void __launch_bounds__(kBinWarps * 32, 3) s1_bin_kernel(
             w = 1;
             have = true;
         }
-        if (!__syncthreads_or(have)) break;                   // also: buckets and cnt are free again
-#pragma unroll 1
-        for (int it = 0; it < kS1Unroll && have; ++it) {      // chunk w-1 = words w-1 (prev) and w (cur)
-            Planes cur = pack_word(chn, lut);
-            int pn = (w + 1) * 32 + lane;
-            chn = pn < len ? src[pn] : 0u;
-            LeWin kw = le_window(prev, cur, lane, hp);
-            if (kw.valid) {
+        // One barrier per round: behind it the set filled last round is complete and the set drained last round is free.
+        bool any = __syncthreads_or(have);
+        // reserve room in the global streams for what last round produced; the answers are picked up after this
+        // round's hashing, so the atomics' round trip costs nothing
+        uint32_t dn[2] = {0, 0}, dg[2] = {0, 0};
+        if (!first_round) {
 #pragma unroll
-                for (int i = 0; i < (E ? E : kMaxE); ++i)
-                    if (i < e) {
-                        uint32_t h = le_hash(kw, hp, i);
-                        uint32_t b = h >> bp.shift;
-                        uint2 lim = bnd[b];
-                        uint32_t slot = lim.x + atomicAdd(&cnt[b], 1u);
-                        if (slot < lim.y) buckets[slot] = h;
-                        else bump_direct(count, h);           // bucket full: rare, exact either way
-                    }
-            }
-            prev = cur;
-            if (++w > nch) { have = false; }
-            if (!pb_ready && r < rec_hi) {                    // candidate's first two words, consumed a read later
-                uint64_t nlen = ce - cs;
-                const uint8_t* nsrc = fq + cs;
-                pb0 = (uint64_t)lane < nlen ? nsrc[lane] : 0u;
-                pb1 = (uint64_t)(32 + lane) < nlen ? nsrc[32 + lane] : 0u;
-                pb_ready = true;
+            for (int q = 0; q < 2; ++q) {
+                int b = mine_b[q];
+                if (b < 0) continue;
+                dn[q] = min(cnt[set ^ 1][b], bnd[b].y - bnd[b].x);
+                if (dn[q] && lane == 0) dg[q] = atomicAdd(bp.cursor + b, dn[q]);
             }
         }
-        __syncthreads();
-        for (int q = 0; q < 2; ++q) {                         // flush: one coalesced run per stream; streams b and
-            int b = q == 0 ? warp : nbins - 1 - warp;         // nbins-1-b together carry an equal share (stream_share)
-            if (b >= nbins || (q == 1 && b < kBinWarps)) continue;
-            uint32_t b0 = bnd[b].x;
-            uint32_t n = min(cnt[b], bnd[b].y - b0);
-            if (n) {
-                uint32_t g = 0;
-                if (lane == 0) g = atomicAdd(bp.cursor + b, n);
-                g = __shfl_sync(kFull, g, 0);
-                uint32_t* dst = bp.pool + bp.off[b];
-                uint32_t cap = bp.off[b + 1] - bp.off[b];
-                if (g + n <= cap) {
-                    dst += g;
-                    for (uint32_t x = lane; x < n; x += 32) dst[x] = buckets[b0 + x];
-                } else {
-                    for (uint32_t x = lane; x < n; x += 32) {
-                        uint32_t h = buckets[b0 + x];
-                        if (g + x < cap) dst[g + x] = h;
-                        else bump_direct(count, h);           // stream region full
-                    }
+        if (any) {
+            uint32_t* buckets = dyn + set * set_entries;
+            uint32_t* fill = cnt[set];
+#pragma unroll 1
+            for (int it = 0; it < kS1Unroll && have; ++it) {  // chunk w-1 = words w-1 (prev) and w (cur)
+                Planes cur = pack_word(chn, lut);
+                int pn = (w + 1) * 32 + lane;
+                chn = pn < len ? src[pn] : 0u;
+                LeWin kw = le_window(prev, cur, lane, hp);
+                if (kw.valid) {
+#pragma unroll
+                    for (int i = 0; i < (E ? E : kMaxE); ++i)
+                        if (i < e) {
+                            uint32_t h = le_hash(kw, hp, i);
+                            uint32_t b = h >> bp.shift;
+                            uint2 lim = bnd[b];
+                            uint32_t slot = lim.x + atomicAdd(&fill[b], 1u);
+                            if (slot < lim.y) buckets[slot] = h;
+                            else bump_direct(count, h);       // bucket full: rare, exact either way
+                        }
+                }
+                prev = cur;
+                if (++w > nch) { have = false; }
+                if (!pb_ready && r < rec_hi) {                // candidate's first two words, consumed a read later
+                    uint64_t nlen = ce - cs;
+                    const uint8_t* nsrc = fq + cs;
+                    pb0 = (uint64_t)lane < nlen ? nsrc[lane] : 0u;
+                    pb1 = (uint64_t)(32 + lane) < nlen ? nsrc[32 + lane] : 0u;
+                    pb_ready = true;
                 }
             }
-            __syncwarp();
-            if (lane == 0) cnt[b] = 0;
         }
+        if (!first_round) {                                   // drain last round's set: one coalesced run per stream
+            const uint32_t* drain = dyn + (set ^ 1) * set_entries;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                int b = mine_b[q];
+                if (b < 0) continue;
+                uint32_t n = dn[q];
+                if (n) {
+                    uint32_t g = __shfl_sync(kFull, dg[q], 0);
+                    uint32_t b0 = bnd[b].x;
+                    uint32_t* dst = bp.pool + bp.off[b];
+                    uint32_t cap = bp.off[b + 1] - bp.off[b];
+                    if (g + n <= cap) {
+                        dst += g;
+                        for (uint32_t x = lane; x < n; x += 32) dst[x] = drain[b0 + x];
+                    } else {
+                        for (uint32_t x = lane; x < n; x += 32) {
+                            uint32_t h = drain[b0 + x];
+                            if (g + x < cap) dst[g + x] = h;
+                            else bump_direct(count, h);       // stream region full
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) cnt[set ^ 1][b] = 0;
+            }
+        }
+        if (!any) break;
+        set ^= 1;
     }
     if (lane == 0 && mine) atomicAdd(n_sampled, mine);
 }
@@ -732,7 +758,7 @@ __global__ void __launch_bounds__(kApplyThreads, MIN_CTAS) s1_apply_kernel(const
 constexpr int kApplyPer = 8, kApplyStages = 4, kApplyMinCtas = 4;
 constexpr size_t kApplySmem = apply_smem_bytes<kApplyPer, kApplyStages>();
 
-size_t s1_bin_smem_bytes(const BinP& bp) { return (size_t)bp.boff[1 << bp.log2] * sizeof(uint32_t); }
+size_t s1_bin_smem_bytes(const BinP& bp) { return (size_t)2 * bp.boff[kMaxBins] * sizeof(uint32_t); }   // two bucket sets
 
 template <int E>
 static cudaError_t s1_bin_launch(const uint8_t* fq, const uint64_t* rs, const uint64_t* re, uint64_t lo, uint64_t hi, uint64_t budget,
@@ -742,7 +768,7 @@ static cudaError_t s1_bin_launch(const uint8_t* fq, const uint64_t* rs, const ui
     cudaError_t rc = cudaFuncSetAttribute(s1_bin_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) return rc;
     uint64_t want = (hi - lo + kBinWarps - 1) / kBinWarps;
-    unsigned grid = (unsigned)(want < (uint64_t)kSMs * 3 ? want : (uint64_t)kSMs * 3);
+    unsigned grid = (unsigned)(want < (uint64_t)kSMs * 4 ? want : (uint64_t)kSMs * 4);
     s1_bin_kernel<E><<<grid, kBinWarps * 32, smem, st>>>(fq, rs, re, lo, hi, budget, sb, ob, hp, bp, count, ns, err);
     return cudaGetLastError();
 }

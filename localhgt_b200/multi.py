@@ -138,8 +138,11 @@ class Shard:
 
     # ---- the pass
     def screen(self, *, size1: int, sample_arg: float, seed: int, rand_skip: int, hit: float, match: float,
-               max_peak: int) -> bytes:
-        """Reads must already be resident (reads_upload / reads_attach_device) and the index loaded."""
+               max_peak: int, size2: Optional[int] = None, before_mate2=None, before_s2=None) -> bytes:
+        """Reads must already be resident (reads_upload / reads_attach_device) and the index loaded -- or arrive through
+        the hooks: before_mate2() runs after S1 of fq1 was launched and must make fq2 resident (size2 = its byte size,
+        needed up front for the Q15 budget), before_s2() must make the index resident.  That is the stage order of the
+        reference's main() (E:1426-1507), which lets host->device copies hide behind S1."""
         eng, w = self.eng, self.world
         ms = np.zeros(10)
         wall = {}
@@ -151,9 +154,9 @@ class Shard:
             return now
 
         eng.reset()
-        nrec1, nrec2 = eng.reads_records(0), eng.reads_records(1)
+        nrec1 = eng.reads_records(0)
         t = lap("reset", t0)
-        info = self._all_gather_ints([nrec1, eng.reads_seq_bases(0), size1, eng.reads_bytes(1)])
+        info = self._all_gather_ints([nrec1, eng.reads_seq_bases(0), size1, eng.reads_bytes(1) if size2 is None else size2])
         t = lap("gather_sizes", t)
         base = sum(r[0] for r in info[: self.rank])
         if sample_arg <= 1:
@@ -168,11 +171,18 @@ class Shard:
         t = lap("set_sampling", t)
         ms[7] = 1000 * (time.perf_counter() - t0)
         n1 = eng.s1_count(0, size1_total)                              # fq1 records never start beyond size(fq1)
+        if before_mate2 is not None:
+            before_mate2()
+            t = lap("s1", t)
+            eng.set_sampling(ratio, seed, rand_skip)                   # fq2 may hold more records than fq1: cover them
         n2 = eng.s1_count(1, budget2) if budget2 >= 0 else 0
         t = t1 = lap("s1", t)
         if w > 1:
             self.exchange_counts()
             t = lap("exchange_counts", t)
+        if before_s2 is not None:
+            before_s2()
+            t = lap("index_upload", t)
         if w > 1 and eng.sharded_s2:
             nt = eng.s2_tiles()
             lo, hi = split_range(nt, w, self.rank)
