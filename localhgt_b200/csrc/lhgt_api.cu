@@ -611,6 +611,14 @@ extern "C" int lhgt_index_prefetch(lhgt_ctx* c, const uint8_t* image, uint64_t n
     if (n % 4) return fail(LHGT_E_FORMAT, "index image size is not a multiple of 4");
     CU(cudaSetDevice(c->device));
     drop_index(c);
+    // The header's coder governs S1 as well (E:1417 re-reads it before read_fastq), and S1 runs before the image is
+    // adopted by lhgt_index_upload: take it now.
+    if (n < (uint64_t)LHGT_CODER_SLOTS * 4) return fail(LHGT_E_FORMAT, "index image shorter than its 1200-byte header");
+    int16_t cc[LHGT_CODER_SLOTS];
+    lhgt_header_to_coder((const uint32_t*)image, cc);
+    if (!coder_ok(cc, c->k, c->e)) return fail(LHGT_E_FORMAT, "index header does not describe k=%d e=%d", c->k, c->e);
+    memcpy(c->cc, cc, sizeof cc);
+    make_hashp(c);
     int rc = c->image_buf.reserve(n / 4);
     if (rc) return rc;
     return start_prefetch(c, c->pf_index, c->image_buf.p, image, n);
