@@ -357,7 +357,7 @@ def ours(args) -> None:
                 sampler.start()
             l0 = scr.launch_count()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            stage = np.zeros(10)
+            stage = np.zeros(11)
             a.record(stream)
             res = None
             for _ in range(steps):
@@ -392,7 +392,7 @@ def ours(args) -> None:
     e2e_value = total_pairs * args.steps / (ms_e2e / 1000)
     peak, peak_src = measured_peak_gbs()
     names = ["fastq_record_scan", "s1_count", "s2_gather", "s2_finish", "s3_pairs", "index_build", "exchange", "host_setup",
-             "s1_hash_streams", "s1_apply_streams"]
+             "s1_hash_streams", "s1_split_streams", "s1_apply_leaves"]
     stage_ms = {nm: round(float(v), 3) for nm, v in zip(names, stage)}
     roofline = make_roofline(stage, n_pairs, meta, peak, peak_src, b1.size + b2.size, args)
     roofline["stage_ms_per_step"] = stage_ms
@@ -430,27 +430,28 @@ def make_roofline(stage, n_pairs, meta, peak, peak_src, fastq_bytes, args):
       S1 direct  : sampled reads x P x e probes x 32 B, one launch per mate
       S3         : sampled pairs x 2 x P x e probes x 32 B
       S2 gather  : reference bases x (4e stored-hash bytes + 32e)
-    With hash streams S1 is two kernels whose own DRAM bytes are different (that is the point of the design):
+    With hash streams S1 is three kernels whose own DRAM bytes are different (that is the point of the design):
       s1_bin_kernel   : FASTQ bytes read + 4 B per hash written
-      s1_apply_kernel : 4 B per hash read + its 64 MiB table slice read and written back, 16 launches per mate
-    For those two the figure under the 32 B/probe convention is reported next to it as `probe_convention`; it can
-    exceed the HBM peak because the probes are served by L2, not DRAM.
+      s1_split_kernel : 4 B per hash read + 4 B per hash written
+      s1_leaf_kernel  : 4 B per hash read + the 2^k x 2 bit table read and written back once
+    one launch each per mate.  For those the figure under the 32 B/probe convention is reported next to it as
+    `probe_convention`; it can exceed the HBM peak because no probe goes to DRAM.
     """
     probes_per_mate = n_pairs * P * E                                   # s = 1 on this workload (ratio >= 100 %)
     traffic = load_traffic()
     kernels = {}
-    if stage[8] > 0 or stage[9] > 0:
-        nb = 16
-        bin_bytes = fastq_bytes / 2 + 4 * probes_per_mate
-        apply_bytes = (4 * probes_per_mate + 2 * (1 << 30)) / nb
-        kernels["s1_bin_kernel<3>"] = (stage[8] / 2, bin_bytes, probes_per_mate * SECTOR)
-        kernels["s1_apply_kernel"] = (stage[9] / (2 * nb), apply_bytes, probes_per_mate * SECTOR / nb)
+    streams = stage[8] > 0 or stage[9] > 0 or stage[10] > 0
+    if streams:
+        table_bytes = (1 << K) // 4
+        kernels["s1_bin_kernel<3>"] = (stage[8] / 2, fastq_bytes / 2 + 4 * probes_per_mate, probes_per_mate * SECTOR)
+        kernels["s1_split_kernel"] = (stage[9] / 2, 8 * probes_per_mate, probes_per_mate * SECTOR)
+        kernels["s1_leaf_kernel"] = (stage[10] / 2, 4 * probes_per_mate + 2 * table_bytes, probes_per_mate * SECTOR)
     else:
         kernels["s1_count_kernel<3>"] = (stage[1] / 2, probes_per_mate * SECTOR, probes_per_mate * SECTOR)
     kernels["s3_pairs_kernel<3>"] = (stage[4], 2 * probes_per_mate * SECTOR, 2 * probes_per_mate * SECTOR)
     kernels["s2_gather_kernel<3>"] = (stage[2], meta["ref_bases"] * (E * SECTOR + 4 * E), meta["ref_bases"] * (E * SECTOR + 4 * E))
-    share = {"s1_bin_kernel<3>": stage[8], "s1_apply_kernel": stage[9], "s1_count_kernel<3>": stage[1], "s3_pairs_kernel<3>": stage[4],
-             "s2_gather_kernel<3>": stage[2]}
+    share = {"s1_bin_kernel<3>": stage[8], "s1_split_kernel": stage[9], "s1_leaf_kernel": stage[10], "s1_count_kernel<3>": stage[1],
+             "s3_pairs_kernel<3>": stage[4], "s2_gather_kernel<3>": stage[2]}
     dom = max(kernels, key=lambda k: share[k])
     per_kernel = {}
     for k, (ms, nbytes, conv) in kernels.items():
@@ -466,7 +467,7 @@ def make_roofline(stage, n_pairs, meta, peak, peak_src, fastq_bytes, args):
             "ms_per_launch": d["ms_per_launch"], "kernels": per_kernel,
             "s1_stage_probe_convention": {"achieved": s1_conv, "frac": s1_conv / peak, "unit": "GB/s",
                                           "what": "S1 as a whole at SURVEY 8(d)'s 32 B per probe: 2 mates x reads x P x e x 32 B / S1 device time"},
-            "s1_mode": "hash streams (L2-resident table slices)" if stage[8] > 0 else "direct probes"}
+            "s1_mode": "hash streams (two-level split, table slices updated in shared memory)" if streams else "direct probes"}
 
 
 def load_traffic():

@@ -134,8 +134,10 @@ int    lhgt_set_ordinal_base(lhgt_ctx* c, uint64_t base);
  * for both files, E:1419-1444).  Returns the number of sampled reads. */
 long lhgt_s1_count(lhgt_ctx* c, int mate, uint64_t byte_budget);
 /* How S1 addresses the table: 0 = automatic (tables larger than 64 MiB are counted through hash
- * streams so every table slice is L2-resident while it is updated; smaller ones are probed directly),
- * 1 = direct probes, 2 = streams regardless of table size.  The counts are identical either way. */
+ * streams: the hashes are partitioned by their low bits until each partition's table slice fits in
+ * shared memory, where it is updated; smaller tables are probed directly), 1 = direct probes,
+ * 2 = streams regardless of table size (needs k > 18, or LHGT_LEAF_LOG2 in the environment at
+ * lhgt_create time).  The counts are identical either way. */
 int  lhgt_set_s1_mode(lhgt_ctx* c, int mode);
 /* S2 (read_index + slide_window + Peaks::add_peak, E:888-979, 550-725, 239-301).  Returns the
  * number of peaks.  [tile_begin, tile_end) restricts the table gather to a slice of the reference
@@ -173,8 +175,9 @@ int      lhgt_count_merge(lhgt_ctx* c, const void* dev_other, uint64_t bytes, ui
  * with CUDA events on the context's stream:
  * [0] FASTQ record scan  [1] S1  [2] S2 gather  [3] S2 finish  [4] S3  [5] IB kernel. */
 int  lhgt_stage_ms(const lhgt_ctx* c, float* ms6);
-/* Same with n_stages slots: [6] S1 hash-stream kernel  [7] S1 stream-apply kernels ([1] holds their sum). */
-#define LHGT_STAGES 8
+/* Same with n_stages slots: [6] S1 hash-stream kernel  [7] S1 stream-split kernel  [8] S1 leaf-apply kernel
+ * ([1] holds their sum). */
+#define LHGT_STAGES 9
 int  lhgt_stage_ms_ex(const lhgt_ctx* c, float* ms, int n_stages);
 /* Kernels launched by this context since creation. */
 long lhgt_launch_count(const lhgt_ctx* c);

@@ -353,9 +353,9 @@ class Screen:
 
     def stage_ms(self) -> np.ndarray:
         """Device ms per stage since the last call: [0] FASTQ record scan [1] S1 [2] S2 gather [3] S2 finish [4] S3
-        [5] IB [6] S1 hash-stream kernel [7] S1 stream-apply kernels."""
-        ms = np.zeros(8, dtype=np.float32)
-        _check(self._L.lhgt_stage_ms_ex(self._h, _ptr(ms), 8))
+        [5] IB [6] S1 hash-stream kernel [7] S1 stream-split kernel [8] S1 leaf-apply kernel."""
+        ms = np.zeros(9, dtype=np.float32)
+        _check(self._L.lhgt_stage_ms_ex(self._h, _ptr(ms), 9))
         return ms
 
     def launch_count(self) -> int: return int(self._L.lhgt_launch_count(self._h))

@@ -19,7 +19,6 @@
 
 using namespace lhgt;
 
-static const int kBinWarpsHost = 8;   // warps per CTA of s1_bin_kernel
 
 // ------------------------------------------------------------------------------------------------ errors
 static thread_local char g_err[512] = "";
@@ -153,7 +152,9 @@ struct lhgt_ctx {
     uint32_t* d_cands = nullptr; int32_t* d_tally = nullptr; S3Scratch scratch{};
 
     int s1_mode = 0;                         // 0 auto, 1 direct probes, 2 binned streams (lhgt_set_s1_mode)
-    uint32_t* d_bin_pool = nullptr; uint64_t bin_pool_entries = 0; uint32_t* d_bin_cursor = nullptr;
+    uint32_t *d_bin_pool_a = nullptr, *d_bin_pool_b = nullptr, *d_bin_cursor = nullptr;   // hash streams, leaf streams, their cursors
+    uint64_t bin_pool_a_entries = 0, bin_pool_b_entries = 0, bin_cursor_entries = 0;
+    int leaf_bits = 0;                       // count-table layout (HashP::leaf_bits), fixed at creation
 
     unsigned long long* d_counter = nullptr; int* d_err = nullptr;
 
@@ -166,6 +167,10 @@ static void make_hashp(lhgt_ctx* c) {
     memset(&hp, 0, sizeof hp);
     hp.k = c->k; hp.e = c->e; hp.shr = 32 - c->k;
     hp.kmask = c->k == 32 ? 0xffffffffu : ((1u << c->k) - 1u);
+    if (c->leaf_bits > 0) {
+        hp.leaf_bits = c->leaf_bits; hp.idx_bits = c->k - c->leaf_bits; hp.leaf_mask = (1u << c->leaf_bits) - 1u;
+        hp.leaf_lo = (c->k - c->leaf_bits) / 2; hp.lo_mask = (1u << hp.leaf_lo) - 1u;
+    }
     for (int i = 0; i < c->e; ++i)
         for (int z = 0; z < c->k; ++z) {
             int which = c->cc[z * c->e + i];
@@ -274,6 +279,15 @@ extern "C" int lhgt_create(lhgt_ctx** out, int device, int k, int e) {
     }
     lhgt_ctx* c = new lhgt_ctx();
     c->device = device; c->k = k; c->e = e;
+    {
+        // Table layout: leaves of 2^leaf_log2 counters (one shared-memory slice of s1_leaf_kernel), at most
+        // 2^(kMaxB1 + kMaxB2) of them.  LHGT_LEAF_LOG2 shrinks the leaves so that small-k tests run the stream path.
+        const char* g = getenv("LHGT_LEAF_LOG2");
+        int leaf_log2 = g ? atoi(g) : s1_leaf_max_log2();
+        leaf_log2 = std::max(5, std::min(leaf_log2, s1_leaf_max_log2()));
+        leaf_log2 = std::max(leaf_log2, k - (kMaxB1 + kMaxB2));
+        c->leaf_bits = k > leaf_log2 ? k - leaf_log2 : 0;
+    }
     for (int i = 0; i < LHGT_CODER_SLOTS; ++i) c->cc[i] = 100;
     for (int j = 0; j < k * e; ++j) c->cc[j] = (int16_t)(j % 3);
     make_hashp(c);
@@ -285,13 +299,13 @@ extern "C" int lhgt_create(lhgt_ctx** out, int device, int k, int e) {
     c->count_words = std::max<uint64_t>(1, entries / 16);
     if (!rc) rc = dev_alloc(&c->d_count, c->count_words);
     if (!rc) rc = dev_alloc(&c->d_peak_kmer, entries);
-    if (!rc) rc = dev_alloc(&c->d_prefilter, (size_t)1 << (kFilterLog2 - 5));
+    if (!rc) rc = dev_alloc(&c->d_prefilter, (size_t)kFilterWords);
     if (!rc) rc = dev_alloc(&c->d_counter, 4);
     if (!rc) rc = dev_alloc(&c->d_err, 4);
     if (!rc) {
         cudaMemsetAsync(c->d_count, 0, c->count_words * 4, c->st);
         cudaMemsetAsync(c->d_peak_kmer, 0, entries * 4, c->st);
-        cudaMemsetAsync(c->d_prefilter, 0, (size_t)1 << (kFilterLog2 - 3), c->st);
+        cudaMemsetAsync(c->d_prefilter, 0, ((size_t)kFilterWords) * 4, c->st);
         cudaMemsetAsync(c->d_counter, 0, 4 * sizeof(unsigned long long), c->st);
         cudaMemsetAsync(c->d_err, 0, 4 * sizeof(int), c->st);
         if (cudaStreamSynchronize(c->st) != cudaSuccess) rc = fail(LHGT_E_CUDA, "table clear failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -336,7 +350,7 @@ extern "C" void lhgt_destroy(lhgt_ctx* c) {
     dev_free(c->d_loci); dev_free(c->d_filter); dev_free(c->d_sample_bits);
     c->rand_m_buf.release(); delete c->rand_gen;
     dev_free(c->d_cands); dev_free(c->d_tally); dev_free(c->d_counter); dev_free(c->d_err);
-    dev_free(c->d_bin_pool); dev_free(c->d_bin_cursor);
+    dev_free(c->d_bin_pool_a); dev_free(c->d_bin_pool_b); dev_free(c->d_bin_cursor);
     if (c->copy_st) { cudaStreamSynchronize(c->copy_st); cudaStreamDestroy(c->copy_st); }
     for (lhgt_ctx::Prefetch* p : {&c->pf_reads[0], &c->pf_reads[1], &c->pf_index}) if (p->done) cudaEventDestroy(p->done);
     if (c->own) cudaStreamDestroy(c->own);
@@ -895,74 +909,76 @@ static const uint64_t kSliceBytes = (uint64_t)64 << 20;
 
 extern "C" int lhgt_set_s1_mode(lhgt_ctx* c, int mode) {
     if (!c || mode < 0 || mode > 2) return fail(LHGT_E_ARG, "lhgt_set_s1_mode: mode is 0 (auto), 1 (direct) or 2 (binned)");
-    if (mode == 2 && c->k < 8) return fail(LHGT_E_ARG, "binned counting needs k >= 8");
+    if (mode == 2 && c->leaf_bits < 1) return fail(LHGT_E_ARG, "stream counting needs a table of more than one leaf (k > %d; LHGT_LEAF_LOG2 lowers it)", c->k);
     c->s1_mode = mode;
     return 0;
 }
 
-static uint64_t bin_pool_limit_entries() {
+static uint64_t bin_pool_limit_entries() {                           // per pool (there are two)
     const char* g = getenv("LHGT_BIN_POOL_MB");                      // test knob: forces several chunks
-    uint64_t mb = g ? (uint64_t)atol(g) : (uint64_t)12 << 10;
+    uint64_t mb = g ? (uint64_t)atol(g) : (uint64_t)8 << 10;
     if (mb < 1) mb = 1;
     return (mb << 20) / 4;
 }
 
-// A canonical hash is the smaller of two (forward, reverse-complement) near-uniform 32-bit values, so its
-// density falls linearly: the stream of the b-th of n equal table slices receives (2(n-b)-1)/n^2 of the hashes.
-static double stream_share(int b, int nbins) { return (2.0 * (nbins - b) - 1.0) / ((double)nbins * nbins); }
-
+// S1 through hash streams (lhgt_kernels.cu, "S1, streamed form").  The sample is cut into record ranges whose hashes
+// fit the two stream pools; every range runs P1 (hash + split by b1 bits), P2 (split by b2 bits), P3 (apply leaves).
 static int s1_binned(lhgt_ctx* c, Reads& r, uint64_t byte_budget) {
-    uint64_t table_bytes = c->count_words * 4;
+    const int L = c->hp.leaf_bits;
     BinP bp{};
-    bp.log2 = 0;
-    while (bp.log2 < 4 && (table_bytes >> bp.log2) > kSliceBytes) ++bp.log2;
-    if (c->s1_mode == 2) bp.log2 = 4;                                // forced (tests at small k)
-    bp.shift = c->k - bp.log2;
-    int nbins = 1 << bp.log2;
-    // shared-memory buckets: one round of a CTA hashes kBinWarpsHost x 128 positions; 1.5x the expected share + 64
-    double round_hashes = (double)kBinWarpsHost * 128 * c->e;
-    bp.boff[0] = 0;
-    for (int b = 0; b < kMaxBins; ++b)
-        bp.boff[b + 1] = bp.boff[b] + (b < nbins ? (uint32_t)(1.5 * round_hashes * stream_share(b, nbins)) + 64 : 0);
+    bp.b1 = std::min(kMaxB1, (L + 1) / 2);
+    bp.b2 = L - bp.b1;
+    const uint64_t n_a = 1ull << bp.b1, n_l = 1ull << L;
+    bp.round_chunks = std::max(1, std::min(kBinRoundChunks, 12 / c->e));
+    double round_hashes = (double)kBinWarps * bp.round_chunks * 32 * c->e;
+    bp.bcap = (uint32_t)(1.25 * round_hashes / (double)n_a) + 16;
     // hashes one record contributes on average (sampled fraction included)
     double avg_len = r.nrec ? (double)r.seq_bases / (double)r.nrec : 0.0;
     double per_rec = std::max(1.0, avg_len - c->k + 1) * c->e * std::min(1.0, c->sample_bits_on ? c->ratio / 100.0 : 1.0);
-    const double slack = 1.0625;                                     // on top of each stream's expected share
-    uint64_t want = (uint64_t)(per_rec * (double)r.nrec * slack) + (uint64_t)nbins * 8192;
-    uint64_t total = std::min(want, bin_pool_limit_entries());
-    if (total > 0xf0000000ull) total = 0xf0000000ull;                // offsets and cursors are 32-bit
-    if (total < (uint64_t)nbins * 16384) total = (uint64_t)nbins * 16384;
-    if (c->bin_pool_entries < total) {
-        dev_free(c->d_bin_pool);
-        c->bin_pool_entries = 0;
-        int rc = dev_alloc(&c->d_bin_pool, total + 8 * kMaxBins);
+    const double slack_a = 1.0625, slack_b = 1.125;                  // on top of a stream's / a leaf's expected share
+    const uint64_t pad_a = 4096, pad_b = 256;
+    uint64_t limit = bin_pool_limit_entries();
+    if (limit > 0xf0000000ull) limit = 0xf0000000ull;
+    uint64_t floor_entries = std::max(n_a * 2 * pad_a, n_l * 2 * pad_b);
+    if (limit < floor_entries) limit = floor_entries;
+    // the largest record range both pools can take
+    double room_a = ((double)limit - (double)(n_a * pad_a)) / slack_a, room_b = ((double)limit - (double)(n_l * pad_b)) / slack_b;
+    uint64_t per_chunk = std::max<uint64_t>(1, (uint64_t)(std::min(room_a, room_b) / per_rec));
+    per_chunk = std::min<uint64_t>(per_chunk, std::max<uint64_t>(r.nrec, 1));
+    double expect = per_rec * (double)per_chunk;
+    bp.cap_a = (uint32_t)(((uint64_t)(expect / (double)n_a * slack_a) + pad_a) & ~(uint64_t)7);
+    bp.cap_b = (uint32_t)((uint64_t)(expect / (double)n_l * slack_b) + pad_b);
+    uint64_t need_a = n_a * bp.cap_a, need_b = n_l * bp.cap_b;
+    if (c->bin_pool_a_entries < need_a) {
+        dev_free(c->d_bin_pool_a); c->bin_pool_a_entries = 0;
+        int rc = dev_alloc(&c->d_bin_pool_a, need_a + 64);
         if (rc) return rc;
-        c->bin_pool_entries = total;
+        c->bin_pool_a_entries = need_a;
     }
-    if (!c->d_bin_cursor) { int rc = dev_alloc(&c->d_bin_cursor, kMaxBins); if (rc) return rc; }
-    bp.pool = c->d_bin_pool; bp.cursor = c->d_bin_cursor;
-    uint64_t usable = total - (uint64_t)nbins * 8192;
-    bp.off[0] = 0;
-    for (int b = 0; b < kMaxBins; ++b) {
-        uint64_t region = b < nbins ? ((uint64_t)((double)usable * stream_share(b, nbins)) + 8192) & ~(uint64_t)7 : 0;
-        bp.off[b + 1] = (uint32_t)(bp.off[b] + region);
+    if (c->bin_pool_b_entries < need_b) {
+        dev_free(c->d_bin_pool_b); c->bin_pool_b_entries = 0;
+        int rc = dev_alloc(&c->d_bin_pool_b, need_b + 64);
+        if (rc) return rc;
+        c->bin_pool_b_entries = need_b;
     }
-    uint64_t per_chunk = std::max<uint64_t>(1, (uint64_t)((double)usable / slack / per_rec));
+    if (c->bin_cursor_entries < n_a + n_l) {
+        dev_free(c->d_bin_cursor);
+        int rc = dev_alloc(&c->d_bin_cursor, n_a + n_l);
+        if (rc) return rc;
+        c->bin_cursor_entries = n_a + n_l;
+    }
+    bp.pool_a = c->d_bin_pool_a; bp.pool_b = c->d_bin_pool_b;
+    bp.cursor_a = c->d_bin_cursor; bp.cursor_b = c->d_bin_cursor + n_a;
+    const uint32_t* sb = c->sample_bits_on ? c->d_sample_bits : nullptr;
     for (uint64_t lo = 0; lo < r.nrec; lo += per_chunk) {
         uint64_t hi = std::min(r.nrec, lo + per_chunk);
-        CU(cudaMemsetAsync(c->d_bin_cursor, 0, kMaxBins * sizeof(uint32_t), c->st));
-        int n;
-        {
-            Span sp(c, 6);
-            n = launch_s1_binned(r.d_fq, r.d_start, r.d_end, lo, hi, byte_budget, c->sample_bits_on ? c->d_sample_bits : nullptr, c->ordinal_base, c->hp, bp,
-                                 c->d_count, c->d_counter, c->d_err, 0, c->st);
-        }
-        if (n < 0) return fail(LHGT_E_CUDA, "S1 stream kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-        c->launches += n;
-        {
-            Span sp(c, 7);
-            c->launches += launch_s1_binned(r.d_fq, r.d_start, r.d_end, lo, hi, byte_budget, c->sample_bits_on ? c->d_sample_bits : nullptr, c->ordinal_base, c->hp, bp,
-                                            c->d_count, c->d_counter, c->d_err, 1, c->st);
+        CU(cudaMemsetAsync(c->d_bin_cursor, 0, (n_a + n_l) * sizeof(uint32_t), c->st));
+        for (int phase = 0; phase < 3; ++phase) {
+            Span sp(c, 6 + phase);
+            int n = launch_s1_binned(r.d_fq, r.d_start, r.d_end, lo, hi, byte_budget, sb, c->ordinal_base, c->hp, bp,
+                                     c->d_count, c->d_counter, c->d_err, phase, c->st);
+            if (n < 0) return fail(LHGT_E_CUDA, "S1 stream kernel launch failed (phase %d): %s", phase, cudaGetErrorString(cudaGetLastError()));
+            c->launches += n;
         }
     }
     return 0;
@@ -976,7 +992,7 @@ extern "C" long lhgt_s1_count(lhgt_ctx* c, int mate, uint64_t byte_budget) {
     CU(cudaSetDevice(c->device));
     CU(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), c->st));
     CU(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->st));
-    bool binned = c->s1_mode == 2 || (c->s1_mode == 0 && c->count_words * 4 > kSliceBytes);
+    bool binned = c->s1_mode == 2 || (c->s1_mode == 0 && c->leaf_bits >= 1 && c->count_words * 4 > kSliceBytes);
     {
         Span sp(c, 1);
         if (binned) {
@@ -1098,9 +1114,11 @@ extern "C" long lhgt_s3_pairs(lhgt_ctx* c, long first, long count) {
     CU(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->st));
     if (c->n_peaks > 0) {
         Span sp(c, 4);
-        c->launches += launch_s3(a.d_fq, a.d_start, a.d_end, a.nrec, b.d_fq, b.d_start, b.d_end, b.nrec, b.tail_start, b.tail_len,
+        int nl = launch_s3(a.d_fq, a.d_start, a.d_end, a.nrec, b.d_fq, b.d_start, b.d_end, b.nrec, b.tail_start, b.tail_len,
                                  (uint64_t)first, cnt, c->sample_bits_on ? c->d_sample_bits : nullptr, c->ordinal_base, c->hp, c->d_prefilter, c->d_peak_kmer, c->d_loci,
                                  c->d_filter, c->scratch, s3_grid_blocks(c->device), c->d_counter, c->d_err, c->st);
+        if (nl < 0) return fail(LHGT_E_CUDA, "S3 kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        c->launches += nl;
     }
     unsigned long long sampled = 0; int flag = 0;
     CU(cudaMemcpyAsync(&sampled, c->d_counter, sizeof sampled, cudaMemcpyDeviceToHost, c->st));
@@ -1171,7 +1189,7 @@ extern "C" int lhgt_count_table_copy(lhgt_ctx* c, uint8_t* dst) {
     uint8_t* d = nullptr;
     int rc = dev_alloc(&d, entries);
     if (rc) return rc;
-    c->launches += launch_count_unpack(c->d_count, entries, d, c->st);
+    c->launches += launch_count_unpack(c->d_count, entries, c->hp, d, c->st);
     cudaError_t e1 = cudaMemcpyAsync(dst, d, entries, cudaMemcpyDeviceToHost, c->st);
     if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(c->st);
     cudaFree(d);

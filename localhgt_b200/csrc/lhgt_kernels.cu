@@ -2,6 +2,7 @@
 // "E:" = reference src/extract_ref_normal_peak.cpp (cited for semantics only; nothing here is a
 // translation of it — see DESIGN.md §4 for the data-parallel forms these kernels evaluate).
 #include "lhgt_kernels.cuh"
+#include <cstdlib>
 
 namespace lhgt {
 
@@ -101,7 +102,7 @@ __device__ __forceinline__ uint32_t le_hash(const LeWin& k, const HashP& hp, int
 }
 
 // ------------------------------------------------------------------------------------------------
-// 2-bit saturating count table: entry h lives in bits [2*(h&15), +2) of word h>>4
+// 2-bit saturating count table: entry g = tbl_index(h) lives in bits [2*(g&15), +2) of word g>>4
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t ld_table(const uint32_t* p) {
     uint32_t v;
@@ -114,7 +115,74 @@ __device__ __forceinline__ uint32_t ld_stream(const uint32_t* p) {
     return v;
 }
 
-// count[h] = min(3, count[h] + 1), exact under any interleaving (E:1082-1084 made race-free).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- TMA (cp.async.bulk) + mbarrier plumbing ----
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LHGT_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LHGT_DONE;\n"
+        "bra LHGT_WAIT;\n"
+        "LHGT_DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// 1-D bulk copy shared -> global (bulk async-group completion)
+__device__ __forceinline__ void bulk_store(void* dst, const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_store_commit_wait() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// ---- read staging -------------------------------------------------------------------------------------------
+// A warp has the bytes of the read it will hash NEXT copied into its own shared-memory slot by the TMA unit (one
+// cp.async.bulk issued by lane 0, completion counted on the slot's mbarrier), so no lane ever waits on a FASTQ byte
+// in DRAM: by the time a read is hashed its bytes have been on chip for a whole read's worth of work, and no
+// register or load scoreboard is held meanwhile.  A slot receives the 16-byte granules that cover [start, start+len).
+constexpr int kStageBytes = 528;                                       // 15 bytes of misalignment + kMaxReadLen, in granules
+static_assert(kStageBytes % 16 == 0 && kStageBytes >= 15 + kMaxReadLen, "stage slot too small");
+
+// fq must be 16-byte aligned (device allocations are; lhgt_reads_attach_device checks).  Returns the offset of the
+// read's first byte inside the slot.  The last granule may run past start + len: it stays inside the 16-byte block
+// that holds the read's last byte.  Call with len > 0; `bytes_out` accumulates what the barrier has to expect.
+__device__ __forceinline__ uint32_t stage_granules(uint64_t start, uint32_t len) { return ((uint32_t)start & 15u) + len + 15u >> 4; }
+__device__ __forceinline__ uint32_t stage_read(uint8_t* slot, uint64_t* bar, const uint8_t* __restrict__ fq, uint64_t start, uint32_t len, int lane) {
+    uint32_t mis = (uint32_t)start & 15u;
+    if (lane == 0) {
+        uint32_t bytes = stage_granules(start, len) << 4;
+        mbar_expect_tx(bar, bytes);
+        bulk_load(slot, fq + (start - mis), bytes, bar);
+    }
+    return mis;
+}
+// S3 stages the two mates of a pair behind ONE barrier
+__device__ __forceinline__ void stage_pair_reads(uint8_t* slot1, uint8_t* slot2, uint64_t* bar, const uint8_t* __restrict__ fq1, uint64_t s1,
+                                                 uint32_t l1, const uint8_t* __restrict__ fq2, uint64_t s2, uint32_t l2, int lane) {
+    if (lane == 0) {
+        uint32_t b1 = l1 ? stage_granules(s1, l1) << 4 : 0u, b2 = l2 ? stage_granules(s2, l2) << 4 : 0u;
+        mbar_expect_tx(bar, b1 + b2);
+        if (b1) bulk_load(slot1, fq1 + (s1 & ~15ull), b1, bar);
+        if (b2) bulk_load(slot2, fq2 + (s2 & ~15ull), b2, bar);
+    }
+}
+
+// count[h] = min(3, count[h] + 1), exact under any interleaving (E:1082-1084 made race-free).  Here and in
+// bump_batch `h` is the TABLE INDEX of the hash (tbl_index), not the hash itself.
 __device__ __forceinline__ void bump(uint32_t* count, uint32_t h, uint32_t seen) {
     uint32_t* addr = count + (h >> 4);
     int sh = (h & 15u) * 2;
@@ -406,7 +474,7 @@ int launch_index_build(const uint8_t* seq, const Contig* contigs, const Tile* ti
 // packed into shared memory by ballots; each lane hashes positions lane, lane+32, ... and issues all
 // its table loads before the first compare-and-swap so ~12 independent sectors per lane are in flight.
 // ------------------------------------------------------------------------------------------------
-constexpr int kS1Warps = 8, kS1Unroll = 4;
+constexpr int kS1Warps = 8;
 
 __device__ __forceinline__ bool is_sampled(const uint32_t* __restrict__ sample_bits, uint64_t ordinal) {
     if (!sample_bits) return true;
@@ -451,7 +519,7 @@ __global__ void __launch_bounds__(kS1Warps * 32, 4) s1_count_kernel(
 #pragma unroll
             for (int i = 0; i < (E ? E : kMaxE); ++i) {
                 ok[i] = i < e && kw.valid;
-                h[i] = i < e ? le_hash(kw, hp, i) : 0u;
+                h[i] = i < e ? tbl_index(le_hash(kw, hp, i), hp) : 0u;   // table index from here on
                 seen[i] = 0u;
                 if (ok[i]) seen[i] = ld_table(count + (h[i] >> 4));
             }
@@ -485,20 +553,25 @@ int launch_s1(const uint8_t* fq, const uint64_t* rec_start, const uint64_t* rec_
 }
 
 // ------------------------------------------------------------------------------------------------
-// S1, binned form.  A 2^k-entry table far larger than L2 makes every direct probe a
-// 128-byte DRAM fill (profiles/r01_probe_bench_*: 43 G probes/s), while a table slice that fits L2
-// sustains 290 G probes/s.  So counting runs in two phases:
-//   A  s1_bin_kernel: hash the sampled reads and append every hash to one of 2^bin_log2 streams
-//      chosen by its top bits (per-CTA shared-memory buckets, flushed as coalesced runs);
-//   B  s1_apply_kernel, once per stream: the 64 MiB table slice the stream addresses stays L2-resident
-//      while the stream is read back sequentially and applied with the same load + CAS update.
-// Saturating increments commute, so the table is bit-identical to the direct form's.  A stream that
-// would overflow its region (pathological, low-complexity input) applies the surplus directly.
+// S1, streamed form.  A 2^k-entry table far larger than L2 makes every direct probe a
+// 128-byte DRAM fill (profiles/r01_probe_bench_*: 43 G probes/s), and even an L2-resident slice is capped by
+// the L2's atomic rate (profiles/r01_apply_bench_*: ~125 G updates/s).  So counting moves the hashes, not the
+// table: the table is stored leaf-major (HashP: a leaf = the hashes sharing a field of middle bits) and
+//   P1  s1_bin_kernel   hashes the sampled reads and appends every hash to one of 2^b1 streams chosen by its
+//                       first b1 leaf bits (per-CTA shared-memory buckets, flushed as coalesced runs);
+//   P2  s1_split_kernel splits every stream by the other b2 bits of the leaf field into leaf streams (tile histogram -> one
+//                       reservation per leaf -> ordered scatter through shared memory -> coalesced runs);
+//   P3  s1_leaf_kernel  one CTA per leaf: the leaf's table slice (<= 64 KiB) is bulk-copied into shared memory,
+//                       the leaf stream is applied to it with shared-memory compare-and-swap, and the slice
+//                       is copied back.  No global atomics, no random DRAM access.
+// Saturating increments commute, so the table is bit-identical to the direct form's.  Middle bits of a canonical
+// hash are uniform, so streams and leaves fill evenly; whatever does not fit a bucket or a stream region
+// (low-complexity input) is applied directly with the global compare-and-swap -- exact either way.
 // ------------------------------------------------------------------------------------------------
-constexpr int kBinWarps = 8;
 
-__device__ __forceinline__ void bump_direct(uint32_t* count, uint32_t h) {
-    bump(count, h, ld_table(count + (h >> 4)));
+__device__ __forceinline__ void bump_direct(uint32_t* count, uint32_t h, const HashP& hp) {
+    uint32_t g = tbl_index(h, hp);
+    bump(count, g, ld_table(count + (g >> 4)));
 }
 
 template <int E>
@@ -507,60 +580,87 @@ __global__ void __launch_bounds__(kBinWarps * 32, 4) s1_bin_kernel(
     uint64_t rec_lo, uint64_t rec_hi, uint64_t budget, const uint32_t* __restrict__ sample_bits, uint64_t ordinal_base,
     HashP hp, BinP bp, uint32_t* __restrict__ count, unsigned long long* __restrict__ n_sampled, int* __restrict__ err) {
     extern __shared__ uint32_t dyn[];                         // two bucket sets: one fills while the other drains
-    __shared__ uint32_t cnt[2][kMaxBins];
-    __shared__ uint2 bnd[kMaxBins];                           // bucket b of a set = set base + [bnd[b].x, bnd[b].y)
+    __shared__ uint32_t cnt[2][1 << kMaxB1];
     __shared__ uint8_t lut[256];
+    __shared__ __align__(16) uint8_t stage[kBinWarps][2][kStageBytes];
+    __shared__ __align__(8) uint64_t sbar[kBinWarps][2];      // "slot filled", one per stage slot
     const int e = E ? E : hp.e;
-    const int nbins = 1 << bp.log2;
-    const uint32_t set_entries = bp.boff[kMaxBins];
+    const int nbins = 1 << bp.b1;
+    const uint32_t bin_mask = (uint32_t)nbins - 1u;
+    const int bin_lo = hp.leaf_lo;
+    const uint32_t bcap = bp.bcap;
+    const uint32_t set_entries = bcap << bp.b1;
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x < kMaxBins) {
-        bnd[threadIdx.x] = make_uint2(bp.boff[threadIdx.x], bp.boff[threadIdx.x + 1]);
-        cnt[0][threadIdx.x] = 0; cnt[1][threadIdx.x] = 0;
-    }
+    if (threadIdx.x < (1 << kMaxB1)) { cnt[0][threadIdx.x] = 0; cnt[1][threadIdx.x] = 0; }
+    if (lane == 0) { mbar_init(&sbar[warp][0], 1); mbar_init(&sbar[warp][1], 1); }
     fill_base_lut(lut);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    // the two streams this warp drains: b and nbins-1-b together carry an equal share of the hashes (stream_share)
-    int mine_b[2] = {warp < nbins ? warp : -1, nbins - 1 - warp >= kBinWarps ? nbins - 1 - warp : -1};
+    // Draining: this warp owns streams warp, warp + 8, ...; they are drained side by side, a group of `lpb` lanes each
+    // (64 streams: 8 per warp, 4 lanes each), so no lane idles on a short run and there is no per-stream loop.
+    const int per_warp = (nbins + kBinWarps - 1) / kBinWarps;             // 1, 2, 4 or 8
+    const int lpb = 32 / per_warp;
+    const int grp = lane / lpb, sub = lane - grp * lpb;
+    const int my_bin = warp + kBinWarps * grp;
+    const bool owner = my_bin < nbins;
     unsigned long long mine = 0;
     const uint64_t stride = (uint64_t)gridDim.x * kBinWarps;
     auto next_sampled = [&](uint64_t q) {                     // warp-uniform
         while (q < rec_hi && !is_sampled(sample_bits, q + ordinal_base)) q += stride;
         return q;
     };
-    // The candidate record (next sampled one of this warp) is always one step ahead: its offsets are loaded when the
-    // current read is accepted, its first 64 bases after the current read's first chunk, so a warp never sits
-    // through the start -> end -> bytes load chain between reads.
-    uint64_t r = next_sampled(rec_lo + (uint64_t)blockIdx.x * kBinWarps + warp);
-    uint64_t cs = 0, ce = 0;
-    if (r < rec_hi) { cs = rec_start[r]; ce = rec_end[r]; }
-    uint32_t pb0 = 0, pb1 = 0;
-    bool pb_ready = false;
-    const uint8_t* src = fq;
+    // Two records ahead: the offsets of the record after next are in flight while the bytes of the next record are
+    // being staged (both issued when the current read was accepted), so a warp never sits through the
+    // start -> end -> bytes load chain between reads.
+    uint64_t rn = next_sampled(rec_lo + (uint64_t)blockIdx.x * kBinWarps + warp);   // next record: offsets known (ns, ne)
+    uint64_t ns = 0, ne = 0;
+    if (rn < rec_hi) { ns = rec_start[rn]; ne = rec_end[rn]; }
+    uint64_t rnn = rn < rec_hi ? next_sampled(rn + stride) : rn;   // the one after: offsets loading (nns, nne)
+    uint64_t nns = 0, nne = 0;
+    if (rnn < rec_hi) { nns = rec_start[rnn]; nne = rec_end[rnn]; }
+    bool nstaged = false;                                     // next record's bytes are on their way into stage[warp][slot ^ 1]
+    uint32_t nmis = 0, phase = 0;                             // phase bit s: parity the next fill of slot s completes
+    int slot = 0;
+    auto stageable = [&](uint64_t s0, uint64_t e0) { return s0 <= budget && e0 - s0 <= (uint64_t)kMaxReadLen && e0 - s0 >= (uint64_t)hp.k; };
+    if (rn < rec_hi && stageable(ns, ne)) { nmis = stage_read(stage[warp][1], &sbar[warp][1], fq, ns, (uint32_t)(ne - ns), lane); nstaged = true; }
+    const uint8_t* src = stage[warp][0];
     int len = 0, w = 0, nch = 0;                              // current read: length, next word to pack, hash chunks
-    uint32_t chn = 0;                                         // this lane's byte of word w, loaded one chunk ahead
+    uint32_t chn = 0;                                         // this lane's byte of word w, read one chunk ahead
     Planes prev{0, 0, 0, 0};
     bool have = false;
     int set = 0;                                              // the set this round fills; set^1 drains
     for (bool first_round = true;; first_round = false) {
-        while (!have && r < rec_hi) {                         // turn the candidate into the current read
-            uint64_t start = cs, len64 = ce - cs;
-            uint32_t b0 = pb0, b1 = pb1;
-            bool fetched = pb_ready;
-            r = next_sampled(r + stride);
-            if (r < rec_hi) { cs = rec_start[r]; ce = rec_end[r]; }
-            pb_ready = false;
-            if (start > budget) continue;                     // Q15
-            if (len64 > (uint64_t)kMaxReadLen) { if (lane == 0) atomicExch(err, 1); continue; }
-            ++mine;
+        while (!have && rn < rec_hi) {                        // turn the next record into the current read
+            uint64_t start = ns, len64 = ne - ns;
+            bool staged = nstaged;
+            uint32_t mis = nmis;
+            nstaged = false;
+            bool too_long = len64 > (uint64_t)kMaxReadLen;
+            bool counted = start <= budget && !too_long;      // Q15
+            bool accept = counted && len64 >= (uint64_t)hp.k;
+            if (accept) {
+                slot ^= 1;                                    // the slot the bytes were (or now are) staged into
+                if (!staged) mis = stage_read(stage[warp][slot], &sbar[warp][slot], fq, start, (uint32_t)len64, lane);   // only after a skipped record
+                mbar_wait(&sbar[warp][slot], (phase >> slot) & 1u);
+                phase ^= 1u << slot;
+            }
+            rn = rnn; ns = nns; ne = nne;
+            if (rnn < rec_hi) {
+                rnn = next_sampled(rnn + stride);
+                if (rnn < rec_hi) { nns = rec_start[rnn]; nne = rec_end[rnn]; }
+            }
+            if (start <= budget && too_long && lane == 0) atomicExch(err, 1);
+            mine += counted;
+            if (!accept) continue;
             len = (int)len64;
             int np = len - hp.k + 1;
-            if (np <= 0) continue;
-            src = fq + start;
-            if (!fetched) { b0 = lane < len ? src[lane] : 0u; b1 = 32 + lane < len ? src[32 + lane] : 0u; }
+            src = stage[warp][slot] + mis;
+            __syncwarp();                                     // every lane is done with the other slot
+            if (rn < rec_hi && stageable(ns, ne)) { nmis = stage_read(stage[warp][slot ^ 1], &sbar[warp][slot ^ 1], fq, ns, (uint32_t)(ne - ns), lane); nstaged = true; }
             nch = (np + 31) >> 5;
-            prev = pack_word(b0, lut);
-            chn = b1;
+            prev = pack_word(lane < len ? src[lane] : 0u, lut);
+            chn = 32 + lane < len ? src[32 + lane] : 0u;
             w = 1;
             have = true;
         }
@@ -568,74 +668,49 @@ __global__ void __launch_bounds__(kBinWarps * 32, 4) s1_bin_kernel(
         bool any = __syncthreads_or(have);
         // reserve room in the global streams for what last round produced; the answers are picked up after this
         // round's hashing, so the atomics' round trip costs nothing
-        uint32_t dn[2] = {0, 0}, dg[2] = {0, 0};
-        if (!first_round) {
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                int b = mine_b[q];
-                if (b < 0) continue;
-                dn[q] = min(cnt[set ^ 1][b], bnd[b].y - bnd[b].x);
-                if (dn[q] && lane == 0) dg[q] = atomicAdd(bp.cursor + b, dn[q]);
-            }
+        uint32_t dn = 0, dg = 0;
+        if (!first_round && owner) {
+            dn = min(cnt[set ^ 1][my_bin], bcap);
+            if (dn && sub == 0) dg = atomicAdd(bp.cursor_a + my_bin, dn);
         }
         if (any) {
             uint32_t* buckets = dyn + set * set_entries;
             uint32_t* fill = cnt[set];
 #pragma unroll 1
-            for (int it = 0; it < kS1Unroll && have; ++it) {  // chunk w-1 = words w-1 (prev) and w (cur)
+            for (int it = 0; it < bp.round_chunks && have; ++it) {  // chunk w-1 = words w-1 (prev) and w (cur)
                 Planes cur = pack_word(chn, lut);
                 int pn = (w + 1) * 32 + lane;
                 chn = pn < len ? src[pn] : 0u;
                 LeWin kw = le_window(prev, cur, lane, hp);
                 if (kw.valid) {
+                    uint32_t h[E ? E : kMaxE], at[E ? E : kMaxE];
+#pragma unroll
+                    for (int i = 0; i < (E ? E : kMaxE); ++i)
+                        if (i < e) { h[i] = le_hash(kw, hp, i); at[i] = atomicAdd(&fill[(h[i] >> bin_lo) & bin_mask], 1u); }
 #pragma unroll
                     for (int i = 0; i < (E ? E : kMaxE); ++i)
                         if (i < e) {
-                            uint32_t h = le_hash(kw, hp, i);
-                            uint32_t b = h >> bp.shift;
-                            uint2 lim = bnd[b];
-                            uint32_t slot = lim.x + atomicAdd(&fill[b], 1u);
-                            if (slot < lim.y) buckets[slot] = h;
-                            else bump_direct(count, h);       // bucket full: rare, exact either way
+                            if (at[i] < bcap) buckets[((h[i] >> bin_lo) & bin_mask) * bcap + at[i]] = h[i];
+                            else bump_direct(count, h[i], hp);   // bucket full: rare, exact either way
                         }
                 }
                 prev = cur;
                 if (++w > nch) { have = false; }
-                if (!pb_ready && r < rec_hi) {                // candidate's first two words, consumed a read later
-                    uint64_t nlen = ce - cs;
-                    const uint8_t* nsrc = fq + cs;
-                    pb0 = (uint64_t)lane < nlen ? nsrc[lane] : 0u;
-                    pb1 = (uint64_t)(32 + lane) < nlen ? nsrc[32 + lane] : 0u;
-                    pb_ready = true;
-                }
             }
         }
-        if (!first_round) {                                   // drain last round's set: one coalesced run per stream
-            const uint32_t* drain = dyn + (set ^ 1) * set_entries;
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                int b = mine_b[q];
-                if (b < 0) continue;
-                uint32_t n = dn[q];
-                if (n) {
-                    uint32_t g = __shfl_sync(kFull, dg[q], 0);
-                    uint32_t b0 = bnd[b].x;
-                    uint32_t* dst = bp.pool + bp.off[b];
-                    uint32_t cap = bp.off[b + 1] - bp.off[b];
-                    if (g + n <= cap) {
-                        dst += g;
-                        for (uint32_t x = lane; x < n; x += 32) dst[x] = drain[b0 + x];
-                    } else {
-                        for (uint32_t x = lane; x < n; x += 32) {
-                            uint32_t h = drain[b0 + x];
-                            if (g + x < cap) dst[g + x] = h;
-                            else bump_direct(count, h);       // stream region full
-                        }
-                    }
+        if (!first_round) {                                   // drain last round's set: coalesced runs, all streams of this warp at once
+            dg = __shfl_sync(kFull, dg, grp * lpb);
+            if (owner && dn) {
+                const uint32_t* from = dyn + (set ^ 1) * set_entries + (uint32_t)my_bin * bcap;
+                uint32_t* dst = bp.pool_a + (size_t)my_bin * bp.cap_a;
+                for (uint32_t x = sub; x < dn; x += lpb) {
+                    uint32_t h = from[x];
+                    if (dg + x < bp.cap_a) dst[dg + x] = h;
+                    else bump_direct(count, h, hp);           // stream region full
                 }
-                __syncwarp();
-                if (lane == 0) cnt[set ^ 1][b] = 0;
             }
+            __syncwarp();
+            if (owner && sub == 0) cnt[set ^ 1][my_bin] = 0;
         }
         if (!any) break;
         set ^= 1;
@@ -643,122 +718,155 @@ __global__ void __launch_bounds__(kBinWarps * 32, 4) s1_bin_kernel(
     if (lane == 0 && mine) atomicAdd(n_sampled, mine);
 }
 
-// ---- TMA (cp.async.bulk) + mbarrier plumbing for the stream reader ----
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "LHGT_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra LHGT_DONE;\n"
-        "bra LHGT_WAIT;\n"
-        "LHGT_DONE:\n"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// 1-D bulk copy global -> shared, completion counted in bytes on `bar`; the stream is read once: evict-first in L2
-__device__ __forceinline__ void bulk_load_evict_first(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
-}
+// P2.  Grid (tiles, 2^b1): CTA (x, y) splits tile x of stream y by bits [b1, b1 + b2) of the hash.
+constexpr int kSplitThreads = 512, kSplitPer = 16, kSplitTile = kSplitThreads * kSplitPer;   // 8192 hashes = 32 KiB
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// Phase B.  A CTA walks tiles of 2048 hashes of one stream.  An elected thread keeps a ring of TMA bulk copies in
-// flight (UBLKCP; "full" mbarriers count the bytes landed, "empty" mbarriers count the warps done with a slot), so
-// the stream never occupies load scoreboards and every thread spends its own on the 8 table probes it issues per
-// tile.  No CTA-wide barrier inside the loop.
-constexpr int kApplyThreads = 256;
-template <int PER, int STAGES> constexpr size_t apply_smem_bytes() {
-    return (size_t)STAGES * kApplyThreads * PER * sizeof(uint32_t) + 2 * STAGES * sizeof(uint64_t);
-}
-
-// MODE 0: the product.  Other modes exist for tools/apply_bench.cu only (cost probes): 1 = probes without updates.
-template <int PER, int STAGES, int MIN_CTAS, int MODE>
-__global__ void __launch_bounds__(kApplyThreads, MIN_CTAS) s1_apply_kernel(const uint32_t* __restrict__ stream,
-                                                                           const uint32_t* __restrict__ cursor, uint32_t cap,
-                                                                           uint32_t* __restrict__ count) {
-    constexpr int kTileN = kApplyThreads * PER;
-    extern __shared__ __align__(128) uint32_t apply_smem[];
-    uint32_t* tiles = apply_smem;                                              // [STAGES][kTileN]
-    uint64_t* full = reinterpret_cast<uint64_t*>(apply_smem + STAGES * kTileN);
-    uint64_t* empty = full + STAGES;
-    const uint32_t n = min(*cursor, cap);
-    const uint32_t ntiles = (n + kTileN - 1) / kTileN;
-    if (blockIdx.x >= ntiles) return;
-    const uint32_t mine = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;    // tiles blockIdx.x + i * gridDim.x
-    const int lane = threadIdx.x & 31;
-    auto issue = [&](uint32_t j) {                                             // thread 0 only
-        uint32_t stg = j % STAGES;
-        if (j >= (uint32_t)STAGES) mbar_wait(&empty[stg], ((j / STAGES) - 1u) & 1u);   // previous tenant drained
-        uint32_t first = (blockIdx.x + j * gridDim.x) * kTileN;
-        uint32_t bytes = (min((uint32_t)kTileN, n - first) * 4u + 15u) & ~15u;  // regions are multiples of 8 entries
-        mbar_expect_tx(&full[stg], bytes);
-        bulk_load_evict_first(tiles + stg * kTileN, stream + first, bytes, &full[stg]);
-    };
-    if (threadIdx.x == 0) {
-        for (int s2 = 0; s2 < STAGES; ++s2) { mbar_init(&full[s2], 1); mbar_init(&empty[s2], kApplyThreads / 32); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        for (uint32_t j = 0; j < min(mine, (uint32_t)STAGES - 1); ++j) issue(j);
+__global__ void __launch_bounds__(kSplitThreads, 3) s1_split_kernel(BinP bp, HashP hp, uint32_t* __restrict__ count) {
+    __shared__ uint32_t tile[kSplitTile];                      // the tile again, grouped by sub-stream
+    __shared__ uint32_t hist[1 << kMaxB2], off[1 << kMaxB2];
+    __shared__ uint2 route[1 << kMaxB2];                       // per sub-stream: {pool_b index of grouped position 0, first position that does not fit}
+    __shared__ uint32_t wsum[8];
+    const int nsub = 1 << bp.b2;
+    const uint32_t sub_mask = (uint32_t)nsub - 1u;
+    const int sub_lo = hp.leaf_lo + bp.b1;
+    const uint32_t y = blockIdx.y;
+    const uint32_t n = min(bp.cursor_a[y], bp.cap_a);
+    const uint32_t first = blockIdx.x * kSplitTile;
+    if (first >= n) return;
+    const uint32_t valid = min((uint32_t)kSplitTile, n - first);
+    const uint32_t* __restrict__ in = bp.pool_a + (size_t)y * bp.cap_a + first;
+    if (threadIdx.x < nsub) hist[threadIdx.x] = 0;
+    uint32_t h[kSplitPer], rank[kSplitPer / 2];                // two 16-bit ranks per register
+#pragma unroll
+    for (int q = 0; q < kSplitPer; ++q) {
+        uint32_t x = threadIdx.x + q * kSplitThreads;
+        h[q] = x < valid ? ld_stream(in + x) : 0u;
     }
     __syncthreads();
-    uint32_t sink = 0;
-    for (uint32_t i = 0; i < mine; ++i) {
-        if (threadIdx.x == 0 && i + STAGES - 1 < mine) issue(i + STAGES - 1);
-        uint32_t stg = i % STAGES;
-        mbar_wait(&full[stg], (i / STAGES) & 1u);
-        uint32_t first = (blockIdx.x + i * gridDim.x) * kTileN;
-        uint32_t valid = min((uint32_t)kTileN, n - first);
-        const uint32_t* tile = tiles + stg * kTileN;
-        uint32_t h[PER], seen[PER];
-        bool ok[PER];
 #pragma unroll
-        for (int q = 0; q < PER; ++q) {
-            uint32_t x = threadIdx.x + q * kApplyThreads;
-            ok[q] = x < valid;
-            h[q] = tile[x];
-        }
+    for (int q = 0; q < kSplitPer; ++q) {
+        uint32_t x = threadIdx.x + q * kSplitThreads;
+        uint32_t r = x < valid ? atomicAdd(&hist[(h[q] >> sub_lo) & sub_mask], 1u) : 0u;
+        if (q & 1) rank[q >> 1] |= r << 16; else rank[q >> 1] = r;
+    }
+    __syncthreads();
+    // exclusive scan of the histogram (<= 256 entries: threads 0..255, one each) + one reservation per leaf
+    {
+        uint32_t v = threadIdx.x < nsub ? hist[threadIdx.x] : 0u;
+        if (threadIdx.x < (1 << kMaxB2)) {
+            int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+            uint32_t inc = v;
 #pragma unroll
-        for (int q = 0; q < PER; ++q)
-            if (ok[q]) seen[q] = ld_table(count + (h[q] >> 4));
-        __syncwarp();                                                          // every lane's tile words are in registers
-        if (lane == 0) mbar_arrive(&empty[stg]);
-        if (MODE == 0) bump_batch<PER>(count, h, seen, ok);
-        else if (MODE == 1) {
-#pragma unroll
-            for (int q = 0; q < PER; ++q) if (ok[q]) sink += seen[q];
-        } else {                                                               // cost probes, NOT exact: tools/apply_bench.cu
-#pragma unroll
-            for (int q = 0; q < PER; ++q) {
-                int sh = (h[q] & 15u) * 2;
-                if (ok[q] && ((seen[q] >> sh) & 3u) < 3u) {
-                    uint32_t* addr = count + (h[q] >> 4);
-                    if (MODE == 2) sink += atomicAdd(addr, 1u << sh);          // returning add
-                    else if (MODE == 3) atomicAdd(addr, 1u << sh);             // fire-and-forget (RED)
-                    else if (MODE == 4) atomicOr(addr, 1u << sh);              // RED.OR
-                    else if (MODE == 5) atomicCAS(addr, seen[q], seen[q] + (1u << sh));   // CAS, result dropped
-                }
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t t = __shfl_up_sync(kFull, inc, d);
+                if (lane >= d) inc += t;
+            }
+            if (lane == 31) wsum[wp] = inc;
+            asm volatile("bar.sync 1, 256;");                  // the first eight warps only
+            uint32_t before = 0;
+            for (int q = 0; q < wp; ++q) before += wsum[q];
+            if (threadIdx.x < nsub) {
+                uint32_t o = before + inc - v;
+                off[threadIdx.x] = o;
+                uint32_t leaf = y | ((uint32_t)threadIdx.x << bp.b1);
+                uint32_t g = v ? atomicAdd(bp.cursor_b + leaf, v) : 0u;
+                // grouped position p of this sub-stream lands at pool_b[leaf * cap_b + g + (p - o)] while g + (p - o) < cap_b
+                route[threadIdx.x] = make_uint2(leaf * bp.cap_b + g - o, g < bp.cap_b ? o + (bp.cap_b - g) : o);
             }
         }
     }
-    if (MODE != 0 && sink == 0x9e3779b9u) count[0] = sink;
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < kSplitPer; ++q) {
+        uint32_t x = threadIdx.x + q * kSplitThreads;
+        uint32_t r = (q & 1) ? rank[q >> 1] >> 16 : rank[q >> 1] & 0xffffu;
+        if (x < valid) tile[off[(h[q] >> sub_lo) & sub_mask] + r] = h[q];
+    }
+    __syncthreads();
+    // neighbours in the grouped tile are neighbours in their leaf stream: coalesced runs
+    for (uint32_t p = threadIdx.x; p < valid; p += kSplitThreads) {
+        uint32_t hh = tile[p];
+        uint2 rt = route[(hh >> sub_lo) & sub_mask];
+        if (p < rt.y) bp.pool_b[rt.x + p] = hh;
+        else bump_direct(count, hh, hp);                       // leaf region full
+    }
 }
 
-constexpr int kApplyPer = 8, kApplyStages = 4, kApplyMinCtas = 4;
-constexpr size_t kApplySmem = apply_smem_bytes<kApplyPer, kApplyStages>();
+// P3.  One CTA per leaf.
+constexpr int kLeafThreads = 256, kLeafPer = 8;
+constexpr int kLeafMaxLog2 = 18;                               // 2^18 counters = 64 KiB of shared memory
 
-size_t s1_bin_smem_bytes(const BinP& bp) { return (size_t)2 * bp.boff[kMaxBins] * sizeof(uint32_t); }   // two bucket sets
+__global__ void __launch_bounds__(kLeafThreads, 3) s1_leaf_kernel(BinP bp, HashP hp, uint32_t* __restrict__ count) {
+    extern __shared__ __align__(128) uint32_t slice[];         // 2^(idx_bits - 4) words
+    __shared__ __align__(8) uint64_t bar;
+    const uint32_t leaf = blockIdx.x;
+    const uint32_t n = min(bp.cursor_b[leaf], bp.cap_b);
+    if (n == 0) return;
+    const uint32_t words = 1u << (hp.idx_bits - 4);
+    uint32_t* __restrict__ home = count + (size_t)leaf * words;
+    const uint32_t* __restrict__ in = bp.pool_b + (size_t)leaf * bp.cap_b;
+    const bool bulk = words >= 4;                              // bulk copies move multiples of 16 bytes
+    if (bulk) {
+        if (threadIdx.x == 0) {
+            mbar_init(&bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&bar, words * 4u);
+            for (uint32_t o = 0; o < words; o += 4096u)        // 16 KiB pieces
+                bulk_load(slice + o, home + o, min(4096u, words - o) * 4u, &bar);
+        }
+    } else {
+        for (uint32_t x = threadIdx.x; x < words; x += kLeafThreads) slice[x] = home[x];
+    }
+    // the first hashes travel while the slice does
+    uint32_t h[kLeafPer];
+#pragma unroll
+    for (int q = 0; q < kLeafPer; ++q) {
+        uint32_t x = threadIdx.x + q * kLeafThreads;
+        h[q] = x < n ? ld_stream(in + x) : 0u;
+    }
+    __syncthreads();
+    if (bulk) mbar_wait(&bar, 0);
+    for (uint32_t base = 0; base < n; base += kLeafThreads * kLeafPer) {
+        uint32_t nx[kLeafPer];
+        uint32_t nbase = base + kLeafThreads * kLeafPer;
+#pragma unroll
+        for (int q = 0; q < kLeafPer; ++q) {                   // next batch in flight while this one is applied
+            uint32_t x = nbase + threadIdx.x + q * kLeafThreads;
+            nx[q] = x < n ? ld_stream(in + x) : 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < kLeafPer; ++q) {
+            uint32_t x = base + threadIdx.x + q * kLeafThreads;
+            if (x < n) {
+                uint32_t idx = tbl_idx(h[q], hp);
+                uint32_t* addr = slice + (idx >> 4);
+                int sh = (idx & 15u) * 2;
+                uint32_t seen = *addr;
+                while (((seen >> sh) & 3u) < 3u) {
+                    uint32_t old = atomicCAS(addr, seen, seen + (1u << sh));
+                    if (old == seen) break;
+                    seen = old;
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < kLeafPer; ++q) h[q] = nx[q];
+    }
+    __syncthreads();
+    if (bulk) {
+        if (threadIdx.x == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            for (uint32_t o = 0; o < words; o += 4096u) bulk_store(home + o, slice + o, min(4096u, words - o) * 4u);
+            bulk_store_commit_wait();
+        }
+    } else {
+        for (uint32_t x = threadIdx.x; x < words; x += kLeafThreads) home[x] = slice[x];
+    }
+}
+
+size_t s1_bin_smem_bytes(const BinP& bp) { return (size_t)2 * ((size_t)bp.bcap << bp.b1) * sizeof(uint32_t); }   // two bucket sets
+int s1_leaf_max_log2() { return kLeafMaxLog2; }
 
 template <int E>
 static cudaError_t s1_bin_launch(const uint8_t* fq, const uint64_t* rs, const uint64_t* re, uint64_t lo, uint64_t hi, uint64_t budget,
@@ -777,13 +885,16 @@ int launch_s1_binned(const uint8_t* fq, const uint64_t* rec_start, const uint64_
                      uint64_t budget, const uint32_t* sample_bits, uint64_t ordinal_base, const HashP& hp, const BinP& bp,
                      uint32_t* count, unsigned long long* n_sampled, int* err, int phase, cudaStream_t st) {
     if (rec_hi <= rec_lo) return 0;
-    int nbins = 1 << bp.log2;
     if (phase == 1) {
-        auto kern = s1_apply_kernel<kApplyPer, kApplyStages, kApplyMinCtas, 0>;
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kApplySmem) != cudaSuccess) return -1;
-        for (int b = 0; b < nbins; ++b)
-            kern<<<kSMs * kApplyMinCtas, kApplyThreads, kApplySmem, st>>>(bp.pool + bp.off[b], bp.cursor + b, bp.off[b + 1] - bp.off[b], count);
-        return nbins;
+        unsigned tiles = (bp.cap_a + kSplitTile - 1) / kSplitTile;
+        s1_split_kernel<<<dim3(tiles, 1u << bp.b1), kSplitThreads, 0, st>>>(bp, hp, count);
+        return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    }
+    if (phase == 2) {
+        size_t smem = (size_t)4 << (hp.idx_bits - 4);
+        if (cudaFuncSetAttribute(s1_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        s1_leaf_kernel<<<1u << hp.leaf_bits, kLeafThreads, smem, st>>>(bp, hp, count);
+        return cudaGetLastError() == cudaSuccess ? 1 : -1;
     }
     cudaError_t rc;
     switch (hp.e) {
@@ -826,13 +937,16 @@ __global__ void __launch_bounds__(256) s2_gather_kernel(const uint32_t* __restri
     for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int i = 0; i < (E ? E : kMaxE); ++i)
-            if (i < e) w[r][i] = h[r][i] ? ld_stream(count + (h[r][i] >> 4)) : 0u;   // stored 0 = no hit (Q4, E:936-941)
+            if (i < e) {                                           // stored 0 = no hit (Q4, E:936-941)
+                uint32_t g = tbl_index(h[r][i], hp);
+                w[r][i] = h[r][i] ? (ld_stream(count + (g >> 4)) >> ((g & 15u) * 2)) & 3u : 0u;
+            }
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         int full = 0;
 #pragma unroll
         for (int i = 0; i < (E ? E : kMaxE); ++i)
-            if (i < e) full += h[r][i] && ((w[r][i] >> ((h[r][i] & 15u) * 2)) & 3u) == 3u;
+            if (i < e) full += w[r][i] == 3u;
         uint32_t ws = __ballot_sync(kFull, full > 0);
         uint32_t wt = __ballot_sync(kFull, full == e);
         if (lane == 0) {
@@ -1048,7 +1162,8 @@ __global__ void __launch_bounds__(256) s2_register_kernel(const uint32_t* __rest
             for (int i = 0; i < e; ++i) {
                 uint32_t h = hashes[i];
                 if (!h) continue;
-                uint32_t cnt = (count[h >> 4] >> ((h & 15u) * 2)) & 3u;
+                uint32_t g = tbl_index(h, hp);
+                uint32_t cnt = (count[g >> 4] >> ((g & 15u) * 2)) & 3u;
                 if (!cnt) continue;                                        // E:250,265: hit > 0
                 uint32_t slot = prefilter_slot(h);
                 if (mode == 0) {
@@ -1117,37 +1232,39 @@ constexpr int kS3Warps = 8;
 int s3_warps_per_block() { return kS3Warps; }
 int s3_grid_blocks(int) { return kSMs * 4; }
 
+// src points into the warp's shared-memory stage (s3_pairs_kernel).
 template <int E>
-__device__ __forceinline__ int s3_scan_mate(const uint8_t* __restrict__ src, int len, const uint8_t* lut, const HashP& hp,
-                                            const uint32_t* __restrict__ prefilter, const uint32_t* __restrict__ peak_kmer,
-                                            uint32_t* __restrict__ cands, int n_listed, int lane) {
+__device__ __forceinline__ int s3_scan_mate(const uint8_t* src, int len, const uint8_t* lut, const HashP& hp,
+                                            const uint32_t* __restrict__ prefilter,
+                                            const uint32_t* __restrict__ peak_kmer, uint32_t* __restrict__ cands, int n_listed,
+                                            int lane) {
     const int e = E ? E : hp.e;
     int np = len - hp.k + 1;
     if (np <= 0) return n_listed;
     int nch = (np + 31) >> 5;
     Planes prev = pack_word(lane < len ? src[lane] : 0u, lut);
-    uint32_t c1 = 32 + lane < len ? src[32 + lane] : 0u;      // bytes run two words ahead of the hashing
-    uint32_t c2 = 64 + lane < len ? src[64 + lane] : 0u;
+    uint32_t c1 = 32 + lane < len ? src[32 + lane] : 0u;      // bytes run one word ahead of the hashing
     for (int w = 1; w <= nch; ++w) {                          // chunk w-1: positions 32(w-1) + lane, ascending
         Planes cur = pack_word(c1, lut);
-        c1 = c2;
-        int pn = (w + 2) * 32 + lane;
-        c2 = pn < len ? src[pn] : 0u;
+        int pn = (w + 1) * 32 + lane;
+        c1 = pn < len ? src[pn] : 0u;
         LeWin kw = le_window(prev, cur, lane, hp);
         prev = cur;
         uint32_t h[E ? E : kMaxE], pk[E ? E : kMaxE], fw[E ? E : kMaxE];
+        // all e filter words are requested back to back; .cg: a probe must not claim an L1 line (the lines in
+        // flight, not the warps, would bound the probes in flight)
 #pragma unroll
         for (int i = 0; i < (E ? E : kMaxE); ++i)
             if (i < e) {
                 h[i] = le_hash(kw, hp, i);
                 uint32_t slot = prefilter_slot(h[i]);
-                fw[i] = kw.valid ? __ldg(prefilter + (slot >> 5)) >> (slot & 31) : 0u;
+                fw[i] = kw.valid ? ld_table(prefilter + (slot >> 5)) >> (slot & 31) : 0u;
             }
         bool any = false;
 #pragma unroll
         for (int i = 0; i < (E ? E : kMaxE); ++i)
             if (i < e) {
-                pk[i] = (fw[i] & 1u) ? __ldg(peak_kmer + h[i]) : 0u;
+                pk[i] = (fw[i] & 1u) ? ld_table(peak_kmer + h[i]) : 0u;
                 any |= pk[i] != 0u;
             }
         uint32_t mask = __ballot_sync(kFull, any);
@@ -1199,6 +1316,10 @@ __device__ void s3_vote(const uint32_t* cands, int n_listed, int e, const int32_
     }
 }
 
+struct PairOff { uint64_t a0, b0; uint32_t l1, l2; bool ok; };
+
+// One warp per pair, two pairs ahead: while a pair is voted on, the TMA unit is staging the bytes of the next sampled
+// pair into the warp's other shared-memory slots and the offsets of the one after are in flight (see stage_read).
 template <int E>
 __global__ void __launch_bounds__(kS3Warps * 32, 4) s3_pairs_kernel(
     const uint8_t* __restrict__ fq1, const uint64_t* __restrict__ s1, const uint64_t* __restrict__ e1, uint64_t nrec1,
@@ -1208,25 +1329,69 @@ __global__ void __launch_bounds__(kS3Warps * 32, 4) s3_pairs_kernel(
     const int32_t* __restrict__ loci, uint8_t* __restrict__ peak_filter, S3Scratch scratch,
     unsigned long long* __restrict__ n_sampled, int* __restrict__ err) {
     __shared__ uint8_t lut[256];
+    __shared__ __align__(16) uint8_t stage[kS3Warps][4][kStageBytes];
+    __shared__ __align__(8) uint64_t sbar[kS3Warps][2];        // "pair staged", one per slot pair
     const int e = E ? E : hp.e;
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { mbar_init(&sbar[warp][0], 1); mbar_init(&sbar[warp][1], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     fill_base_lut(lut);
     __syncthreads();
     uint64_t gwarp = (uint64_t)blockIdx.x * kS3Warps + warp;
     uint32_t* cands = scratch.cands + gwarp * scratch.cands_stride;
     int32_t* tally = scratch.tally + gwarp * scratch.tally_stride;
     unsigned long long mine = 0;
-    uint64_t stride = (uint64_t)gridDim.x * kS3Warps;
-    uint64_t last = first + count < nrec1 ? first + count : nrec1;
-    for (uint64_t r = first + gwarp; r < last; r += stride) {
-        if (!is_sampled(sample_bits, r + ordinal_base)) continue;
-        uint64_t a0 = s1[r], l1 = e1[r] - a0, b0, l2;
-        if (r < nrec2) { b0 = s2[r]; l2 = e2[r] - b0; }
-        else { b0 = tail_start; l2 = tail_len; }            // fq2 exhausted: std::getline leaves its last string
-        if (l1 > (uint64_t)kMaxReadLen || l2 > (uint64_t)kMaxReadLen) { if (lane == 0) atomicExch(err, 1); continue; }
+    const uint64_t stride = (uint64_t)gridDim.x * kS3Warps;
+    const uint64_t last = first + count < nrec1 ? first + count : nrec1;
+    auto next_sampled = [&](uint64_t q) {
+        while (q < last && !is_sampled(sample_bits, q + ordinal_base)) q += stride;
+        return q;
+    };
+    auto load_off = [&](uint64_t r) {
+        PairOff o;
+        uint64_t l1, l2;
+        o.a0 = s1[r]; l1 = e1[r] - o.a0;
+        if (r < nrec2) { o.b0 = s2[r]; l2 = e2[r] - o.b0; }
+        else { o.b0 = tail_start; l2 = tail_len; }            // fq2 exhausted: std::getline leaves its last string
+        o.ok = l1 <= (uint64_t)kMaxReadLen && l2 <= (uint64_t)kMaxReadLen;
+        o.l1 = (uint32_t)l1; o.l2 = (uint32_t)l2;
+        return o;
+    };
+    auto stage_pair = [&](const PairOff& o, int sl) {
+        stage_pair_reads(stage[warp][2 * sl], stage[warp][2 * sl + 1], &sbar[warp][sl], fq1, o.a0, o.l1, fq2, o.b0, o.l2, lane);
+    };
+    uint64_t rn = next_sampled(first + gwarp);
+    PairOff on{0, 0, 0, 0, false}, onn{0, 0, 0, 0, false};
+    if (rn < last) on = load_off(rn);
+    uint64_t rnn = rn < last ? next_sampled(rn + stride) : rn;
+    if (rnn < last) onn = load_off(rnn);
+    int slot = 0;
+    bool nstaged = false;
+    uint32_t phase = 0;                                         // bit s: parity the next fill of slot pair s completes
+    if (rn < last && on.ok) { stage_pair(on, 1); nstaged = true; }
+    while (rn < last) {
+        PairOff cur = on;
+        bool staged = nstaged;
+        nstaged = false;
+        if (cur.ok) {
+            slot ^= 1;
+            if (!staged) stage_pair(cur, slot);                 // only after a refused pair
+            mbar_wait(&sbar[warp][slot], (phase >> slot) & 1u);
+            phase ^= 1u << slot;
+        }
+        rn = rnn; on = onn;
+        if (rnn < last) {
+            rnn = next_sampled(rnn + stride);
+            if (rnn < last) onn = load_off(rnn);
+        }
+        if (!cur.ok) { if (lane == 0) atomicExch(err, 1); continue; }
         ++mine;
-        int n_listed = s3_scan_mate<E>(fq1 + a0, (int)l1, lut, hp, prefilter, peak_kmer, cands, 0, lane);
-        n_listed = s3_scan_mate<E>(fq2 + b0, (int)l2, lut, hp, prefilter, peak_kmer, cands, n_listed, lane);
+        __syncwarp();                                           // every lane is done with the other slot pair
+        if (rn < last && on.ok) { stage_pair(on, slot ^ 1); nstaged = true; }
+        uint32_t m1 = (uint32_t)cur.a0 & 15u, m2 = (uint32_t)cur.b0 & 15u;
+        int n_listed = s3_scan_mate<E>(stage[warp][2 * slot] + m1, (int)cur.l1, lut, hp, prefilter, peak_kmer, cands, 0, lane);
+        n_listed = s3_scan_mate<E>(stage[warp][2 * slot + 1] + m2, (int)cur.l2, lut, hp, prefilter, peak_kmer, cands, n_listed, lane);
         if (n_listed >= 6) {                                 // base_hits >= MIN_BASE_NUM (E:496)
             __syncwarp();
             if (lane == 0) s3_vote(cands, n_listed, e, loci, tally, peak_filter);
@@ -1280,13 +1445,15 @@ int launch_sample_bits(const uint32_t* m, uint64_t n, uint32_t m_star, uint32_t*
 // ------------------------------------------------------------------------------------------------
 // table utilities
 // ------------------------------------------------------------------------------------------------
-__global__ void count_unpack_kernel(const uint32_t* __restrict__ count, uint64_t entries, uint8_t* __restrict__ out) {
-    for (uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h < entries; h += (uint64_t)gridDim.x * blockDim.x)
-        out[h] = (count[h >> 4] >> ((h & 15u) * 2)) & 3u;
+__global__ void count_unpack_kernel(const uint32_t* __restrict__ count, uint64_t entries, HashP hp, uint8_t* __restrict__ out) {
+    for (uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h < entries; h += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t g = tbl_index((uint32_t)h, hp);
+        out[h] = (count[g >> 4] >> ((g & 15u) * 2)) & 3u;
+    }
 }
 
-int launch_count_unpack(const uint32_t* count, uint64_t entries, uint8_t* out, cudaStream_t st) {
-    count_unpack_kernel<<<kSMs * 8, 256, 0, st>>>(count, entries, out);
+int launch_count_unpack(const uint32_t* count, uint64_t entries, const HashP& hp, uint8_t* out, cudaStream_t st) {
+    count_unpack_kernel<<<kSMs * 8, 256, 0, st>>>(count, entries, hp, out);
     return 1;
 }
 

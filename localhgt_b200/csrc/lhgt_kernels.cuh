@@ -12,6 +12,7 @@ constexpr int kTile = 1024;            // reference positions per S2 / IB tile
 constexpr int kTileWords = kTile / 32;
 constexpr int kRandomArray = 50000000; // E:40
 constexpr int kFilterLog2 = 28;        // S3 pre-filter: 2^28 bits = 32 MiB, L2-resident on B200
+constexpr int kFilterWords = 1 << (kFilterLog2 - 5);
 
 // Everything a kernel needs to hash: F_i = W2 ^ ((W0^W2)&m0[i]) ^ ((W1^W2)&m1[i]) and the mirrored
 // form for the reverse complement.  m2 is implied (the three masks partition kmask).
@@ -20,7 +21,23 @@ struct HashP {
     int shr;                           // 32 - k
     uint32_t kmask;
     uint32_t m0[kMaxE], m1[kMaxE];
+    // Count-table layout: the table is stored leaf-major.  The leaf of hash h is its bit field
+    // [leaf_lo, leaf_lo + leaf_bits); the remaining idx_bits = k - leaf_bits bits, closed up, index the counter inside
+    // the leaf's contiguous slice:  g(h) = leaf << idx_bits | idx.  The field sits in the MIDDLE of the hash: a canonical
+    // hash is min(forward, reverse-complement) and that choice is decided by the leading bases (top bits of the forward
+    // code) and the trailing bases (top bits of the other, which are also the LOW bits of the forward code), so only
+    // middle bits are uniform.  leaf_bits = 0 (all fields 0) is the identity.
+    int leaf_bits, idx_bits, leaf_lo;
+    uint32_t leaf_mask, lo_mask;
 };
+
+__host__ __device__ inline uint32_t tbl_leaf(uint32_t h, const HashP& hp) { return (h >> hp.leaf_lo) & hp.leaf_mask; }
+__host__ __device__ inline uint32_t tbl_idx(uint32_t h, const HashP& hp) {
+    return ((h >> (hp.leaf_lo + hp.leaf_bits)) << hp.leaf_lo) | (h & hp.lo_mask);
+}
+__host__ __device__ inline uint32_t tbl_index(uint32_t h, const HashP& hp) {
+    return (tbl_leaf(h, hp) << hp.idx_bits) | tbl_idx(h, hp);
+}
 
 struct Tile { uint32_t contig; uint32_t j0; };
 
@@ -32,15 +49,22 @@ struct Contig {
     uint32_t tile0;                    // first tile
 };
 
-constexpr int kMaxBins = 16;           // S1 hash streams (table slices of 2^k / 4 / nbins bytes)
+// S1, streamed form: hashes are partitioned by their leaf field in two steps -- 2^b1 streams written
+// by the hashing kernel (low b1 bits of the leaf), each split into 2^b2 leaf streams (the other b2 bits) -- and every
+// leaf stream is applied to its table slice in shared memory.  leaf_bits = b1 + b2.
+constexpr int kMaxB1 = 6, kMaxB2 = 8;
+constexpr int kBinWarps = 8;           // warps per CTA of s1_bin_kernel
+constexpr int kBinRoundChunks = 4;     // 32-position chunks a warp hashes per round
 
-struct BinP {                          // S1, binned form
-    uint32_t* pool;                    // stream b occupies pool[off[b] .. off[b+1])
-    uint32_t* cursor;                  // [1 << log2] entries appended so far (may run past the region: surplus was applied directly)
-    uint32_t off[kMaxBins + 1];        // multiples of 8 entries
-    uint32_t boff[kMaxBins + 1];       // shared-memory bucket b of a CTA occupies dyn[boff[b] .. boff[b+1])
-    int log2;                          // streams = 1 << log2 <= kMaxBins
-    int shift;                         // stream of hash h = h >> shift  (k - log2)
+struct BinP {
+    uint32_t* pool_a;                  // stream b (b < 2^b1) occupies pool_a[b * cap_a .. +cap_a)
+    uint32_t* cursor_a;                // [2^b1] entries appended so far (may run past cap_a: the surplus was applied directly)
+    uint32_t* pool_b;                  // leaf stream l (l < 2^(b1+b2)) occupies pool_b[l * cap_b .. +cap_b)
+    uint32_t* cursor_b;                // [2^(b1+b2)]
+    uint32_t cap_a, cap_b;             // entries; cap_a is a multiple of 8
+    uint32_t bcap;                     // shared-memory bucket entries per stream in s1_bin_kernel
+    int round_chunks;                  // 32-position chunks a warp hashes per round (<= kBinRoundChunks)
+    int b1, b2;
 };
 
 struct S3Scratch {                     // per resident warp
@@ -67,12 +91,13 @@ int launch_s1(const uint8_t* fq, const uint64_t* rec_start, const uint64_t* rec_
               unsigned long long* n_sampled, int* err, cudaStream_t st);
 
 // phase 0: stream the hashes of records [rec_lo, rec_hi) (cursors must be zero on entry);
-// phase 1: one apply launch per stream
+// phase 1: split the streams into leaf streams; phase 2: apply the leaf streams
 int launch_s1_binned(const uint8_t* fq, const uint64_t* rec_start, const uint64_t* rec_end, uint64_t rec_lo,
                      uint64_t rec_hi, uint64_t budget, const uint32_t* sample_bits, uint64_t ordinal_base,
                      const HashP& hp, const BinP& bp, uint32_t* count, unsigned long long* n_sampled, int* err,
                      int phase, cudaStream_t st);
 size_t s1_bin_smem_bytes(const BinP& bp);
+int s1_leaf_max_log2();              // largest table slice (log2 counters) s1_leaf_kernel holds in shared memory
 
 int launch_s2_gather(const uint32_t* image, const Contig* contigs, const Tile* tiles, uint64_t tile_begin,
                      uint64_t tile_end, const HashP& hp, const uint32_t* count, uint32_t* single,
@@ -101,7 +126,7 @@ int s3_warps_per_block();
 
 // bit o of `bits` := o < n && m[o] < m_star (the sampling decision of ordinal o); the other bits of the 50 M-bit array := 0
 int launch_sample_bits(const uint32_t* m, uint64_t n, uint32_t m_star, uint32_t* bits, uint64_t words, cudaStream_t st);
-int launch_count_unpack(const uint32_t* count, uint64_t entries, uint8_t* out, cudaStream_t st);
+int launch_count_unpack(const uint32_t* count, uint64_t entries, const HashP& hp, uint8_t* out, cudaStream_t st);
 int launch_count_merge(uint32_t* count, const uint32_t* other, uint64_t words, cudaStream_t st);
 
 __host__ __device__ inline uint32_t prefilter_slot(uint32_t h) {

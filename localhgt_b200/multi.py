@@ -81,7 +81,7 @@ class Shard:
     def __init__(self, scr, rank: int = 0, world: int = 1, dist=None, torch=None, engine=None):
         self.rank, self.world, self.dist, self.torch = rank, world, dist, torch
         self.eng = engine if engine is not None else GpuEngine(scr, torch)
-        self.last_stage_ms = np.zeros(10)
+        self.last_stage_ms = np.zeros(11)
         self.last_peaks = 0
         self.last_counts = {}
         self.last_wall_ms = {}
@@ -144,7 +144,7 @@ class Shard:
         needed up front for the Q15 budget), before_s2() must make the index resident.  That is the stage order of the
         reference's main() (E:1426-1507), which lets host->device copies hide behind S1."""
         eng, w = self.eng, self.world
-        ms = np.zeros(10)
+        ms = np.zeros(11)
         wall = {}
         t0 = time.perf_counter()
 
@@ -210,8 +210,8 @@ class Shard:
         self.last_wall_ms = wall
         st = eng.stage_ms()
         ms[:6] = st[:6]
-        if len(st) >= 8:
-            ms[8:10] = st[6:8]                                          # S1 split: hash-stream kernel, stream-apply kernels
+        if len(st) >= 9:
+            ms[8:11] = st[6:9]                                          # S1 in streams: hash, split, leaf-apply kernels
         ms[6] = 1000 * (t2 - t1) - st[2] - st[3] if w > 1 else 0.0
         self.last_stage_ms = ms
         self.last_peaks = int(n_peaks)

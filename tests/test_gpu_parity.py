@@ -153,11 +153,16 @@ def test_s1_streams_equal_direct_and_oracle(k, e, workdir, monkeypatch):
     want_n = o.s1_count(fq, len(raw), ratio)
     want = o.count_table().copy()
     o.close()
-    for mode, pool_mb in ((1, None), (2, None), (2, "1")):
-        if pool_mb:
-            monkeypatch.setenv("LHGT_BIN_POOL_MB", pool_mb)      # 16 K entries per stream: many chunks + full regions
-        else:
-            monkeypatch.delenv("LHGT_BIN_POOL_MB", raising=False)
+    # modes: direct probes; hash streams with the default leaves (2^18 counters: few leaves at these k); streams with
+    # small leaves (the k=32 shape: 2^6 streams x 2^8 leaves each); the same with tiny pools (many chunks, full regions)
+    for mode, pool_mb, leaf_log2 in ((1, None, None), (1, None, "10"), (2, None, None), (2, None, "10"), (2, "1", "10")):
+        for name, val in (("LHGT_BIN_POOL_MB", pool_mb), ("LHGT_LEAF_LOG2", leaf_log2)):
+            if val:
+                monkeypatch.setenv(name, val)
+            else:
+                monkeypatch.delenv(name, raising=False)
+        if mode == 2 and leaf_log2 is None and k <= 18:
+            continue                                               # a single leaf: nothing to stream
         with api.Screen(k, e) as s:
             s.set_coder(cc)
             s.set_s1_mode(mode)
@@ -165,7 +170,7 @@ def test_s1_streams_equal_direct_and_oracle(k, e, workdir, monkeypatch):
             s.set_sampling(ratio, 3, k * (e // 3 + 1))
             assert s.s1_count(0, len(raw)) == want_n
             got = s.count_table()
-            assert np.array_equal(got, want), (mode, pool_mb, int((got != want).sum()))
+            assert np.array_equal(got, want), (mode, pool_mb, leaf_log2, int((got != want).sum()))
             s.s1_count(0, len(raw))                               # counting again only saturates further
             assert np.array_equal(s.count_table(), np.minimum(3, 2 * want.astype(np.int32)))
 

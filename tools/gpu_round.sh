@@ -9,12 +9,12 @@ nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > $O/gpu.txt
 nproc >> $O/gpu.txt; free -g >> $O/gpu.txt
 for w in $what; do case $w in
 tests)
-  timeout 1500 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu.log; tail -5 $O/pytest_gpu.log;;
+  timeout 900 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu.log; tail -5 $O/pytest_gpu.log;;
 quick)
   timeout 900 python -m pytest tests -m gpu -x -q -k "${TESTK:-s1 or streamed or k32 or large_run_properties}" > $O/pytest_quick.log 2>&1; echo "pytest rc=$?" >> $O/pytest_quick.log; tail -5 $O/pytest_quick.log;;
 benchq)
-  timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu ${BENCHARGS:-} > $O/bench_quick.json 2> $O/bench_quick.err; echo "bench rc=$?"; python -c "
-import json;d=json.load(open('$O/bench_quick.json'));print(d['value'],d['ms_per_step'],d['e2e']['value'],d['roofline']['stage_ms_per_step'])"; tail -5 $O/bench_quick.err;;
+  timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu ${BENCHARGS:-} > $O/bench_quick${TAG:-}.json 2> $O/bench_quick${TAG:-}.err; echo "bench rc=$?"; python -c "
+import json;d=json.load(open('$O/bench_quick${TAG:-}.json'));print(d['value'],d['ms_per_step'],d['e2e']['value'],d['roofline']['stage_ms_per_step'])"; tail -5 $O/bench_quick${TAG:-}.err;;
 smoke)
   timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke rc=$?" >> $O/smoke.log; tail -3 $O/smoke.log;;
 bench)
@@ -25,7 +25,7 @@ ncu)
   timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv \
      python bench.py --steps 2 --warmup 1 --no-cpu > $O/ncu_bench.log 2>&1; echo "ncu list rc=$?";;
 full)
-  for kn in ${KERNELS:-s1_count_kernel s3_pairs_kernel s2_gather_kernel index_build_kernel}; do
+  for kn in ${KERNELS:-s1_bin_kernel s1_split_kernel s1_leaf_kernel s3_pairs_kernel}; do
     timeout 900 ncu --set full --clock-control none --import-source on -k regex:$kn -s 1 -c 1 -f -o $O/$kn \
        python bench.py --steps 1 --warmup 1 --no-cpu > $O/ncu_$kn.log 2>&1; echo "ncu $kn rc=$?"
   done;;
