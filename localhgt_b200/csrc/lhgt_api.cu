@@ -931,7 +931,7 @@ static int s1_binned(lhgt_ctx* c, Reads& r, uint64_t byte_budget) {
     const uint64_t n_a = 1ull << bp.b1, n_l = 1ull << L;
     bp.round_chunks = std::max(1, std::min(kBinRoundChunks, 12 / c->e));
     double round_hashes = (double)kBinWarps * bp.round_chunks * 32 * c->e;
-    bp.bcap = (uint32_t)(1.25 * round_hashes / (double)n_a) + 16;
+    bp.bcap = ((uint32_t)(1.25 * round_hashes / (double)n_a) + 16 + 7 + 7) & ~7u;   // a round's share, slack, the carry; whole sectors
     // hashes one record contributes on average (sampled fraction included)
     double avg_len = r.nrec ? (double)r.seq_bases / (double)r.nrec : 0.0;
     double per_rec = std::max(1.0, avg_len - c->k + 1) * c->e * std::min(1.0, c->sample_bits_on ? c->ratio / 100.0 : 1.0);
@@ -961,18 +961,19 @@ static int s1_binned(lhgt_ctx* c, Reads& r, uint64_t byte_budget) {
         if (rc) return rc;
         c->bin_pool_b_entries = need_b;
     }
-    if (c->bin_cursor_entries < n_a + n_l) {
+    const uint64_t cursor_words = n_a * kCursorStride + n_l;
+    if (c->bin_cursor_entries < cursor_words) {
         dev_free(c->d_bin_cursor);
-        int rc = dev_alloc(&c->d_bin_cursor, n_a + n_l);
+        int rc = dev_alloc(&c->d_bin_cursor, cursor_words);
         if (rc) return rc;
-        c->bin_cursor_entries = n_a + n_l;
+        c->bin_cursor_entries = cursor_words;
     }
     bp.pool_a = c->d_bin_pool_a; bp.pool_b = c->d_bin_pool_b;
-    bp.cursor_a = c->d_bin_cursor; bp.cursor_b = c->d_bin_cursor + n_a;
+    bp.cursor_a = c->d_bin_cursor; bp.cursor_b = c->d_bin_cursor + n_a * kCursorStride;
     const uint32_t* sb = c->sample_bits_on ? c->d_sample_bits : nullptr;
     for (uint64_t lo = 0; lo < r.nrec; lo += per_chunk) {
         uint64_t hi = std::min(r.nrec, lo + per_chunk);
-        CU(cudaMemsetAsync(c->d_bin_cursor, 0, (n_a + n_l) * sizeof(uint32_t), c->st));
+        CU(cudaMemsetAsync(c->d_bin_cursor, 0, cursor_words * sizeof(uint32_t), c->st));
         for (int phase = 0; phase < 3; ++phase) {
             Span sp(c, 6 + phase);
             int n = launch_s1_binned(r.d_fq, r.d_start, r.d_end, lo, hi, byte_budget, sb, c->ordinal_base, c->hp, bp,

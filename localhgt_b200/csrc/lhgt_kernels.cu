@@ -579,7 +579,7 @@ __global__ void __launch_bounds__(kBinWarps * 32, 4) s1_bin_kernel(
     const uint8_t* __restrict__ fq, const uint64_t* __restrict__ rec_start, const uint64_t* __restrict__ rec_end,
     uint64_t rec_lo, uint64_t rec_hi, uint64_t budget, const uint32_t* __restrict__ sample_bits, uint64_t ordinal_base,
     HashP hp, BinP bp, uint32_t* __restrict__ count, unsigned long long* __restrict__ n_sampled, int* __restrict__ err) {
-    extern __shared__ uint32_t dyn[];                         // two bucket sets: one fills while the other drains
+    extern __shared__ __align__(16) uint32_t dyn[];           // two bucket sets: one fills while the other drains
     __shared__ uint32_t cnt[2][1 << kMaxB1];
     __shared__ uint8_t lut[256];
     __shared__ __align__(16) uint8_t stage[kBinWarps][2][kStageBytes];
@@ -668,10 +668,13 @@ __global__ void __launch_bounds__(kBinWarps * 32, 4) s1_bin_kernel(
         bool any = __syncthreads_or(have);
         // reserve room in the global streams for what last round produced; the answers are picked up after this
         // round's hashing, so the atomics' round trip costs nothing
-        uint32_t dn = 0, dg = 0;
+        // Streams only ever grow by whole 32-byte sectors (8 hashes): a bucket hands over the multiple of 8 it holds and
+        // carries the rest into its next fill, so every store below is a full, aligned sector.
+        uint32_t dn = 0, n8 = 0, dg = 0;
         if (!first_round && owner) {
             dn = min(cnt[set ^ 1][my_bin], bcap);
-            if (dn && sub == 0) dg = atomicAdd(bp.cursor_a + my_bin, dn);
+            n8 = dn & ~7u;
+            if (n8 && sub == 0) dg = atomicAdd(bp.cursor_a + my_bin * kCursorStride, n8);
         }
         if (any) {
             uint32_t* buckets = dyn + set * set_entries;
@@ -698,23 +701,33 @@ __global__ void __launch_bounds__(kBinWarps * 32, 4) s1_bin_kernel(
                 if (++w > nch) { have = false; }
             }
         }
-        if (!first_round) {                                   // drain last round's set: coalesced runs, all streams of this warp at once
+        if (!first_round) {                                   // drain last round's set: all streams of this warp side by side
             dg = __shfl_sync(kFull, dg, grp * lpb);
-            if (owner && dn) {
-                const uint32_t* from = dyn + (set ^ 1) * set_entries + (uint32_t)my_bin * bcap;
-                uint32_t* dst = bp.pool_a + (size_t)my_bin * bp.cap_a;
-                for (uint32_t x = sub; x < dn; x += lpb) {
-                    uint32_t h = from[x];
-                    if (dg + x < bp.cap_a) dst[dg + x] = h;
-                    else bump_direct(count, h, hp);           // stream region full
-                }
+            uint32_t* from = dyn + (set ^ 1) * set_entries + (uint32_t)(owner ? my_bin : 0) * bcap;
+            if (owner && n8) {
+                uint32_t fit = dg < bp.cap_a ? min(n8, bp.cap_a - dg) : 0u;            // a multiple of 8, like dg and cap_a
+                const uint2* from2 = reinterpret_cast<const uint2*>(from);
+                uint2* dst2 = reinterpret_cast<uint2*>(bp.pool_a + (size_t)my_bin * bp.cap_a + dg);
+                for (uint32_t x = sub; x < fit / 2; x += lpb) dst2[x] = from2[x];
+                for (uint32_t x = fit + sub; x < n8; x += lpb) bump_direct(count, from[x], hp);   // stream region full
             }
             __syncwarp();
-            if (owner && sub == 0) cnt[set ^ 1][my_bin] = 0;
+            if (owner && n8)
+                for (uint32_t j = sub; j < dn - n8; j += lpb) from[j] = from[n8 + j];  // carry (disjoint: n8 >= 8 > dn - n8)
+            __syncwarp();
+            if (owner && sub == 0) cnt[set ^ 1][my_bin] = dn - n8;
         }
         if (!any) break;
         set ^= 1;
     }
+    // what the buckets still carry (< 8 hashes each) goes to the table directly
+    __syncthreads();
+    if (owner)
+        for (int s2 = 0; s2 < 2; ++s2) {
+            const uint32_t* from = dyn + s2 * set_entries + (uint32_t)my_bin * bcap;
+            uint32_t left = min(cnt[s2][my_bin], bcap);
+            for (uint32_t j = sub; j < left; j += lpb) bump_direct(count, from[j], hp);
+        }
     if (lane == 0 && mine) atomicAdd(n_sampled, mine);
 }
 
@@ -730,7 +743,7 @@ __global__ void __launch_bounds__(kSplitThreads, 3) s1_split_kernel(BinP bp, Has
     const uint32_t sub_mask = (uint32_t)nsub - 1u;
     const int sub_lo = hp.leaf_lo + bp.b1;
     const uint32_t y = blockIdx.y;
-    const uint32_t n = min(bp.cursor_a[y], bp.cap_a);
+    const uint32_t n = min(bp.cursor_a[y * kCursorStride], bp.cap_a);
     const uint32_t first = blockIdx.x * kSplitTile;
     if (first >= n) return;
     const uint32_t valid = min((uint32_t)kSplitTile, n - first);

@@ -54,11 +54,14 @@ struct Contig {
 // leaf stream is applied to its table slice in shared memory.  leaf_bits = b1 + b2.
 constexpr int kMaxB1 = 6, kMaxB2 = 8;
 constexpr int kBinWarps = 8;           // warps per CTA of s1_bin_kernel
+constexpr int kCursorStride = 64;      // words between stream cursors: every CTA bumps every cursor every round, and atomics on one
+                                       // cache line are served one per clock by one L2 slice (profiles/r01g) -- give each its own lines
 constexpr int kBinRoundChunks = 4;     // 32-position chunks a warp hashes per round
 
 struct BinP {
     uint32_t* pool_a;                  // stream b (b < 2^b1) occupies pool_a[b * cap_a .. +cap_a)
-    uint32_t* cursor_a;                // [2^b1] entries appended so far (may run past cap_a: the surplus was applied directly)
+    uint32_t* cursor_a;                // cursor_a[b * kCursorStride]: entries appended to stream b so far (may run past cap_a: the
+                                       // surplus was applied directly)
     uint32_t* pool_b;                  // leaf stream l (l < 2^(b1+b2)) occupies pool_b[l * cap_b .. +cap_b)
     uint32_t* cursor_b;                // [2^(b1+b2)]
     uint32_t cap_a, cap_b;             // entries; cap_a is a multiple of 8
