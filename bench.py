@@ -403,8 +403,11 @@ def ours(args) -> None:
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "pairs/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(h1.numel() + h2.numel() + himg.numel()), "d2h_bytes_per_step": len(text_resident) + 64,
+                "pcie_gbs": (h1.numel() + h2.numel() + himg.numel()) / 1e6 / (ms_e2e / args.steps),
                 "what": "pinned host FASTQ x2 + index image -> HBM (copy stream, overlapping S1) -> S1,S2,S3 -> interval text on host, "
-                        "through the C ABI; every byte crosses PCIe inside the timed region"},
+                        "through the C ABI; every byte crosses PCIe inside the timed region.  The step is bound by that copy "
+                        "(`pcie_gbs` = h2d bytes / step time; running two samples back to back on two contexts was measured "
+                        "and is no faster, profiles/README.md r01j)"},
         "gpu_launches": int(launches), "roofline": roofline, "index_build": index_build,
         "result": {"interval_lines": len(text_resident.splitlines()), "interval_sha256": hashlib.sha256(text_resident).hexdigest()[:16],
                    "planted_recovered": recovered(text_resident, meta), "peaks": shard.last_peaks,

@@ -800,7 +800,7 @@ __global__ void __launch_bounds__(kSplitThreads, 3) s1_split_kernel(BinP bp, Has
     for (uint32_t p = threadIdx.x; p < valid; p += kSplitThreads) {
         uint32_t hh = tile[p];
         uint2 rt = route[(hh >> sub_lo) & sub_mask];
-        if (p < rt.y) bp.pool_b[rt.x + p] = hh;
+        if (p < rt.y) bp.pool_b[rt.x + p] = tbl_idx(hh, hp);      // the leaf is implied by the stream: keep the counter index only
         else bump_direct(count, hh, hp);                       // leaf region full
     }
 }
@@ -852,7 +852,7 @@ __global__ void __launch_bounds__(kLeafThreads, 3) s1_leaf_kernel(BinP bp, HashP
         for (int q = 0; q < kLeafPer; ++q) {
             uint32_t x = base + threadIdx.x + q * kLeafThreads;
             if (x < n) {
-                uint32_t idx = tbl_idx(h[q], hp);
+                uint32_t idx = h[q];                           // s1_split_kernel stored tbl_idx(hash)
                 uint32_t* addr = slice + (idx >> 4);
                 int sh = (idx & 15u) * 2;
                 uint32_t seen = *addr;
