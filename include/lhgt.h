@@ -218,6 +218,27 @@ int lhgt_extract_ref(const lhgt_args* a, lhgt_stats* stats /* nullable */);
  * Returns the process exit status. */
 int lhgt_main(int argc, char** argv);
 
+/* ------------------------------------------------------------------ post-screen glue (host-side text; no GPU work)
+ *
+ * What scripts/pipeline.sh:36-37 runs right after extract_ref.  Buffers are caller-owned; pass dst = NULL to size. */
+
+/* scripts/get_bed_file.py:8-23,46-53: every interval line `ref_index start end` becomes `name:start-end`, the name looked
+ * up through <ref>.genome.len.txt (column 2 -> column 1; later lines win); start < 1 becomes 1; |end - start| < 50 is
+ * dropped.  *extract_len (nullable) = the script's "extracted ref length".  A ref_index the table does not list is
+ * LHGT_E_FORMAT (the script dies with KeyError there). */
+int lhgt_bed_text(const char* interval_text, size_t n_interval, const char* len_text, size_t n_len,
+                  char* dst, size_t cap, size_t* n, long* extract_len);
+/* `samtools faidx -r <bed> <ref.fa>` (pipeline.sh:37): per region `>name:start-end` and the bases start..end (1-based,
+ * inclusive, clipped at the end of the sequence), 60 per line.  Sequence names are the header text up to the first
+ * white space.  PARITY UNPINNED: samtools is not available where this was written; the format follows its
+ * documentation, not a run. */
+int lhgt_regions_fasta(const uint8_t* fasta, size_t n_fasta, const char* bed_text, size_t n_bed,
+                       char* dst, size_t cap, size_t* n);
+/* Both on files: reads <fasta>.genome.len.txt and <interval>, writes <interval>.bed and, if out_fasta is not NULL, the
+ * extracted reference. */
+int lhgt_extract_regions_files(const char* fasta_path, const char* interval_path, const char* out_fasta,
+                               long* extract_len);
+
 #ifdef __cplusplus
 }
 #endif

@@ -96,6 +96,9 @@ SYMBOLS = {
     "lhgt_launch_count": (_l, [_vp]),
     "lhgt_extract_ref": (_i, [C.POINTER(Args), C.POINTER(Stats)]),
     "lhgt_main": (_i, [_i, C.POINTER(_s)]),
+    "lhgt_bed_text": (_i, [_s, _sz, _s, _sz, _vp, _sz, C.POINTER(_sz), C.POINTER(_l)]),
+    "lhgt_regions_fasta": (_i, [_vp, _sz, _s, _sz, _vp, _sz, C.POINTER(_sz)]),
+    "lhgt_extract_regions_files": (_i, [_s, _s, _s, C.POINTER(_l)]),
 }
 
 _lib: Optional[C.CDLL] = None
@@ -370,3 +373,32 @@ def extract_ref(fq1: str, fq2: str, fasta: str, interval: str, *, hit_ratio: flo
     st = Stats()
     _check(load().lhgt_extract_ref(C.byref(a), C.byref(st)))
     return st
+
+
+# ---------------------------------------------------------------------------------------------- post-screen glue
+def bed_text(interval_text: bytes, len_text: bytes):
+    """scripts/get_bed_file.py on buffers: returns (bed text, extracted length)."""
+    L = load()
+    n, total = _sz(0), _l(0)
+    _check(L.lhgt_bed_text(interval_text, len(interval_text), len_text, len(len_text), None, 0, C.byref(n), C.byref(total)))
+    buf = C.create_string_buffer(max(1, n.value))
+    _check(L.lhgt_bed_text(interval_text, len(interval_text), len_text, len(len_text), buf, n.value, C.byref(n), C.byref(total)))
+    return buf.raw[:n.value], int(total.value)
+
+
+def regions_fasta(fasta: bytes, bed: bytes) -> bytes:
+    """`samtools faidx -r` on buffers (format per its documentation; see include/lhgt.h)."""
+    L = load()
+    n = _sz(0)
+    src = (C.c_ubyte * max(1, len(fasta))).from_buffer_copy(fasta or b"\0")
+    _check(L.lhgt_regions_fasta(src, len(fasta), bed, len(bed), None, 0, C.byref(n)))
+    buf = C.create_string_buffer(max(1, n.value))
+    _check(L.lhgt_regions_fasta(src, len(fasta), bed, len(bed), buf, n.value, C.byref(n)))
+    return buf.raw[:n.value]
+
+
+def extract_regions_files(fasta: str, interval: str, out_fasta: Optional[str] = None) -> int:
+    total = _l(0)
+    _check(load().lhgt_extract_regions_files(fasta.encode(), interval.encode(), out_fasta.encode() if out_fasta else None,
+                                             C.byref(total)))
+    return int(total.value)

@@ -15,6 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "liblhgt.so")
 EXE = os.path.join(OUT, "extract_ref")
+EXE_REGIONS = os.path.join(OUT, "extract_regions")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -44,6 +45,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     main_src = os.path.join(CSRC, "extract_ref_main.cpp")
     if force or _stale(EXE, [main_src, LIB]):
         subprocess.check_call(["g++", "-O2", "-o", EXE, main_src, "-L" + OUT, "-llhgt", "-Wl,-rpath,$ORIGIN"])
+    regions_src = os.path.join(CSRC, "extract_regions_main.cpp")
+    if force or _stale(EXE_REGIONS, [regions_src, LIB]):
+        subprocess.check_call(["g++", "-O2", "-o", EXE_REGIONS, regions_src, "-L" + OUT, "-llhgt", "-Wl,-rpath,$ORIGIN"])
     return LIB
 
 

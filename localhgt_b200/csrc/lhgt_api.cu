@@ -4,12 +4,14 @@
 #include "lhgt_kernels.cuh"
 
 #include <algorithm>
+#include <cerrno>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -1391,6 +1393,162 @@ extern "C" int lhgt_extract_ref(const lhgt_args* a, lhgt_stats* stats) {
     if (say) printf("Finish with time:\t%.3f\n", st.seconds[0]);
     if (stats) *stats = st;
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ post-screen glue
+// what pipeline.sh:36-37 runs right after extract_ref -- scripts/get_bed_file.py and
+// `samtools faidx -r` -- as host-side text functions over the files this library already produces.
+
+static void split_ws(const char* b, const char* e, std::vector<std::string>& out) {     // str.split() of Python
+    out.clear();
+    while (b < e) {
+        while (b < e && (*b == ' ' || (*b >= '\t' && *b <= '\r'))) ++b;
+        const char* t = b;
+        while (b < e && !(*b == ' ' || (*b >= '\t' && *b <= '\r'))) ++b;
+        if (b > t) out.emplace_back(t, b);
+    }
+}
+
+static bool py_int(const std::string& s, long* v) {            // int() on the tokens these files hold: [+-]digits
+    if (s.empty()) return false;
+    char* end = nullptr;
+    errno = 0;
+    long x = strtol(s.c_str(), &end, 10);
+    if (errno || end == s.c_str() || *end) return false;
+    *v = x;
+    return true;
+}
+
+extern "C" int lhgt_bed_text(const char* interval_text, size_t n_interval, const char* len_text, size_t n_len, char* dst,
+                             size_t cap, size_t* n, long* extract_len) {
+    if ((!interval_text && n_interval) || (!len_text && n_len) || !n) return fail(LHGT_E_ARG, "lhgt_bed_text: null pointer");
+    std::vector<std::string> tok;
+    std::map<long, std::string> name_of;                        // index2name (get_bed_file.py:46-53): later lines win
+    for (const char *p = len_text, *end = len_text + n_len; p < end;) {
+        const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+        const char* le = nl ? nl : end;
+        split_ws(p, le, tok);
+        long idx;
+        if (tok.size() < 2 || !py_int(tok[1], &idx)) return fail(LHGT_E_FORMAT, "genome.len.txt: line without a numeric second column");
+        name_of[idx] = tok[0];
+        p = nl ? nl + 1 : end;
+    }
+    std::string out;
+    long total = 0;
+    for (const char *p = interval_text, *end = interval_text + n_interval; p < end;) {      // find_chr_name (get_bed_file.py:8-23)
+        const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+        const char* le = nl ? nl : end;
+        split_ws(p, le, tok);
+        p = nl ? nl + 1 : end;
+        long chr, a, b;
+        if (tok.size() < 3 || !py_int(tok[0], &chr) || !py_int(tok[1], &a) || !py_int(tok[2], &b))
+            return fail(LHGT_E_FORMAT, "interval file: line without three integers");
+        std::string start = tok[1];
+        if (a < 1) { a = 1; start = "1"; }
+        if (labs(b - a) < 50) continue;                         // minimum fragment length
+        auto it = name_of.find(chr);
+        if (it == name_of.end()) return fail(LHGT_E_FORMAT, "interval file names reference %ld, which genome.len.txt does not list", chr);
+        out += it->second; out += ':'; out += start; out += '-'; out += tok[2]; out += '\n';
+        total += b - a;
+    }
+    *n = out.size();
+    if (extract_len) *extract_len = total;
+    if (dst) {
+        if (cap < out.size()) return fail(LHGT_E_ARG, "bed buffer too small (%zu needed)", out.size());
+        memcpy(dst, out.data(), out.size());
+    }
+    return 0;
+}
+
+extern "C" int lhgt_regions_fasta(const uint8_t* fasta, size_t n_fasta, const char* bed_text, size_t n_bed, char* dst, size_t cap,
+                                  size_t* n) {
+    if ((!fasta && n_fasta) || (!bed_text && n_bed) || !n) return fail(LHGT_E_ARG, "lhgt_regions_fasta: null pointer");
+    // one pass over the FASTA: name (up to the first white space, as faidx keys it) -> the line structure of its sequence
+    struct Seq { size_t first = 0, end = 0; size_t len = 0; std::vector<std::pair<size_t, size_t>> lines; };   // (offset in file, bases before it)
+    std::map<std::string, Seq> seqs;
+    Seq* cur = nullptr;
+    for (size_t p = 0; p < n_fasta;) {
+        const uint8_t* nl = (const uint8_t*)memchr(fasta + p, '\n', n_fasta - p);
+        size_t le = nl ? (size_t)(nl - fasta) : n_fasta;
+        size_t l = le - p;
+        if (l && fasta[le - 1] == '\r') --l;
+        if (l && fasta[p] == '>') {
+            size_t q = p + 1;
+            while (q < p + l && !(fasta[q] == ' ' || (fasta[q] >= '\t' && fasta[q] <= '\r'))) ++q;
+            cur = &seqs[std::string((const char*)fasta + p + 1, q - p - 1)];
+            *cur = Seq();
+        } else if (l && cur) {
+            cur->lines.emplace_back(p, cur->len);
+            cur->len += l;
+        }
+        p = nl ? le + 1 : n_fasta;
+    }
+    std::string out;
+    for (const char *p = bed_text, *end = bed_text + n_bed; p < end;) {
+        const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+        const char* le = nl ? nl : end;
+        std::string region(p, le);
+        p = nl ? nl + 1 : end;
+        while (!region.empty() && (region.back() == '\r' || region.back() == ' ')) region.pop_back();
+        if (region.empty()) continue;
+        size_t colon = region.rfind(':');
+        size_t dash = colon == std::string::npos ? std::string::npos : region.find('-', colon + 1);
+        long a, b;
+        if (colon == std::string::npos || dash == std::string::npos || !py_int(region.substr(colon + 1, dash - colon - 1), &a) ||
+            !py_int(region.substr(dash + 1), &b))
+            return fail(LHGT_E_FORMAT, "region \"%s\" is not name:start-end", region.c_str());
+        auto it = seqs.find(region.substr(0, colon));
+        if (it == seqs.end()) return fail(LHGT_E_FORMAT, "region \"%s\": no such sequence in the FASTA", region.c_str());
+        const Seq& sq = it->second;
+        out += '>'; out += region; out += '\n';
+        long lo = std::max(a, 1L) - 1, hi = std::min<long>(b, (long)sq.len);    // 0-based [lo, hi)
+        size_t col = 0;
+        if (hi > lo) {
+            // first line that holds base lo
+            size_t li = (size_t)(std::upper_bound(sq.lines.begin(), sq.lines.end(), (size_t)lo,
+                                                  [](size_t v, const std::pair<size_t, size_t>& x) { return v < x.second; }) - sq.lines.begin()) - 1;
+            long at = lo;
+            while (at < hi) {
+                size_t line_bases = (li + 1 < sq.lines.size() ? sq.lines[li + 1].second : sq.len) - sq.lines[li].second;
+                size_t off = (size_t)at - sq.lines[li].second;
+                size_t take = std::min<size_t>(line_bases - off, (size_t)(hi - at));
+                const char* src = (const char*)fasta + sq.lines[li].first + off;
+                while (take) {
+                    size_t m = std::min<size_t>(take, 60 - col);
+                    out.append(src, m);
+                    src += m; take -= m; at += (long)m; col += m;
+                    if (col == 60) { out += '\n'; col = 0; }
+                }
+                ++li;
+            }
+        }
+        if (col) out += '\n';
+    }
+    *n = out.size();
+    if (dst) {
+        if (cap < out.size()) return fail(LHGT_E_ARG, "FASTA buffer too small (%zu needed)", out.size());
+        memcpy(dst, out.data(), out.size());
+    }
+    return 0;
+}
+
+extern "C" int lhgt_extract_regions_files(const char* fasta_path, const char* interval_path, const char* out_fasta, long* extract_len) {
+    if (!fasta_path || !interval_path) return fail(LHGT_E_ARG, "null pointer");
+    HostFile iv, lens, fa;
+    int rc;
+    std::string len_path = std::string(fasta_path) + ".genome.len.txt", bed_path = std::string(interval_path) + ".bed";
+    if ((rc = slurp(interval_path, iv, false)) || (rc = slurp(len_path.c_str(), lens, false))) return rc;
+    size_t need = 0;
+    if ((rc = lhgt_bed_text((const char*)iv.p, iv.n, (const char*)lens.p, lens.n, nullptr, 0, &need, extract_len))) return rc;
+    std::string bed(need, '\0');
+    if ((rc = lhgt_bed_text((const char*)iv.p, iv.n, (const char*)lens.p, lens.n, &bed[0], bed.size(), &need, extract_len))) return rc;
+    if ((rc = spill(bed_path.c_str(), bed.data(), bed.size()))) return rc;
+    if (!out_fasta) return 0;
+    if ((rc = slurp(fasta_path, fa, false))) return rc;
+    if ((rc = lhgt_regions_fasta(fa.p, fa.n, bed.data(), bed.size(), nullptr, 0, &need))) return rc;
+    std::string text(need, '\0');
+    if ((rc = lhgt_regions_fasta(fa.p, fa.n, bed.data(), bed.size(), &text[0], text.size(), &need))) return rc;
+    return spill(out_fasta, text.data(), text.size());
 }
 
 // stod-like parse of a whole argument (E:1359-1371)
