@@ -949,7 +949,7 @@ static int s1_binned(lhgt_ctx* c, Reads& r, uint64_t byte_budget) {
     per_chunk = std::min<uint64_t>(per_chunk, std::max<uint64_t>(r.nrec, 1));
     double expect = per_rec * (double)per_chunk;
     bp.cap_a = (uint32_t)(((uint64_t)(expect / (double)n_a * slack_a) + pad_a) & ~(uint64_t)7);
-    bp.cap_b = (uint32_t)((uint64_t)(expect / (double)n_l * slack_b) + pad_b);
+    bp.cap_b = (uint32_t)(((uint64_t)(expect / (double)n_l * slack_b) + pad_b + 3) & ~(uint64_t)3);   // leaf regions start on 16-byte boundaries
     uint64_t need_a = n_a * bp.cap_a, need_b = n_l * bp.cap_b;
     if (c->bin_pool_a_entries < need_a) {
         dev_free(c->d_bin_pool_a); c->bin_pool_a_entries = 0;

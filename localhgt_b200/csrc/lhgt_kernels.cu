@@ -338,25 +338,50 @@ __global__ void __launch_bounds__(kFqThreads) fq_count_kernel(const uint8_t* __r
     }
 }
 
-// newline with global rank g ends line g: line 4r+1 is the sequence of record r
+// newline with global rank g ends line g: line 4r+1 is the sequence of record r.
+// A thread owns kFqIter 16-byte chunks, iteration-major (coalesced); the ranks of its newlines need the exclusive scan
+// of the per-chunk counts in file order = (iteration, thread) order.  All kFqIter scans run as ONE block scan over
+// kFqIter-vectors (same barriers as a scalar scan), then the iteration totals are chained.
 __global__ void __launch_bounds__(kFqThreads) fq_assign_kernel(const uint8_t* __restrict__ fq, uint64_t n,
                                                                const uint32_t* __restrict__ tile_base,
                                                                uint64_t* __restrict__ rec_start,
                                                                uint64_t* __restrict__ rec_end, uint64_t rec_cap) {
-    __shared__ uint32_t sm[33];
-    uint64_t tile0 = (uint64_t)blockIdx.x * kFqTile;
-    uint64_t running = tile_base[blockIdx.x];
+    __shared__ uint32_t wsum[kFqIter][kFqThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t tile0 = (uint64_t)blockIdx.x * kFqTile;
+    uint32_t m[kFqIter][4], c[kFqIter], inc[kFqIter];
+#pragma unroll
     for (int it = 0; it < kFqIter; ++it) {
         uint64_t off = tile0 + (uint64_t)it * kFqSub + (uint64_t)threadIdx.x * kFqChunk;
-        uint32_t w[4] = {0, 0, 0, 0}, m[4], c = 0;
+        uint32_t w[4] = {0, 0, 0, 0};
         if (off < n) load16(fq, off, n, w);
+        c[it] = 0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { m[q] = off < n ? __vcmpeq4(w[q], 0x0a0a0a0au) : 0u; c += __popc(m[q]) >> 3; }
-        uint32_t total, ex = block_exclusive_scan(c, &total, sm);
-        uint64_t g = running + ex;
+        for (int q = 0; q < 4; ++q) { m[it][q] = off < n ? __vcmpeq4(w[q], 0x0a0a0a0au) : 0u; c[it] += __popc(m[it][q]) >> 3; }
+        inc[it] = c[it];
+    }
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+#pragma unroll
+        for (int it = 0; it < kFqIter; ++it) {
+            uint32_t t = __shfl_up_sync(kFull, inc[it], d);
+            if (lane >= d) inc[it] += t;
+        }
+    if (lane == 31)
+#pragma unroll
+        for (int it = 0; it < kFqIter; ++it) wsum[it][warp] = inc[it];
+    __syncthreads();
+    uint64_t running = tile_base[blockIdx.x];
+#pragma unroll
+    for (int it = 0; it < kFqIter; ++it) {
+        uint32_t before = 0, total = 0;
+#pragma unroll
+        for (int q = 0; q < kFqThreads / 32; ++q) { uint32_t v = wsum[it][q]; before += q < warp ? v : 0u; total += v; }
+        uint64_t g = running + before + inc[it] - c[it];
+        uint64_t off = tile0 + (uint64_t)it * kFqSub + (uint64_t)threadIdx.x * kFqChunk;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            uint32_t mm = m[q];
+            uint32_t mm = m[it][q];
             while (mm) {
                 int bit = __ffs(mm) - 1;
                 mm &= ~(0xffu << (bit & ~7));
@@ -806,7 +831,7 @@ __global__ void __launch_bounds__(kSplitThreads, 3) s1_split_kernel(BinP bp, Has
 }
 
 // P3.  One CTA per leaf.
-constexpr int kLeafThreads = 256, kLeafPer = 8;
+constexpr int kLeafThreads = 256, kLeafPer = 2;      // 2 x 16-byte loads = 8 entries per thread per batch
 constexpr int kLeafMaxLog2 = 18;                               // 2^18 counters = 64 KiB of shared memory
 
 __global__ void __launch_bounds__(kLeafThreads, 3) s1_leaf_kernel(BinP bp, HashP hp, uint32_t* __restrict__ count) {
@@ -831,41 +856,41 @@ __global__ void __launch_bounds__(kLeafThreads, 3) s1_leaf_kernel(BinP bp, HashP
     } else {
         for (uint32_t x = threadIdx.x; x < words; x += kLeafThreads) slice[x] = home[x];
     }
-    // the first hashes travel while the slice does
-    uint32_t h[kLeafPer];
+    // The stream is read four entries per load (leaf regions start on 16-byte boundaries), two loads per thread in
+    // flight beyond the pair being applied; the first ones travel while the slice does.
+    const uint4* __restrict__ in4 = reinterpret_cast<const uint4*>(in);
+    const uint32_t nvec = n >> 2;
+    auto fetch = [&](uint32_t v) {
+        uint4 r = make_uint4(0u, 0u, 0u, 0u);
+        if (v < nvec) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(in4 + v));
+        return r;
+    };
+    auto apply = [&](uint32_t idx) {                           // idx = tbl_idx(hash), stored by s1_split_kernel
+        uint32_t* addr = slice + (idx >> 4);
+        int sh = (idx & 15u) * 2;
+        uint32_t seen = *addr;
+        while (((seen >> sh) & 3u) < 3u) {
+            uint32_t old = atomicCAS(addr, seen, seen + (1u << sh));
+            if (old == seen) break;
+            seen = old;
+        }
+    };
+    uint4 cur[kLeafPer];
 #pragma unroll
-    for (int q = 0; q < kLeafPer; ++q) {
-        uint32_t x = threadIdx.x + q * kLeafThreads;
-        h[q] = x < n ? ld_stream(in + x) : 0u;
-    }
+    for (int q = 0; q < kLeafPer; ++q) cur[q] = fetch(threadIdx.x + q * kLeafThreads);
     __syncthreads();
     if (bulk) mbar_wait(&bar, 0);
-    for (uint32_t base = 0; base < n; base += kLeafThreads * kLeafPer) {
-        uint32_t nx[kLeafPer];
-        uint32_t nbase = base + kLeafThreads * kLeafPer;
+    for (uint32_t base = 0; base < nvec; base += kLeafThreads * kLeafPer) {
+        uint4 nx[kLeafPer];
 #pragma unroll
-        for (int q = 0; q < kLeafPer; ++q) {                   // next batch in flight while this one is applied
-            uint32_t x = nbase + threadIdx.x + q * kLeafThreads;
-            nx[q] = x < n ? ld_stream(in + x) : 0u;
-        }
+        for (int q = 0; q < kLeafPer; ++q) nx[q] = fetch(base + kLeafThreads * kLeafPer + threadIdx.x + q * kLeafThreads);
 #pragma unroll
-        for (int q = 0; q < kLeafPer; ++q) {
-            uint32_t x = base + threadIdx.x + q * kLeafThreads;
-            if (x < n) {
-                uint32_t idx = h[q];                           // s1_split_kernel stored tbl_idx(hash)
-                uint32_t* addr = slice + (idx >> 4);
-                int sh = (idx & 15u) * 2;
-                uint32_t seen = *addr;
-                while (((seen >> sh) & 3u) < 3u) {
-                    uint32_t old = atomicCAS(addr, seen, seen + (1u << sh));
-                    if (old == seen) break;
-                    seen = old;
-                }
-            }
-        }
+        for (int q = 0; q < kLeafPer; ++q)
+            if (base + threadIdx.x + q * kLeafThreads < nvec) { apply(cur[q].x); apply(cur[q].y); apply(cur[q].z); apply(cur[q].w); }
 #pragma unroll
-        for (int q = 0; q < kLeafPer; ++q) h[q] = nx[q];
+        for (int q = 0; q < kLeafPer; ++q) cur[q] = nx[q];
     }
+    for (uint32_t x = (nvec << 2) + threadIdx.x; x < n; x += kLeafThreads) apply(in[x]);   // n % 4 entries
     __syncthreads();
     if (bulk) {
         if (threadIdx.x == 0) {
