@@ -307,17 +307,23 @@ def ours(args) -> None:
         scr.set_stream(stream.cuda_stream)
         # ---- index build (the IB half of the metric): kernel time and host->host time
         ib_ms_kernel, ib_ms_e2e = [], []
+        scr.index_build(fasta)
+        image = scr.index_download()                                   # the image the e2e steps upload again
+        scr.stage_ms()
+        pinned_image = torch.empty(image.size, dtype=torch.uint8).pin_memory()
         for i in range(3):
             t = time.perf_counter()
             scr.index_build(fasta)
-            image = scr.index_download()
+            scr.index_download_ptr(pinned_image.data_ptr(), pinned_image.numel())
             ib_ms_e2e.append(1000 * (time.perf_counter() - t))
             ib_ms_kernel.append(float(scr.stage_ms()[5]))
             scr.reset()
+        assert bytes(pinned_image.numpy()[:4096]) == bytes(image[:4096]) and bytes(pinned_image.numpy()[-4096:]) == bytes(image[-4096:])
+        del pinned_image
         index_bases = scr.index_bases()
         index_build = {"gbp_per_s": index_bases / 1e6 / min(ib_ms_kernel), "kernel_ms": min(ib_ms_kernel),
                        "e2e_gbp_per_s": index_bases / 1e6 / min(ib_ms_e2e), "e2e_ms": min(ib_ms_e2e), "bases": index_bases,
-                       "index_bytes": int(image.size), "e2e_how": "host FASTA bytes -> parse -> H2D -> kernel -> D2H index image (pageable)",
+                       "index_bytes": int(image.size), "e2e_how": "host FASTA bytes -> header scan on the host, H2D, sequence compaction + hashing on the device -> D2H index image (pinned)",
                        "roofline": {"bound": "hbm", "achieved": index_bases * (1 + 4 * E) / 1e6 / min(ib_ms_kernel),
                                     "unit": "GB/s", "bytes_per_base": 1 + 4 * E}}
 

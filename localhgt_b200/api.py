@@ -226,6 +226,10 @@ class Screen:
         _check(self._L.lhgt_index_download(self._h, _ptr(out), out.size))
         return out
 
+    def index_download_ptr(self, host_ptr: int, cap: int) -> None:
+        """Into caller-owned host memory (pinned memory makes the copy run at PCIe speed)."""
+        _check(self._L.lhgt_index_download(self._h, host_ptr, cap))
+
     def index_len_text(self) -> bytes:
         n = _sz(0)
         _check(self._L.lhgt_index_len_text(self._h, None, 0, C.byref(n)))

@@ -480,28 +480,95 @@ static int alloc_image(lhgt_ctx* c, uint64_t words) {
     return 0;
 }
 
+// The same loop with the sequence bytes left where they are: the host only finds the header lines (few) and the
+// device compacts the rest (launch_fasta_compact).  Fills `pf.contigs` / `pf.len_text`; the compacted bytes end up in
+// *d_seq (caller frees).  Used for files whose sequence-byte count fits the 32-bit tile scan.
+static int ingest_fasta_device(lhgt_ctx* c, const uint8_t* fa, size_t n, ParsedFasta& pf, uint8_t** d_seq) {
+    std::vector<ByteSpan> spans;
+    std::vector<std::string> names;
+    for (size_t pos = 0; pos < n;) {
+        const uint8_t* gt = (const uint8_t*)memchr(fa + pos, '>', n - pos);
+        if (!gt) break;
+        size_t at = (size_t)(gt - fa);
+        if (at && fa[at - 1] != '\n') { pos = at + 1; continue; }                // a '>' inside a line is a (bad) base
+        const uint8_t* nl = (const uint8_t*)memchr(gt, '\n', n - at);
+        size_t end = nl ? (size_t)(nl - fa) : n;                                  // header text is [at, end)
+        size_t idl = read_id_len(gt, end - at);
+        names.emplace_back((const char*)gt + 1, idl > 0 ? idl - 1 : 0);           // E:764
+        spans.push_back({(uint64_t)at, (uint64_t)(nl ? end : n - 1)});
+        pos = nl ? end + 1 : n;
+    }
+    const uint32_t ns = (uint32_t)spans.size();
+    uint64_t tiles = fastq_index_tiles(n);
+    std::vector<uint64_t> q(ns + 1), before(ns + 1, 0);
+    for (uint32_t i = 0; i < ns; ++i) q[i] = spans[i].lo;
+    q[ns] = n;
+    uint8_t* d_fa = nullptr; ByteSpan* d_spans = nullptr; uint64_t *d_q = nullptr, *d_before = nullptr;
+    uint32_t *d_cnt = nullptr, *d_base = nullptr, *d_tmp = nullptr;
+    *d_seq = nullptr;
+    int rc = 0;
+    auto cleanup = [&]() { dev_free(d_fa); dev_free(d_spans); dev_free(d_q); dev_free(d_before); dev_free(d_cnt); dev_free(d_base); dev_free(d_tmp); };
+    if ((rc = dev_alloc(&d_fa, n + 64)) || (rc = dev_alloc(&d_spans, (size_t)ns + 1)) || (rc = dev_alloc(&d_q, (size_t)ns + 1)) ||
+        (rc = dev_alloc(&d_before, (size_t)ns + 1)) || (rc = dev_alloc(&d_cnt, tiles + 1)) || (rc = dev_alloc(&d_base, tiles + 1)) ||
+        (rc = dev_alloc(&d_tmp, scan_tmp_words(tiles))) || (rc = dev_alloc(d_seq, n + 64))) {
+        cleanup();
+        return rc;
+    }
+    cudaMemcpyAsync(d_fa, fa, n, cudaMemcpyHostToDevice, c->st);
+    if (ns) cudaMemcpyAsync(d_spans, spans.data(), ns * sizeof(ByteSpan), cudaMemcpyHostToDevice, c->st);
+    cudaMemcpyAsync(d_q, q.data(), (ns + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->st);
+    c->launches += launch_fasta_compact(d_fa, n, d_spans, ns, d_cnt, d_base, d_tmp, *d_seq, d_q, ns + 1, d_before, 0, c->st);
+    c->launches += launch_fasta_compact(d_fa, n, d_spans, ns, d_cnt, d_base, d_tmp, *d_seq, d_q, ns + 1, d_before, 1, c->st);
+    cudaMemcpyAsync(before.data(), d_before, (ns + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->st);
+    cudaError_t e1 = cudaStreamSynchronize(c->st);
+    cleanup();
+    if (e1 != cudaSuccess) { dev_free(*d_seq); *d_seq = nullptr; return fail(LHGT_E_CUDA, "FASTA compaction failed: %s", cudaGetErrorString(e1)); }
+    // contig 0 is what precedes the first header (name "start", E:747); contig i >= 1 follows header i
+    uint64_t word = LHGT_CODER_SLOTS;
+    long cumulative = 0;
+    for (uint32_t i = 0; i <= ns; ++i) {
+        uint64_t lo = i ? before[i - 1] : 0, hi = before[i];
+        size_t len = (size_t)(hi - lo);
+        cumulative += (long)len;
+        if (len > (size_t)c->k) {                                                 // E:772, 836
+            char buf[96];
+            snprintf(buf, sizeof buf, "\t%ld\t%zu\t%ld\n", (long)i, len, cumulative);
+            pf.len_text += i ? names[i - 1] : std::string("start"); pf.len_text += buf;
+            Contig g{};
+            g.hash_word = word + 1; g.seq_off = lo; g.len = (uint32_t)len; g.tile0 = 0;
+            if (len > 178000000u) { dev_free(*d_seq); *d_seq = nullptr; return fail(LHGT_E_FORMAT, "contig longer than the reference's int buffers allow (E:925)"); }
+            pf.contigs.push_back(g);
+            word += 1 + (uint64_t)(len - c->k + 1) * c->e;
+        }
+    }
+    return 0;
+}
+
 extern "C" int lhgt_index_build(lhgt_ctx* c, const uint8_t* fasta, size_t n) {
     if (!c || (!fasta && n)) return fail(LHGT_E_ARG, "lhgt_index_build: null pointer");
     CU(cudaSetDevice(c->device));
     if (!coder_ok(c->cc, c->k, c->e)) return fail(LHGT_E_STATE, "set the coder before building an index");
     drop_index(c);
     ParsedFasta pf;
-    parse_fasta(fasta, n, c->k, c->e, pf);
-    for (auto& g : pf.contigs)
-        if (g.len > 178000000u) return fail(LHGT_E_FORMAT, "contig longer than the reference's int buffers allow (E:925)");
+    uint8_t* d_seq = nullptr;
+    int rc;
+    if (n > 0 && n < 0xf0000000ull) {
+        if ((rc = ingest_fasta_device(c, fasta, n, pf, &d_seq))) return rc;
+    } else {                                                                      // host getline loop, then one upload
+        parse_fasta(fasta, n, c->k, c->e, pf);
+        for (auto& g : pf.contigs)
+            if (g.len > 178000000u) return fail(LHGT_E_FORMAT, "contig longer than the reference's int buffers allow (E:925)");
+        if ((rc = dev_alloc(&d_seq, pf.seq.size() + 64))) return rc;
+        CU(cudaMemcpyAsync(d_seq, pf.seq.data(), pf.seq.size(), cudaMemcpyHostToDevice, c->st));
+    }
     c->contigs = pf.contigs;
     c->len_text = pf.len_text;
     uint64_t words = LHGT_CODER_SLOTS;
     for (auto& g : c->contigs) words += 1 + (uint64_t)(g.len - c->k + 1) * c->e;
-    int rc = alloc_image(c, words);
-    if (rc) return rc;
-    if ((rc = finish_index_tables(c))) return rc;
+    if ((rc = alloc_image(c, words)) || (rc = finish_index_tables(c))) { cudaStreamSynchronize(c->st); cudaFree(d_seq); return rc; }
     uint32_t header[LHGT_CODER_SLOTS];
     lhgt_coder_to_header(c->cc, header);
     CU(cudaMemcpyAsync(c->d_image, header, sizeof header, cudaMemcpyHostToDevice, c->st));
-    uint8_t* d_seq = nullptr;
-    if ((rc = dev_alloc(&d_seq, pf.seq.size() + 64))) return rc;
-    CU(cudaMemcpyAsync(d_seq, pf.seq.data(), pf.seq.size(), cudaMemcpyHostToDevice, c->st));
     {
         Span sp(c, 5);
         c->launches += launch_index_build(d_seq, c->d_contigs, c->d_tiles, c->tiles.size(), c->hp, c->d_image, nullptr, c->st);

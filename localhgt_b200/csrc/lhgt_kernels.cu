@@ -420,6 +420,149 @@ __global__ void sum_lengths_kernel(const uint64_t* __restrict__ s, const uint64_
     if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
 }
 
+// ------------------------------------------------------------------------------------------------
+// FASTA ingest on the device (the getline loop of read_ref, E:761-831, as a stream compaction): the raw file bytes
+// are uploaded once; a byte is a sequence byte iff it is not '\n' and not inside a header line.  Header lines are
+// few: the host finds them (memchr) and passes their byte spans.  Same tile geometry as the FASTQ scan.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t fa_keep_mask(const uint8_t* __restrict__ fa, uint64_t off, uint64_t n,
+                                                 const ByteSpan* __restrict__ spans, uint32_t nspans) {   // bit b: byte off+b is kept
+    if (off >= n) return 0u;
+    uint32_t w[4];
+    load16(fa, off, n, w);
+    uint32_t keep = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint32_t nl = __vcmpeq4(w[q], 0x0a0a0a0au);             // 0xff per newline byte
+        uint32_t bits = ((~nl) & 0x01010101u) * 0x01020408u >> 24;   // 4 bits: byte j kept -> bit j
+        keep |= (bits & 0xfu) << (q * 4);
+    }
+    if (off + 16 > n) keep &= (1u << (uint32_t)(n - off)) - 1u;
+    // header spans that overlap [off, off + 16): first span with hi >= off
+    uint32_t lo = 0, hi = nspans;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (spans[mid].hi < off) lo = mid + 1; else hi = mid;
+    }
+    for (; lo < nspans && spans[lo].lo < off + 16; ++lo) {
+        uint64_t a = spans[lo].lo > off ? spans[lo].lo - off : 0, b = spans[lo].hi - off;   // local [a, b], b may exceed 15
+        uint32_t upto = b >= 15 ? 0xffffu : (1u << (uint32_t)(b + 1)) - 1u;
+        keep &= ~(upto & ~((1u << (uint32_t)a) - 1u));
+    }
+    return keep;
+}
+
+__global__ void __launch_bounds__(kFqThreads) fa_count_kernel(const uint8_t* __restrict__ fa, uint64_t n, const ByteSpan* __restrict__ spans,
+                                                              uint32_t nspans, uint32_t* __restrict__ tile_cnt) {
+    __shared__ uint32_t sm[8];
+    uint64_t tile0 = (uint64_t)blockIdx.x * kFqTile;
+    uint32_t c = 0;
+#pragma unroll
+    for (int it = 0; it < kFqIter; ++it)
+        c += __popc(fa_keep_mask(fa, tile0 + (uint64_t)it * kFqSub + (uint64_t)threadIdx.x * kFqChunk, n, spans, nspans));
+#pragma unroll
+    for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(kFull, c, d);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < kFqThreads / 32; ++w) t += sm[w];
+        tile_cnt[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(kFqThreads) fa_compact_kernel(const uint8_t* __restrict__ fa, uint64_t n, const ByteSpan* __restrict__ spans,
+                                                                uint32_t nspans, const uint32_t* __restrict__ tile_base,
+                                                                uint8_t* __restrict__ out) {
+    __shared__ uint32_t wsum[kFqIter][kFqThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t tile0 = (uint64_t)blockIdx.x * kFqTile;
+    uint32_t keep[kFqIter], c[kFqIter], inc[kFqIter];
+#pragma unroll
+    for (int it = 0; it < kFqIter; ++it) {
+        keep[it] = fa_keep_mask(fa, tile0 + (uint64_t)it * kFqSub + (uint64_t)threadIdx.x * kFqChunk, n, spans, nspans);
+        c[it] = __popc(keep[it]);
+        inc[it] = c[it];
+    }
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+#pragma unroll
+        for (int it = 0; it < kFqIter; ++it) {
+            uint32_t t = __shfl_up_sync(kFull, inc[it], d);
+            if (lane >= d) inc[it] += t;
+        }
+    if (lane == 31)
+#pragma unroll
+        for (int it = 0; it < kFqIter; ++it) wsum[it][warp] = inc[it];
+    __syncthreads();
+    uint64_t running = tile_base[blockIdx.x];
+#pragma unroll
+    for (int it = 0; it < kFqIter; ++it) {
+        uint32_t before = 0, total = 0;
+#pragma unroll
+        for (int q = 0; q < kFqThreads / 32; ++q) { uint32_t v = wsum[it][q]; before += q < warp ? v : 0u; total += v; }
+        uint64_t g = running + before + inc[it] - c[it];
+        uint64_t off = tile0 + (uint64_t)it * kFqSub + (uint64_t)threadIdx.x * kFqChunk;
+        uint32_t mm = keep[it];
+        while (mm) {
+            int b = __ffs(mm) - 1;
+            mm &= mm - 1;
+            out[g++] = fa[off + b];
+        }
+        running += total;
+    }
+}
+
+// out[i] = number of kept bytes before byte position pos[i] (pos[i] <= n); one CTA per query
+__global__ void __launch_bounds__(kFqThreads) fa_offsets_kernel(const uint8_t* __restrict__ fa, uint64_t n, const ByteSpan* __restrict__ spans,
+                                                                uint32_t nspans, const uint32_t* __restrict__ tile_base, uint64_t ntiles,
+                                                                const uint64_t* __restrict__ pos, uint64_t* __restrict__ out) {
+    __shared__ uint32_t sm[8];
+    uint64_t q = pos[blockIdx.x];
+    uint64_t tile = q / kFqTile;
+    uint32_t c = 0;
+    uint64_t base = 0;
+    if (tile < ntiles) {
+        base = tile_base[tile];
+        uint64_t tile0 = tile * kFqTile;
+        for (int it = 0; it < kFqIter; ++it) {
+            uint64_t off = tile0 + (uint64_t)it * kFqSub + (uint64_t)threadIdx.x * kFqChunk;
+            if (off >= q) continue;
+            uint32_t m = fa_keep_mask(fa, off, n, spans, nspans);
+            if (q - off < 16) m &= (1u << (uint32_t)(q - off)) - 1u;
+            c += __popc(m);
+        }
+    } else if (ntiles) {                                       // q == n on a tile boundary: everything
+        base = (uint64_t)tile_base[ntiles - 1];
+        uint64_t tile0 = (ntiles - 1) * kFqTile;
+        for (int it = 0; it < kFqIter; ++it)
+            c += __popc(fa_keep_mask(fa, tile0 + (uint64_t)it * kFqSub + (uint64_t)threadIdx.x * kFqChunk, n, spans, nspans));
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(kFull, c, d);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t t = base;
+        for (int w = 0; w < kFqThreads / 32; ++w) t += sm[w];
+        out[blockIdx.x] = t;
+    }
+}
+
+int launch_fasta_compact(const uint8_t* fa, uint64_t n, const ByteSpan* spans, uint32_t nspans, uint32_t* tile_cnt, uint32_t* tile_base,
+                         uint32_t* scan_tmp, uint8_t* out, const uint64_t* pos, uint32_t npos, uint64_t* pos_out, int phase, cudaStream_t st) {
+    uint64_t tiles = fastq_index_tiles(n);
+    if (tiles == 0) return 0;
+    if (phase == 0) {
+        fa_count_kernel<<<(unsigned)tiles, kFqThreads, 0, st>>>(fa, n, spans, nspans, tile_cnt);
+        int l = 1 + launch_scan_exclusive(tile_cnt, tile_base, tiles, scan_tmp, st);
+        if (npos) { fa_offsets_kernel<<<npos, kFqThreads, 0, st>>>(fa, n, spans, nspans, tile_base, tiles, pos, pos_out); ++l; }
+        return l;
+    }
+    fa_compact_kernel<<<(unsigned)tiles, kFqThreads, 0, st>>>(fa, n, spans, nspans, tile_base, out);
+    return 1;
+}
+
 int launch_sum_lengths(const uint64_t* rec_start, const uint64_t* rec_end, uint64_t nrec, unsigned long long* out,
                        cudaStream_t st) {
     if (nrec == 0) return 0;

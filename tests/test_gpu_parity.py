@@ -288,6 +288,41 @@ def test_empty_and_degenerate_inputs(workdir):
         fixtures.clean_outputs(fa)
 
 
+@pytest.mark.parametrize("shape", ["leading_sequence", "no_final_newline", "gt_inside_line", "blank_lines_crlf", "long_lines", "headers_only"])
+def test_fasta_shapes_match_oracle_index(shape, workdir):
+    """The FASTA is compacted on the device (header spans found by the host); the oracle walks it line by line."""
+    rng = np.random.default_rng(len(shape))
+    acgt = np.frombuffer(b"ACGTacgtN", dtype=np.uint8)
+    def seq(n):
+        return acgt[rng.integers(0, len(acgt), n)].tobytes()
+    def wrap(s, w):
+        return b"\n".join(s[i:i + w] for i in range(0, len(s), w))
+    k, e = 21, 3
+    if shape == "leading_sequence":          # bytes before the first header form a contig named "start" (E:747)
+        text = wrap(seq(700), 60) + b"\n>c1 desc\n" + wrap(seq(20000), 70) + b"\n>c2/1\n" + wrap(seq(16384 * 2 + 5), 80) + b"\n"
+    elif shape == "no_final_newline":
+        text = b">a\n" + wrap(seq(5000), 61) + b"\n>b\tx\n" + wrap(seq(3000), 61)
+    elif shape == "gt_inside_line":          # a '>' that does not start a line is just a (bad) base
+        text = b">a\n" + seq(400) + b">not_a_header" + seq(300) + b"\n" + seq(50) + b"\n>b\n" + wrap(seq(4000), 100) + b"\n"
+    elif shape == "blank_lines_crlf":
+        text = b">a\n\n" + wrap(seq(3000), 50).replace(b"\n", b"\r\n") + b"\r\n\n\n>b\n" + seq(2500) + b"\n\n"
+    elif shape == "long_lines":              # one unwrapped line longer than several tiles, header spans across a tile edge
+        text = b">" + b"x" * 16380 + b" tail\n" + seq(70000) + b"\n>s\n" + seq(10) + b"\n>t\n" + seq(40000) + b"\n"
+    else:
+        text = b">a\n>b\n>c\n"
+    fa = os.path.join(workdir, f"shape_{shape}.fa")
+    open(fa, "wb").write(text)
+    o = orc.Oracle(k, e); o.srand(5); cc = o.random_coder()
+    idx, lenp = fa + ".oracle.index.dat", fa + ".oracle.len.txt"
+    assert o.index_build(fa, idx, lenp) >= 0
+    o.close()
+    with api.Screen(k, e) as s:
+        s.set_coder(cc)
+        s.index_build(text)
+        assert s.index_len_text() == _read(lenp)
+        assert bytes(s.index_download()) == _read(idx)
+
+
 # ------------------------------------------------------------------ properties at a size the oracle cannot do in seconds
 @pytest.fixture(scope="module")
 def big(tmp_path_factory):
