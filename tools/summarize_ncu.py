@@ -60,5 +60,28 @@ def kernel(path):
         print()
 
 
+def traffic(*paths):
+    """profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch, keyed the way bench.py names kernels."""
+    import json
+    import os
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    out = {}
+    for path in paths:
+        txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(txt)))
+        hdr, units = rows[0], rows[1]
+        for vals in rows[2:]:
+            d, u = dict(zip(hdr, vals)), dict(zip(hdr, units))
+            name = d.get("Kernel Name", "?").split("(")[0].replace("void ", "").strip()
+            tot = sum(float(d[m].replace(",", "")) * scale.get(u[m], 1) for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+            out[name] = int(tot)
+            if name.startswith("s1_split") or name.startswith("s1_leaf"):
+                out[name.split("<")[0]] = int(tot)
+    dst = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
+    json.dump(out, open(dst, "w"), indent=1, sort_keys=True)
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2])
+    cmd = {"launches": launches, "kernel": kernel, "traffic": traffic}[sys.argv[1]]
+    cmd(*sys.argv[2:])
