@@ -405,7 +405,10 @@ def ours(args) -> None:
     line = {
         "metric": "read pairs/sec through k-mer screen+peak extract", "value": value, "unit": "pairs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": config_dict(args.workload, meta, world),
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": dict(config_dict(args.workload, meta, world),
+                       count_exchange=("one kernel over NVLink peer memory (CUDA IPC)" if shard.p2p else "NCCL all-to-all + merge + all-gather")
+                       if world > 1 else "none (1 GPU)"),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "pairs/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(h1.numel() + h2.numel() + himg.numel()), "d2h_bytes_per_step": len(text_resident) + 64,

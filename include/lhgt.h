@@ -171,13 +171,22 @@ void*    lhgt_dev_peak_filter(lhgt_ctx* c, uint64_t* bytes);
 /* count := min(3, count + other) field-wise on packed tables (other: device pointer, same size). */
 int      lhgt_count_merge(lhgt_ctx* c, const void* dev_other, uint64_t bytes, uint64_t word_offset);
 
+/* The same exchange as ONE kernel over peer memory, for the ranks of one box (one process per GPU): every rank passes
+ * the CUDA IPC handle of its table (64 bytes, lhgt_count_table_ipc) to the others (any transport), maps theirs once
+ * with lhgt_peers_open (handles = world x 64 bytes in rank order; the own slot is ignored), and after S1 -- between two
+ * barriers the caller provides -- lhgt_count_exchange_p2p makes slice `rank` of EVERY rank's table min(3, sum over
+ * ranks) with NVLink loads and stores, no staging buffer.  Once all ranks have run it every table holds the total. */
+int      lhgt_count_table_ipc(lhgt_ctx* c, void* handle64);
+int      lhgt_peers_open(lhgt_ctx* c, int rank, int world, const void* handles);
+int      lhgt_count_exchange_p2p(lhgt_ctx* c);
+
 /* Device time spent in each stage since the previous lhgt_stage_ms call (read-and-clear), measured
  * with CUDA events on the context's stream:
  * [0] FASTQ record scan  [1] S1  [2] S2 gather  [3] S2 finish  [4] S3  [5] IB kernel. */
 int  lhgt_stage_ms(const lhgt_ctx* c, float* ms6);
 /* Same with n_stages slots: [6] S1 hash-stream kernel  [7] S1 stream-split kernel  [8] S1 leaf-apply kernel
- * ([1] holds their sum). */
-#define LHGT_STAGES 9
+ * ([1] holds their sum)  [9] peer-memory count exchange. */
+#define LHGT_STAGES 10
 int  lhgt_stage_ms_ex(const lhgt_ctx* c, float* ms, int n_stages);
 /* Kernels launched by this context since creation. */
 long lhgt_launch_count(const lhgt_ctx* c);

@@ -91,6 +91,9 @@ SYMBOLS = {
     "lhgt_dev_hit_bits": (_vp, [_vp, _i, C.POINTER(_u64)]),
     "lhgt_dev_peak_filter": (_vp, [_vp, C.POINTER(_u64)]),
     "lhgt_count_merge": (_i, [_vp, _vp, _u64, _u64]),
+    "lhgt_count_table_ipc": (_i, [_vp, _vp]),
+    "lhgt_peers_open": (_i, [_vp, _i, _i, _vp]),
+    "lhgt_count_exchange_p2p": (_i, [_vp]),
     "lhgt_stage_ms": (_i, [_vp, _vp]),
     "lhgt_stage_ms_ex": (_i, [_vp, _vp, _i]),
     "lhgt_launch_count": (_l, [_vp]),
@@ -358,11 +361,23 @@ class Screen:
     def count_merge(self, dev_other: int, nbytes: int, word_offset: int = 0) -> None:
         _check(self._L.lhgt_count_merge(self._h, dev_other, nbytes, word_offset))
 
+    def count_table_ipc(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        _check(self._L.lhgt_count_table_ipc(self._h, buf))
+        return buf.raw
+
+    def peers_open(self, rank: int, world: int, handles: bytes) -> None:
+        assert len(handles) == 64 * world
+        _check(self._L.lhgt_peers_open(self._h, rank, world, handles))
+
+    def count_exchange_p2p(self) -> None:
+        _check(self._L.lhgt_count_exchange_p2p(self._h))
+
     def stage_ms(self) -> np.ndarray:
         """Device ms per stage since the last call: [0] FASTQ record scan [1] S1 [2] S2 gather [3] S2 finish [4] S3
-        [5] IB [6] S1 hash-stream kernel [7] S1 stream-split kernel [8] S1 leaf-apply kernel."""
-        ms = np.zeros(9, dtype=np.float32)
-        _check(self._L.lhgt_stage_ms_ex(self._h, _ptr(ms), 9))
+        [5] IB [6] S1 hash-stream kernel [7] S1 stream-split kernel [8] S1 leaf-apply kernel [9] peer-memory count exchange."""
+        ms = np.zeros(10, dtype=np.float32)
+        _check(self._L.lhgt_stage_ms_ex(self._h, _ptr(ms), 10))
         return ms
 
     def launch_count(self) -> int: return int(self._L.lhgt_launch_count(self._h))

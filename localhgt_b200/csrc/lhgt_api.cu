@@ -157,6 +157,7 @@ struct lhgt_ctx {
     uint32_t *d_bin_pool_a = nullptr, *d_bin_pool_b = nullptr, *d_bin_cursor = nullptr;   // hash streams, leaf streams, their cursors
     uint64_t bin_pool_a_entries = 0, bin_pool_b_entries = 0, bin_cursor_entries = 0;
     int leaf_bits = 0;                       // count-table layout (HashP::leaf_bits), fixed at creation
+    PeerTables peers{}; int peer_rank = -1, peer_world = 0;   // other ranks' count tables mapped through CUDA IPC (lhgt_peers_open)
 
     unsigned long long* d_counter = nullptr; int* d_err = nullptr;
 
@@ -324,6 +325,7 @@ static void drop_reads(Reads& r, bool release = false) {      // forgets the sam
 }
 
 static int clear_peak_tables(lhgt_ctx* c);
+static void peers_close(lhgt_ctx* c);
 
 static void drop_index(lhgt_ctx* c, bool release = false) {     // forgets the index, keeps the buffers
     clear_peak_tables(c);                                       // un-writing the peak tables needs the index that wrote them
@@ -353,6 +355,7 @@ extern "C" void lhgt_destroy(lhgt_ctx* c) {
     c->rand_m_buf.release(); delete c->rand_gen;
     dev_free(c->d_cands); dev_free(c->d_tally); dev_free(c->d_counter); dev_free(c->d_err);
     dev_free(c->d_bin_pool_a); dev_free(c->d_bin_pool_b); dev_free(c->d_bin_cursor);
+    peers_close(c);
     if (c->copy_st) { cudaStreamSynchronize(c->copy_st); cudaStreamDestroy(c->copy_st); }
     for (lhgt_ctx::Prefetch* p : {&c->pf_reads[0], &c->pf_reads[1], &c->pf_index}) if (p->done) cudaEventDestroy(p->done);
     if (c->own) cudaStreamDestroy(c->own);
@@ -1312,6 +1315,53 @@ extern "C" int lhgt_count_merge(lhgt_ctx* c, const void* dev_other, uint64_t byt
     if (word_offset + bytes / 4 > c->count_words) return fail(LHGT_E_ARG, "merge range exceeds the count table");
     CU(cudaSetDevice(c->device));
     c->launches += launch_count_merge(c->d_count + word_offset, (const uint32_t*)dev_other, bytes / 4, c->st);
+    return 0;
+}
+
+extern "C" int lhgt_count_table_ipc(lhgt_ctx* c, void* handle64) {
+    if (!c || !handle64) return fail(LHGT_E_ARG, "null pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CU(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, c->d_count));
+    memcpy(handle64, &h, sizeof h);
+    return 0;
+}
+
+static void peers_close(lhgt_ctx* c) {
+    for (int r = 0; r < c->peer_world; ++r)
+        if (r != c->peer_rank && c->peers.table[r]) cudaIpcCloseMemHandle(c->peers.table[r]);
+    c->peers = PeerTables{}; c->peer_rank = -1; c->peer_world = 0;
+}
+
+extern "C" int lhgt_peers_open(lhgt_ctx* c, int rank, int world, const void* handles) {
+    if (!c || !handles || world < 1 || world > kMaxPeers || rank < 0 || rank >= world) return fail(LHGT_E_ARG, "lhgt_peers_open: bad argument");
+    if (c->count_words % (4ull * world)) return fail(LHGT_E_ARG, "count table does not split into %d 16-byte-aligned slices", world);
+    CU(cudaSetDevice(c->device));
+    peers_close(c);
+    c->peer_rank = rank; c->peer_world = world;
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) { c->peers.table[r] = c->d_count; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const uint8_t*)handles + (size_t)r * sizeof h, sizeof h);
+        void* p = nullptr;
+        cudaError_t e1 = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e1 != cudaSuccess) {
+            cudaGetLastError();
+            peers_close(c);
+            return fail(LHGT_E_CUDA, "cannot map rank %d's count table (CUDA IPC): %s", r, cudaGetErrorString(e1));
+        }
+        c->peers.table[r] = (uint32_t*)p;
+    }
+    return 0;
+}
+
+extern "C" int lhgt_count_exchange_p2p(lhgt_ctx* c) {
+    if (!c) return fail(LHGT_E_ARG, "null ctx");
+    if (c->peer_world < 2) return fail(LHGT_E_STATE, "call lhgt_peers_open first");
+    CU(cudaSetDevice(c->device));
+    Span sp(c, 9);
+    c->launches += launch_count_exchange(c->peers, c->peer_world, c->peer_rank, c->count_words, c->st);
     return 0;
 }
 

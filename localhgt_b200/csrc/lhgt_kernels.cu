@@ -1658,4 +1658,35 @@ int launch_count_merge(uint32_t* count, const uint32_t* other, uint64_t words, c
     return 1;
 }
 
+// The multi-GPU count exchange as ONE kernel over peer memory (NVLink loads and stores, no staging buffer): this rank
+// owns slice `rank` of every rank's table; it reads that slice from all `world` tables, combines the 2-bit fields with
+// min(3, sum) and stores the result back into all of them.  Ranks touch disjoint slices, so the only synchronisation
+// is a barrier before (every table final) and after (every slice written everywhere).
+__global__ void __launch_bounds__(256) count_exchange_kernel(PeerTables pt, int world, int rank, uint64_t slice_vec /* uint4s per slice */) {
+    const uint64_t lo = (uint64_t)rank * slice_vec;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < slice_vec; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint4 v[kMaxPeers];
+#pragma unroll
+        for (int r = 0; r < kMaxPeers; ++r)
+            if (r < world) v[r] = reinterpret_cast<const uint4*>(pt.table[r])[lo + i];
+        uint4 acc = v[0];
+#pragma unroll
+        for (int r = 1; r < kMaxPeers; ++r)
+            if (r < world) {
+                acc.x = sat_add2(acc.x, v[r].x); acc.y = sat_add2(acc.y, v[r].y);
+                acc.z = sat_add2(acc.z, v[r].z); acc.w = sat_add2(acc.w, v[r].w);
+            }
+#pragma unroll
+        for (int r = 0; r < kMaxPeers; ++r)
+            if (r < world) reinterpret_cast<uint4*>(pt.table[r])[lo + i] = acc;
+    }
+}
+
+int launch_count_exchange(const PeerTables& pt, int world, int rank, uint64_t table_words, cudaStream_t st) {
+    uint64_t slice_vec = table_words / 4 / (uint64_t)world;
+    if (slice_vec == 0) return 0;
+    count_exchange_kernel<<<kSMs * 8, 256, 0, st>>>(pt, world, rank, slice_vec);
+    return 1;
+}
+
 }  // namespace lhgt

@@ -138,6 +138,11 @@ int launch_sample_bits(const uint32_t* m, uint64_t n, uint32_t m_star, uint32_t*
 int launch_count_unpack(const uint32_t* count, uint64_t entries, const HashP& hp, uint8_t* out, cudaStream_t st);
 int launch_count_merge(uint32_t* count, const uint32_t* other, uint64_t words, cudaStream_t st);
 
+constexpr int kMaxPeers = 8;           // GPUs of one box
+struct PeerTables { uint32_t* table[kMaxPeers]; };   // every rank's count table, own included, as mapped in this process
+// table_words must divide by 4 * world; slice `rank` of every table := min(3, sum over ranks)
+int launch_count_exchange(const PeerTables& pt, int world, int rank, uint64_t table_words, cudaStream_t st);
+
 __host__ __device__ inline uint32_t prefilter_slot(uint32_t h) {
     // any function of h is exact here (the filter only gates the exact lookup); fold the high bits in
     return (h ^ (h >> kFilterLog2)) & ((1u << kFilterLog2) - 1u);

@@ -4,8 +4,11 @@ What is sharded and what is exchanged:
 
   S1   each rank counts the k-mers of ITS record range into its own 2^k table; the tables are then
        combined field-wise with min(3, a+b) — exact because min(3, sum) == min(3, sum of min(3, .)).
-       Exchange: all-to-all of table slices (rank r receives slice r of every table), local merge,
-       all-gather of the merged slices.  2 x table bytes per rank instead of (N-1) x.
+       Exchange, preferred form: the ranks map each other's tables (CUDA IPC) and rank r runs ONE kernel that
+       reads slice r of every table over NVLink, merges, and stores the result into every table
+       (lhgt_count_exchange_p2p) — no staging buffer, no separate merge pass.  NCCL form (when IPC is not
+       available): all-to-all of table slices, local merge, all-gather of the merged slices.  Either way
+       2 x table bytes cross each rank's links instead of (N-1) x.
   S2   the table gather (the HBM-bound part) is sharded over reference tiles; the per-position hit bits
        (2 bits per reference base) are exchanged; the cheap scans/peak registration then run replicated,
        so every rank ends with identical peak ids and an identical peak_kmer table without moving it.
@@ -85,6 +88,28 @@ class Shard:
         self.last_peaks = 0
         self.last_counts = {}
         self.last_wall_ms = {}
+        self.p2p = self._open_peers()
+
+    def _open_peers(self) -> bool:
+        """Maps every rank's count table into this process (CUDA IPC) so that the count exchange can run as one kernel
+        over NVLink peer memory.  All ranks agree on the outcome; when any of them cannot (no IPC in this container, a
+        non-GPU engine) everybody uses the NCCL form."""
+        if self.world == 1 or not hasattr(self.eng, "count_table_ipc") or self.dist is None:
+            return False
+        ok, handles = 1, [None] * self.world
+        try:
+            mine = self.eng.count_table_ipc()
+        except Exception:
+            ok, mine = 0, b"\0" * 64
+        self.dist.all_gather_object(handles, mine)
+        if ok:
+            try:
+                self.eng.peers_open(self.rank, self.world, b"".join(handles))
+            except Exception:
+                ok = 0
+        t = self.torch.tensor([ok], dtype=self.torch.int32, device=self._dev())
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return bool(int(t.item()))
 
     # ---- collectives on small host scalars
     def _all_gather_ints(self, vals):
@@ -108,6 +133,13 @@ class Shard:
     # ---- exchanges
     def exchange_counts(self) -> None:
         """count := min(3, sum over ranks), on every rank."""
+        if self.p2p:                                           # one kernel per rank over peer memory, between two barriers
+            self.eng.sync()
+            self.dist.barrier()                                # every rank's S1 has finished: all tables are final
+            self.eng.count_exchange_p2p()
+            self.eng.sync()
+            self.dist.barrier()                                # every slice has been written into every table
+            return
         tab = self.eng.table()
         n = tab.numel()
         w = self.world
