@@ -18,8 +18,20 @@ __device__ __forceinline__ uint32_t ld_cg(const uint32_t* p) { uint32_t v; asm v
 __device__ __forceinline__ uint32_t ld_nc(const uint32_t* p) { uint32_t v; asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
 __device__ __forceinline__ uint32_t ld_ca(const uint32_t* p) { uint32_t v; asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
 __device__ __forceinline__ uint32_t ld_ef(const uint32_t* p) { uint32_t v; asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+// L2 prefetch-size hints and eviction policies: does anything make an HBM miss fetch less than 128 bytes?
+__device__ __forceinline__ uint32_t ld_cg64(const uint32_t* p) { uint32_t v; asm volatile("ld.global.cg.L2::64B.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+__device__ __forceinline__ uint32_t ld_64(const uint32_t* p) { uint32_t v; asm volatile("ld.global.L2::64B.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+__device__ __forceinline__ uint32_t ld_cg128(const uint32_t* p) { uint32_t v; asm volatile("ld.global.cg.L2::128B.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+__device__ __forceinline__ uint32_t ld_efp(const uint32_t* p) {
+    uint32_t v; uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_u8(const uint32_t* p) { uint32_t v; asm volatile("ld.global.cg.u8 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
 
-// mode 0 cg, 1 nc, 2 ca, 3 evict_first, 4 red.add, 5 load+cas(2-bit sat), 6 scattered store to 32 streams
+// mode 0 cg, 1 nc, 2 ca, 3 volatile, 4 red.add, 5 load+cas(2-bit sat), 6 scattered store to 32 streams,
+// 7 cg.L2::64B, 8 L2::64B, 9 cg.L2::128B, 10 nc + evict_first policy, 11 cg.u8
 template <int MODE, int U>
 __global__ void __launch_bounds__(256) probe(uint32_t* table, uint64_t words_mask, uint64_t iters, uint32_t* sink, uint32_t* streams,
                                              uint64_t stream_cap) {
@@ -30,11 +42,12 @@ __global__ void __launch_bounds__(256) probe(uint32_t* table, uint64_t words_mas
         uint32_t h[U], v[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) h[u] = mix((uint32_t)(tid * 2654435761u) + (uint32_t)(it * U + u) * 40503u + 0x9e3779b9u * (uint32_t)(tid >> 20));
-        if (MODE <= 3 || MODE == 5) {
+        if (MODE <= 3 || MODE == 5 || MODE >= 7) {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const uint32_t* p = table + (((uint64_t)h[u]) & words_mask);
-                v[u] = MODE == 0 || MODE == 5 ? ld_cg(p) : MODE == 1 ? ld_nc(p) : MODE == 2 ? ld_ca(p) : ld_ef(p);
+                v[u] = MODE == 0 || MODE == 5 ? ld_cg(p) : MODE == 1 ? ld_nc(p) : MODE == 2 ? ld_ca(p) : MODE == 3 ? ld_ef(p) :
+                       MODE == 7 ? ld_cg64(p) : MODE == 8 ? ld_64(p) : MODE == 9 ? ld_cg128(p) : MODE == 10 ? ld_efp(p) : ld_u8(p);
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) acc += v[u];
@@ -111,6 +124,17 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&sink, 4));
     uint64_t stream_cap = 1ull << 26;                              // 32 streams x 256 MiB
     CK(cudaMalloc(&streams, 32 * stream_cap * 4));
+    if (argc > 2) {                                                 // ./probe_bench <gran> hints : the fill-size experiments only
+        for (uint64_t s : {1ull << 30}) {
+            run<0, 12>("ld.cg", table, s, 4, sink, streams, stream_cap);
+            run<7, 12>("cg.L2::64B", table, s, 4, sink, streams, stream_cap);
+            run<8, 12>("L2::64B", table, s, 4, sink, streams, stream_cap);
+            run<9, 12>("cg.L2::128", table, s, 4, sink, streams, stream_cap);
+            run<10, 12>("nc+evict1", table, s, 4, sink, streams, stream_cap);
+            run<11, 12>("cg.u8", table, s, 4, sink, streams, stream_cap);
+        }
+        return 0;
+    }
     uint64_t sizes[] = {16ull << 20, 32ull << 20, 48ull << 20, 64ull << 20, 96ull << 20, 128ull << 20, 1ull << 30, 4ull << 30};
     for (uint64_t s : sizes) run<0, 12>("ld.cg", table, s, 4, sink, streams, stream_cap);
     for (uint64_t s : {32ull << 20, 1ull << 30}) {
