@@ -51,6 +51,7 @@ SECTOR = 32                                                             # bytes 
 WORKLOADS = {
     # name: (n_genomes, genome_len, n_pairs, n_events)
     "cfg2": (40, 2_000_000, 5_000_000, 40),
+    "cfg3": (500, 2_000_000, 10_000_000, 200),                          # 1 Gbp reference, 10 M pairs (BASELINE.json configs[2])
     "small": (8, 500_000, 200_000, 6),
 }
 

@@ -152,6 +152,7 @@ struct lhgt_ctx {
     uint64_t ordinal_base = 0;               // records that precede this context's shard in the whole sample
 
     uint32_t* d_cands = nullptr; int32_t* d_tally = nullptr; S3Scratch scratch{};
+    uint32_t* d_vote_table = nullptr; uint32_t vote_contigs = 0;
 
     int s1_mode = 0;                         // 0 auto, 1 direct probes, 2 binned streams (lhgt_set_s1_mode)
     uint32_t *d_bin_pool_a = nullptr, *d_bin_pool_b = nullptr, *d_bin_cursor = nullptr;   // hash streams, leaf streams, their cursors
@@ -353,7 +354,7 @@ extern "C" void lhgt_destroy(lhgt_ctx* c) {
     dev_free(c->d_count); dev_free(c->d_peak_kmer); dev_free(c->d_prefilter);
     dev_free(c->d_loci); dev_free(c->d_filter); dev_free(c->d_sample_bits);
     c->rand_m_buf.release(); delete c->rand_gen;
-    dev_free(c->d_cands); dev_free(c->d_tally); dev_free(c->d_counter); dev_free(c->d_err);
+    dev_free(c->d_cands); dev_free(c->d_tally); dev_free(c->d_vote_table); dev_free(c->d_counter); dev_free(c->d_err);
     dev_free(c->d_bin_pool_a); dev_free(c->d_bin_pool_b); dev_free(c->d_bin_cursor);
     peers_close(c);
     if (c->copy_st) { cudaStreamSynchronize(c->copy_st); cudaStreamDestroy(c->copy_st); }
@@ -1103,8 +1104,18 @@ extern "C" int lhgt_s2_gather(lhgt_ctx* c, long tile_begin, long tile_end) {
 
 static int clear_peak_tables(lhgt_ctx* c) {
     if (c->peak_tables_dirty && c->n_peaks > 0 && c->index_ready) {
-        c->launches += launch_s2_register(c->d_image, c->d_contigs, c->d_tiles, c->tiles.size(), c->hp, c->d_count, c->d_flagged,
-                                          c->d_tile_base, c->d_loci, c->d_peak_kmer, c->d_prefilter, 1, c->st);
+        // Un-writing costs one random DRAM write per registered k-mer (~50 ps each at the measured 20 G/s); clearing the
+        // tables outright streams them at HBM speed.  A sparse result (the usual case at k = 32) is un-written, a dense
+        // one (cfg3: half of a 1 Gbp reference flagged) is cheaper to clear.
+        double unwrite_s = (double)c->n_flagged * c->e * 50e-12;
+        double clear_s = ((double)(1ull << c->k) * 4 + (double)kFilterWords * 4) / 5e12;
+        if (unwrite_s <= clear_s) {
+            c->launches += launch_s2_register(c->d_image, c->d_contigs, c->d_tiles, c->tiles.size(), c->hp, c->d_count, c->d_flagged,
+                                              c->d_tile_base, c->d_loci, c->d_peak_kmer, c->d_prefilter, 1, c->st);
+        } else {
+            CU(cudaMemsetAsync(c->d_peak_kmer, 0, (size_t)(1ull << c->k) * 4, c->st));
+            CU(cudaMemsetAsync(c->d_prefilter, 0, (size_t)kFilterWords * 4, c->st));
+        }
     }
     c->peak_tables_dirty = false;
     return 0;
@@ -1163,14 +1174,31 @@ extern "C" long lhgt_s2_peaks(lhgt_ctx* c, float hit_ratio, float match_ratio, l
 }
 
 static int ensure_s3_scratch(lhgt_ctx* c) {
-    if (c->d_cands) return 0;
     size_t warps = (size_t)s3_grid_blocks(c->device) * s3_warps_per_block();
-    c->scratch.cands_stride = (size_t)2 * kMaxReadLen * c->e;
-    c->scratch.tally_stride = (size_t)3 * 2 * kMaxReadLen;
-    int rc = dev_alloc(&c->d_cands, warps * c->scratch.cands_stride);
-    if (!rc) rc = dev_alloc(&c->d_tally, warps * c->scratch.tally_stride);
-    c->scratch.cands = c->d_cands; c->scratch.tally = c->d_tally;
-    return rc;
+    int rc = 0;
+    if (!c->d_cands) {
+        c->scratch.cands_stride = (size_t)2 * 2 * kMaxReadLen * c->e;       // peak ids + their contigs
+        c->scratch.tally_stride = (size_t)3 * 2 * kMaxReadLen;
+        rc = dev_alloc(&c->d_cands, warps * c->scratch.cands_stride);
+        if (!rc) rc = dev_alloc(&c->d_tally, warps * c->scratch.tally_stride);
+        c->scratch.cands = c->d_cands; c->scratch.tally = c->d_tally;
+        if (rc) return rc;
+    }
+    // vote table direct-addressed by contig (index 1 .. number of index records), per resident warp; skipped beyond 2 GiB
+    uint32_t nc = (uint32_t)c->contigs.size();
+    if (nc > c->vote_contigs || !c->d_vote_table) {
+        dev_free(c->d_vote_table); c->d_vote_table = nullptr; c->vote_contigs = 0;
+        size_t stride = 2 * ((size_t)nc + 1) + 1;
+        if (warps * stride * 4 <= ((size_t)2 << 30)) {
+            if ((rc = dev_alloc(&c->d_vote_table, warps * stride))) return rc;
+            CU(cudaMemsetAsync(c->d_vote_table, 0, warps * stride * 4, c->st));
+            c->vote_contigs = nc;
+        }
+    }
+    c->scratch.vote_table = c->d_vote_table;
+    c->scratch.n_contigs = c->vote_contigs;
+    c->scratch.vote_stride = 2 * ((size_t)c->vote_contigs + 1) + 1;
+    return 0;
 }
 
 extern "C" long lhgt_s3_pairs(lhgt_ctx* c, long first, long count) {

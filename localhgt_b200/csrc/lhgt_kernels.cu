@@ -1417,8 +1417,8 @@ int s3_grid_blocks(int) { return kSMs * 4; }
 template <int E>
 __device__ __forceinline__ int s3_scan_mate(const uint8_t* src, int len, const uint8_t* lut, const HashP& hp,
                                             const uint32_t* __restrict__ prefilter,
-                                            const uint32_t* __restrict__ peak_kmer, uint32_t* __restrict__ cands, int n_listed,
-                                            int lane) {
+                                            const uint32_t* __restrict__ peak_kmer, const int32_t* __restrict__ loci,
+                                            uint32_t* __restrict__ cands, int32_t* __restrict__ cont, int n_listed, int lane) {
     const int e = E ? E : hp.e;
     int np = len - hp.k + 1;
     if (np <= 0) return n_listed;
@@ -1454,7 +1454,10 @@ __device__ __forceinline__ int s3_scan_mate(const uint8_t* src, int len, const u
                 int slot = n_listed + __popc(mask & ((1u << lane) - 1u));
 #pragma unroll
                 for (int i = 0; i < (E ? E : kMaxE); ++i)
-                    if (i < e) cands[(size_t)slot * e + i] = pk[i];
+                    if (i < e) {                                  // the lane that found the peak also fetches its contig
+                        cands[(size_t)slot * e + i] = pk[i];
+                        cont[(size_t)slot * e + i] = pk[i] ? loci[2 * (size_t)pk[i]] : 0;
+                    }
             }
             n_listed += __popc(mask);
         }
@@ -1497,6 +1500,111 @@ __device__ void s3_vote(const uint32_t* cands, int n_listed, int e, const int32_
     }
 }
 
+// The single-lane vote with the tally direct-addressed by contig (one L1-resident load per candidate instead of a search
+// through the contigs seen so far): for pairs that touch many contigs -- a dense peak table makes nearly every position
+// vote.  Entries carry the epoch of the pair that wrote them, so nothing is cleared between pairs.
+__device__ void s3_vote_table(const uint32_t* cands, const int32_t* cont, int n_listed, int e, uint32_t* vt, uint32_t n_contigs,
+                              int32_t* touched, uint8_t* __restrict__ peak_filter) {
+    uint32_t* votes = vt + 1;
+    uint32_t* first = vt + 1 + (n_contigs + 1);
+    uint32_t epoch = vt[0] + 1;
+    if (epoch >= (1u << 22)) {                                  // tags would wrap: start over
+        for (uint32_t c = 0; c <= n_contigs; ++c) votes[c] = 0;
+        epoch = 1;
+    }
+    vt[0] = epoch;
+    int n_t = 0;
+    for (int f = 0; f < n_listed; ++f) {
+        uint32_t sel_peak = 0, sel_tv = 0;
+        int sel_contig = 0, sel_votes = 0;
+        bool sel_seen = false;
+        for (int i = 0; i < e; ++i) {
+            uint32_t pk = __ldcg(cands + (size_t)f * e + i);
+            if (!pk) continue;
+            int contig = __ldcg(cont + (size_t)f * e + i);
+            uint32_t tv = votes[contig];
+            if ((tv >> 10) == epoch) {
+                int v = (int)(tv & 1023u);
+                if (v >= sel_votes) { sel_peak = pk; sel_contig = contig; sel_votes = v; sel_seen = true; sel_tv = tv; }
+            } else if (sel_peak == 0) { sel_peak = pk; sel_contig = contig; sel_votes = 0; sel_seen = false; }
+        }
+        if (sel_seen) votes[sel_contig] = sel_tv + 1;           // <= 2 * kMaxReadLen votes: fits the 10 bits
+        else { votes[sel_contig] = (epoch << 10) | 1u; first[sel_contig] = sel_peak; touched[n_t++] = sel_contig; }
+    }
+    int largest = 0, second = 0, strong = 0;
+    for (int t = 0; t < n_t; ++t) {
+        int n = (int)(votes[touched[t]] & 1023u);
+        if (n < 6) continue;
+        ++strong;
+        if (n >= largest) { second = largest; largest = n; }
+        else if (n >= second) second = n;
+    }
+    if (strong < 2) return;
+    for (int t = 0; t < n_t; ++t) {
+        int n = (int)(votes[touched[t]] & 1023u);
+        if (n >= 6 && (n == largest || n == second)) peak_filter[first[touched[t]]] = 1;
+    }
+}
+
+// The same vote run by the whole warp: lane t keeps tally entry t (contig, votes, first peak) in registers, so
+// "has this contig been seen, and with how many votes" is one ballot + one shuffle instead of a search, and the
+// candidates of 32 listed positions are fetched with one coalesced load each.  The walk over positions stays sequential
+// (every vote depends on the tally so far).  Returns false when a pair touches more than 32 contigs: the caller then
+// runs the single-lane form.
+template <int E>
+__device__ __forceinline__ bool s3_vote_warp(const uint32_t* cands, const int32_t* cont, int n_listed, int e,
+                                             uint8_t* __restrict__ peak_filter, int lane) {
+    int t_contig = 0, t_votes = 0, n_t = 0;
+    uint32_t t_first = 0;
+    for (int base = 0; base < n_listed; base += 32) {
+        const int f = base + lane;
+        uint32_t pk[E ? E : kMaxE];
+        int ct[E ? E : kMaxE];
+#pragma unroll
+        for (int i = 0; i < (E ? E : kMaxE); ++i) {
+            bool on = i < e && f < n_listed;
+            pk[i] = on ? __ldcg(cands + (size_t)f * e + i) : 0u;         // written by other lanes of this warp: read at L2
+            ct[i] = on ? __ldcg(cont + (size_t)f * e + i) : 0;
+        }
+        const int lim = min(32, n_listed - base);
+        for (int j = 0; j < lim; ++j) {
+            uint32_t sel_peak = 0;
+            int sel_contig = 0, sel_votes = 0, sel_t = -1;
+#pragma unroll
+            for (int i = 0; i < (E ? E : kMaxE); ++i) {
+                uint32_t p = __shfl_sync(kFull, pk[i], j);
+                int c = __shfl_sync(kFull, ct[i], j);
+                if (i >= e || !p) continue;                               // warp-uniform
+                uint32_t m = __ballot_sync(kFull, lane < n_t && t_contig == c);
+                if (m) {
+                    int at = __ffs(m) - 1;
+                    int v = __shfl_sync(kFull, t_votes, at);
+                    if (v >= sel_votes) { sel_peak = p; sel_contig = c; sel_votes = v; sel_t = at; }
+                } else if (sel_peak == 0) { sel_peak = p; sel_contig = c; sel_votes = 0; sel_t = -1; }
+            }
+            if (sel_t >= 0) { if (lane == sel_t) ++t_votes; }
+            else {
+                if (n_t == 32) return false;
+                if (lane == n_t) { t_contig = sel_contig; t_votes = 1; t_first = sel_peak; }
+                ++n_t;
+            }
+        }
+    }
+    int v = lane < n_t && t_votes >= 6 ? t_votes : 0;                     // check_split (E:161-202)
+    if (__popc(__ballot_sync(kFull, v > 0)) < 2) return true;
+    int largest = v;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) largest = max(largest, __shfl_xor_sync(kFull, largest, d));
+    int second = largest;
+    if (__popc(__ballot_sync(kFull, v == largest)) < 2) {
+        second = v == largest ? 0 : v;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) second = max(second, __shfl_xor_sync(kFull, second, d));
+    }
+    if (v > 0 && (v == largest || v == second)) peak_filter[t_first] = 1;     // only >= 1 is consumed (E:526)
+    return true;
+}
+
 struct PairOff { uint64_t a0, b0; uint32_t l1, l2; bool ok; };
 
 // One warp per pair, two pairs ahead: while a pair is voted on, the TMA unit is staging the bytes of the next sampled
@@ -1520,7 +1628,8 @@ __global__ void __launch_bounds__(kS3Warps * 32, 4) s3_pairs_kernel(
     fill_base_lut(lut);
     __syncthreads();
     uint64_t gwarp = (uint64_t)blockIdx.x * kS3Warps + warp;
-    uint32_t* cands = scratch.cands + gwarp * scratch.cands_stride;
+    uint32_t* cands = scratch.cands + gwarp * scratch.cands_stride;            // first half: peak ids, second half: their contigs
+    int32_t* cont = reinterpret_cast<int32_t*>(cands + scratch.cands_stride / 2);
     int32_t* tally = scratch.tally + gwarp * scratch.tally_stride;
     unsigned long long mine = 0;
     const uint64_t stride = (uint64_t)gridDim.x * kS3Warps;
@@ -1571,11 +1680,17 @@ __global__ void __launch_bounds__(kS3Warps * 32, 4) s3_pairs_kernel(
         __syncwarp();                                           // every lane is done with the other slot pair
         if (rn < last && on.ok) { stage_pair(on, slot ^ 1); nstaged = true; }
         uint32_t m1 = (uint32_t)cur.a0 & 15u, m2 = (uint32_t)cur.b0 & 15u;
-        int n_listed = s3_scan_mate<E>(stage[warp][2 * slot] + m1, (int)cur.l1, lut, hp, prefilter, peak_kmer, cands, 0, lane);
-        n_listed = s3_scan_mate<E>(stage[warp][2 * slot + 1] + m2, (int)cur.l2, lut, hp, prefilter, peak_kmer, cands, n_listed, lane);
+        int n_listed = s3_scan_mate<E>(stage[warp][2 * slot] + m1, (int)cur.l1, lut, hp, prefilter, peak_kmer, loci, cands, cont, 0, lane);
+        n_listed = s3_scan_mate<E>(stage[warp][2 * slot + 1] + m2, (int)cur.l2, lut, hp, prefilter, peak_kmer, loci, cands, cont, n_listed, lane);
         if (n_listed >= 6) {                                 // base_hits >= MIN_BASE_NUM (E:496)
             __syncwarp();
-            if (lane == 0) s3_vote(cands, n_listed, e, loci, tally, peak_filter);
+            if (!s3_vote_warp<E>(cands, cont, n_listed, e, peak_filter, lane)) {        // more than 32 contigs in one pair
+                if (lane == 0) {
+                    if (scratch.vote_table) s3_vote_table(cands, cont, n_listed, e, scratch.vote_table + gwarp * scratch.vote_stride,
+                                                          scratch.n_contigs, tally, peak_filter);
+                    else s3_vote(cands, n_listed, e, loci, tally, peak_filter);
+                }
+            }
             __syncwarp();
         }
     }

@@ -71,9 +71,14 @@ struct BinP {
 };
 
 struct S3Scratch {                     // per resident warp
-    uint32_t* cands;                   // [2*(kMaxReadLen)] * e
+    uint32_t* cands;                   // [2*(kMaxReadLen)] * e peak ids, then as many contigs
     int32_t* tally;                    // [3 * 2*kMaxReadLen]
     size_t cands_stride, tally_stride; // elements per warp
+    // direct-addressed vote table for pairs that touch many contigs (s3_vote_table): per warp [0] = epoch counter,
+    // [1 + c] = epoch << 10 | votes of contig c, [1 + n_contigs + 1 + c] = first peak voted for contig c
+    uint32_t* vote_table;              // nullptr: not available (too many contigs) -> linear search
+    size_t vote_stride;                // 2 * (n_contigs + 1) + 1
+    uint32_t n_contigs;
 };
 
 // ---- launchers (all asynchronous on `st`; return the number of kernels launched) ----

@@ -288,6 +288,38 @@ def test_empty_and_degenerate_inputs(workdir):
         fixtures.clean_outputs(fa)
 
 
+@pytest.mark.parametrize("k,n_genomes", [(14, 90), (16, 48)])
+def test_s3_vote_with_many_contigs(k, n_genomes, workdir):
+    """A tiny hash space fills the peak table, so nearly every read position holds a peak k-mer of some random contig:
+    pairs vote for far more than 32 contigs, which takes S3 off the in-register tally onto the direct-addressed one."""
+    e, seed = 3, 2
+    w = synth.make_workload(workdir, f"many_{k}", seed=k, n_genomes=n_genomes, genome_len=6000, n_pairs=4000, n_events=6,
+                            seg_len=(300, 900))
+    o = orc.Oracle(k, e); o.srand(seed); cc = o.random_coder()
+    idx, lenp = w.ref_fa + ".many.index.dat", w.ref_fa + ".many.len.txt"
+    assert o.index_build(w.ref_fa, idx, lenp) == 0
+    b1, b2 = _read(w.fq1), _read(w.fq2)
+    with api.Screen(k, e) as s:
+        s.set_coder(cc)
+        s.index_build(_read(w.ref_fa))
+        s.reads_upload(0, b1); s.reads_upload(1, b2)
+        s.set_sampling(100.0, seed, 0)
+        assert (o.s1_count(w.fq1, len(b1), 100.0), o.s1_count(w.fq2, len(b1), 100.0)) == (s.s1_count(0, len(b1)), s.s1_count(1, len(b1)))
+        npo, npg = o.s2_peaks(idx, 0.1, 0.08, 1000000), s.s2_peaks(0.1, 0.08, 1000000)
+        assert npo == npg and npg >= 40
+        loci_g, _ = s.peaks()
+        assert len(set(loci_g[:, 0].tolist())) > 32, "the case must spread its peaks over more than 32 contigs"
+        assert np.array_equal(o.peak_kmer(), s.peak_kmer())
+        assert o.s3_pairs(w.fq1, w.fq2, 100.0) == s.s3_pairs()
+        _, filt_g = s.peaks()
+        assert np.array_equal(o.peak_filter() >= 1, filt_g >= 1)
+        assert int((filt_g >= 1).sum()) > 0
+        out = w.ref_fa + ".many.interval.txt"
+        o.write_intervals(out)
+        assert s.intervals() == _read(out)
+    o.close()
+
+
 @pytest.mark.parametrize("shape", ["leading_sequence", "no_final_newline", "gt_inside_line", "blank_lines_crlf", "long_lines", "headers_only"])
 def test_fasta_shapes_match_oracle_index(shape, workdir):
     """The FASTA is compacted on the device (header spans found by the host); the oracle walks it line by line."""
