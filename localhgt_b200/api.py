@@ -115,11 +115,12 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     """Loads liblhgt.so and types every declared symbol (raises if one is missing)."""
     global _lib
     if _lib is None:
-        if not os.path.exists(_build.LIB):
-            if not build_if_missing:
-                raise FileNotFoundError(_build.LIB + " is not built (python -m localhgt_b200.build)")
+        path = os.environ.get("LHGT_LIB") or _build.LIB          # LHGT_LIB: a variant build (tools/sweep.sh)
+        if not os.path.exists(path):
+            if not build_if_missing or path != _build.LIB:
+                raise FileNotFoundError(path + " is not built (python -m localhgt_b200.build)")
             _build.build()
-        L = C.CDLL(_build.LIB)
+        L = C.CDLL(path)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args

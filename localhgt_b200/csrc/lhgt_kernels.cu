@@ -743,7 +743,7 @@ __device__ __forceinline__ void bump_direct(uint32_t* count, uint32_t h, const H
 }
 
 template <int E>
-__global__ void __launch_bounds__(kBinWarps * 32, 4) s1_bin_kernel(
+__global__ void __launch_bounds__(kBinWarps * 32, kBinCtas) s1_bin_kernel(
     const uint8_t* __restrict__ fq, const uint64_t* __restrict__ rec_start, const uint64_t* __restrict__ rec_end,
     uint64_t rec_lo, uint64_t rec_hi, uint64_t budget, const uint32_t* __restrict__ sample_bits, uint64_t ordinal_base,
     HashP hp, BinP bp, uint32_t* __restrict__ count, unsigned long long* __restrict__ n_sampled, int* __restrict__ err) {
@@ -900,9 +900,19 @@ __global__ void __launch_bounds__(kBinWarps * 32, 4) s1_bin_kernel(
 }
 
 // P2.  Grid (tiles, 2^b1): CTA (x, y) splits tile x of stream y by bits [b1, b1 + b2) of the hash.
-constexpr int kSplitThreads = 512, kSplitPer = 16, kSplitTile = kSplitThreads * kSplitPer;   // 8192 hashes = 32 KiB
+// (the LHGT_* macros exist for tools/sweep.sh: variants built with -D and timed side by side)
+#ifndef LHGT_SPLIT_THREADS
+#define LHGT_SPLIT_THREADS 512
+#endif
+#ifndef LHGT_SPLIT_PER
+#define LHGT_SPLIT_PER 16
+#endif
+#ifndef LHGT_SPLIT_CTAS
+#define LHGT_SPLIT_CTAS 3
+#endif
+constexpr int kSplitThreads = LHGT_SPLIT_THREADS, kSplitPer = LHGT_SPLIT_PER, kSplitTile = kSplitThreads * kSplitPer;   // 8192 hashes = 32 KiB
 
-__global__ void __launch_bounds__(kSplitThreads, 3) s1_split_kernel(BinP bp, HashP hp, uint32_t* __restrict__ count) {
+__global__ void __launch_bounds__(kSplitThreads, LHGT_SPLIT_CTAS) s1_split_kernel(BinP bp, HashP hp, uint32_t* __restrict__ count) {
     __shared__ uint32_t tile[kSplitTile];                      // the tile again, grouped by sub-stream
     __shared__ uint32_t hist[1 << kMaxB2], off[1 << kMaxB2];
     __shared__ uint2 route[1 << kMaxB2];                       // per sub-stream: {pool_b index of grouped position 0, first position that does not fit}
@@ -974,10 +984,19 @@ __global__ void __launch_bounds__(kSplitThreads, 3) s1_split_kernel(BinP bp, Has
 }
 
 // P3.  One CTA per leaf.
-constexpr int kLeafThreads = 256, kLeafPer = 2;      // 2 x 16-byte loads = 8 entries per thread per batch
+#ifndef LHGT_LEAF_THREADS
+#define LHGT_LEAF_THREADS 640          // profiles/r01w_sweep.txt: 256x2 6.7 ms, 384 5.4, 512 5.0, 640 4.8, 1024 (2 CTAs) 5.3 per step
+#endif
+#ifndef LHGT_LEAF_PER
+#define LHGT_LEAF_PER 1
+#endif
+#ifndef LHGT_LEAF_CTAS
+#define LHGT_LEAF_CTAS 3
+#endif
+constexpr int kLeafThreads = LHGT_LEAF_THREADS, kLeafPer = LHGT_LEAF_PER;   // 16-byte loads per thread per batch
 constexpr int kLeafMaxLog2 = 18;                               // 2^18 counters = 64 KiB of shared memory
 
-__global__ void __launch_bounds__(kLeafThreads, 3) s1_leaf_kernel(BinP bp, HashP hp, uint32_t* __restrict__ count) {
+__global__ void __launch_bounds__(kLeafThreads, LHGT_LEAF_CTAS) s1_leaf_kernel(BinP bp, HashP hp, uint32_t* __restrict__ count) {
     extern __shared__ __align__(128) uint32_t slice[];         // 2^(idx_bits - 4) words
     __shared__ __align__(8) uint64_t bar;
     const uint32_t leaf = blockIdx.x;
@@ -999,8 +1018,8 @@ __global__ void __launch_bounds__(kLeafThreads, 3) s1_leaf_kernel(BinP bp, HashP
     } else {
         for (uint32_t x = threadIdx.x; x < words; x += kLeafThreads) slice[x] = home[x];
     }
-    // The stream is read four entries per load (leaf regions start on 16-byte boundaries), two loads per thread in
-    // flight beyond the pair being applied; the first ones travel while the slice does.
+    // The stream is read four entries per load (leaf regions start on 16-byte boundaries), the next batch in flight
+    // while this one is applied; the first loads travel while the slice does.
     const uint4* __restrict__ in4 = reinterpret_cast<const uint4*>(in);
     const uint32_t nvec = n >> 2;
     auto fetch = [&](uint32_t v) {
@@ -1057,7 +1076,7 @@ static cudaError_t s1_bin_launch(const uint8_t* fq, const uint64_t* rs, const ui
     cudaError_t rc = cudaFuncSetAttribute(s1_bin_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) return rc;
     uint64_t want = (hi - lo + kBinWarps - 1) / kBinWarps;
-    unsigned grid = (unsigned)(want < (uint64_t)kSMs * 4 ? want : (uint64_t)kSMs * 4);
+    unsigned grid = (unsigned)(want < (uint64_t)kSMs * kBinCtas ? want : (uint64_t)kSMs * kBinCtas);
     s1_bin_kernel<E><<<grid, kBinWarps * 32, smem, st>>>(fq, rs, re, lo, hi, budget, sb, ob, hp, bp, count, ns, err);
     return cudaGetLastError();
 }
@@ -1409,9 +1428,15 @@ int launch_s2_register(const uint32_t* image, const Contig* contigs, const Tile*
 // 2^k-entry peak table.  Positions that hold a peak k-mer are appended, in read order, to a per-warp
 // list; the order-dependent vote (judge_base) then runs on lane 0 over that (usually empty) list.
 // ------------------------------------------------------------------------------------------------
-constexpr int kS3Warps = 8;
+#ifndef LHGT_S3_WARPS
+#define LHGT_S3_WARPS 8
+#endif
+#ifndef LHGT_S3_CTAS
+#define LHGT_S3_CTAS 4
+#endif
+constexpr int kS3Warps = LHGT_S3_WARPS;
 int s3_warps_per_block() { return kS3Warps; }
-int s3_grid_blocks(int) { return kSMs * 4; }
+int s3_grid_blocks(int) { return kSMs * LHGT_S3_CTAS; }
 
 // src points into the warp's shared-memory stage (s3_pairs_kernel).
 template <int E>
@@ -1610,7 +1635,7 @@ struct PairOff { uint64_t a0, b0; uint32_t l1, l2; bool ok; };
 // One warp per pair, two pairs ahead: while a pair is voted on, the TMA unit is staging the bytes of the next sampled
 // pair into the warp's other shared-memory slots and the offsets of the one after are in flight (see stage_read).
 template <int E>
-__global__ void __launch_bounds__(kS3Warps * 32, 4) s3_pairs_kernel(
+__global__ void __launch_bounds__(kS3Warps * 32, LHGT_S3_CTAS) s3_pairs_kernel(
     const uint8_t* __restrict__ fq1, const uint64_t* __restrict__ s1, const uint64_t* __restrict__ e1, uint64_t nrec1,
     const uint8_t* __restrict__ fq2, const uint64_t* __restrict__ s2, const uint64_t* __restrict__ e2, uint64_t nrec2,
     uint64_t tail_start, uint64_t tail_len, uint64_t first, uint64_t count, const uint32_t* __restrict__ sample_bits,

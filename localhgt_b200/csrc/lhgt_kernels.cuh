@@ -53,10 +53,20 @@ struct Contig {
 // by the hashing kernel (low b1 bits of the leaf), each split into 2^b2 leaf streams (the other b2 bits) -- and every
 // leaf stream is applied to its table slice in shared memory.  leaf_bits = b1 + b2.
 constexpr int kMaxB1 = 6, kMaxB2 = 8;
-constexpr int kBinWarps = 8;           // warps per CTA of s1_bin_kernel
+#ifndef LHGT_BIN_WARPS                 // the LHGT_* macros exist for tools/sweep.sh (variants built with -D, timed side by side)
+#define LHGT_BIN_WARPS 8
+#endif
+#ifndef LHGT_BIN_ROUND_CHUNKS
+#define LHGT_BIN_ROUND_CHUNKS 4
+#endif
+#ifndef LHGT_BIN_CTAS
+#define LHGT_BIN_CTAS 4
+#endif
+constexpr int kBinWarps = LHGT_BIN_WARPS;   // warps per CTA of s1_bin_kernel
 constexpr int kCursorStride = 64;      // words between stream cursors: every CTA bumps every cursor every round, and atomics on one
                                        // cache line are served one per clock by one L2 slice (profiles/r01g) -- give each its own lines
-constexpr int kBinRoundChunks = 4;     // 32-position chunks a warp hashes per round
+constexpr int kBinRoundChunks = LHGT_BIN_ROUND_CHUNKS;   // 32-position chunks a warp hashes per round
+constexpr int kBinCtas = LHGT_BIN_CTAS;     // resident CTAs per SM the kernel is built for
 
 struct BinP {
     uint32_t* pool_a;                  // stream b (b < 2^b1) occupies pool_a[b * cap_a .. +cap_a)
