@@ -1429,10 +1429,10 @@ int launch_s2_register(const uint32_t* image, const Contig* contigs, const Tile*
 // list; the order-dependent vote (judge_base) then runs on lane 0 over that (usually empty) list.
 // ------------------------------------------------------------------------------------------------
 #ifndef LHGT_S3_WARPS
-#define LHGT_S3_WARPS 8
+#define LHGT_S3_WARPS 16
 #endif
 #ifndef LHGT_S3_CTAS
-#define LHGT_S3_CTAS 4
+#define LHGT_S3_CTAS 2
 #endif
 constexpr int kS3Warps = LHGT_S3_WARPS;
 int s3_warps_per_block() { return kS3Warps; }

@@ -54,13 +54,13 @@ struct Contig {
 // leaf stream is applied to its table slice in shared memory.  leaf_bits = b1 + b2.
 constexpr int kMaxB1 = 6, kMaxB2 = 8;
 #ifndef LHGT_BIN_WARPS                 // the LHGT_* macros exist for tools/sweep.sh (variants built with -D, timed side by side)
-#define LHGT_BIN_WARPS 8
-#endif
+#define LHGT_BIN_WARPS 32              // profiles/r01w_sweep.txt: 8 warps x 4 CTAs/SM 13.1 ms per step, 16 x 2 11.7, 32 x 1 11.0 (longer
+#endif                                 // runs per stream, fewer reservations and barriers per hash)
 #ifndef LHGT_BIN_ROUND_CHUNKS
 #define LHGT_BIN_ROUND_CHUNKS 4
 #endif
 #ifndef LHGT_BIN_CTAS
-#define LHGT_BIN_CTAS 4
+#define LHGT_BIN_CTAS 1
 #endif
 constexpr int kBinWarps = LHGT_BIN_WARPS;   // warps per CTA of s1_bin_kernel
 constexpr int kCursorStride = 64;      // words between stream cursors: every CTA bumps every cursor every round, and atomics on one

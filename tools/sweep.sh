@@ -8,12 +8,8 @@ V=tools/_build/variants
 declare -A VAR=(
   [base]=""
   [bin_w16_c2]="-DLHGT_BIN_WARPS=16 -DLHGT_BIN_CTAS=2"
-  [bin_r2_c5]="-DLHGT_BIN_ROUND_CHUNKS=2 -DLHGT_BIN_CTAS=5"
-  [bin_r2_c4]="-DLHGT_BIN_ROUND_CHUNKS=2"
-  [bin_w4_c8]="-DLHGT_BIN_WARPS=4 -DLHGT_BIN_CTAS=8 -DLHGT_BIN_ROUND_CHUNKS=8"
-  [s3_w16_c2]="-DLHGT_S3_WARPS=16 -DLHGT_S3_CTAS=2"
-  [s3_w4_c8]="-DLHGT_S3_WARPS=4 -DLHGT_S3_CTAS=8"
-  [s3_w8_c5]="-DLHGT_S3_CTAS=5"
+  [bin_w32_c1]="-DLHGT_BIN_WARPS=32 -DLHGT_BIN_CTAS=1"
+  [bin_w16_c2_s3_w16_c2]="-DLHGT_BIN_WARPS=16 -DLHGT_BIN_CTAS=2 -DLHGT_S3_WARPS=16 -DLHGT_S3_CTAS=2"
 )
 case "${1:-build}" in
 build)
