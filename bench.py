@@ -385,6 +385,7 @@ def ours(args) -> None:
         sampler = ClockSampler(local_rank) if rank == 0 else None
         ms, res, stage, launches, clocks = timed(step_resident, args.steps, args.warmup, sampler)
         text_resident = res
+        wall_resident = dict(shard.last_wall_ms)
         ms_e2e, res_e2e, stage_e2e, _, _ = timed(step_e2e, args.steps, max(1, min(args.warmup, 2)))
         assert res_e2e == text_resident, "resident and host-buffer passes disagree"
 
@@ -423,6 +424,7 @@ def ours(args) -> None:
                    "planted_recovered": recovered(text_resident, meta), "peaks": shard.last_peaks,
                    "sampled": shard.last_counts},
         "host_wall_ms_last_step": {k: round(v, 3) for k, v in shard.last_wall_ms.items()},
+        "host_wall_ms_last_resident_step": {k: round(v, 3) for k, v in wall_resident.items()},
     }
     if world == 1 and not args.no_cpu:
         try:
