@@ -164,6 +164,9 @@ int  lhgt_peak_kmer_copy(lhgt_ctx* c, uint32_t* dst /* 2^k */);
 long     lhgt_s2_tiles(const lhgt_ctx* c);
 int      lhgt_s2_gather(lhgt_ctx* c, long tile_begin, long tile_end);
 int      lhgt_s2_finish(lhgt_ctx* c, float hit_ratio, float match_ratio, long max_peak, long* n_peaks);
+/* Occupancy of the count table (the diagnostic of src/count_diff_kmer.cpp:26-50): out4[v] = number of the
+ * 2^k counters holding v.  Its "empty" figure is out4[0] / 2^k, its "weak" figure (out4[0] + out4[1] + out4[2]) / 2^k. */
+int      lhgt_count_table_histogram(lhgt_ctx* c, uint64_t* out4);
 /* Raw device pointers for the exchange steps (NCCL / peer loads run by the caller). */
 void*    lhgt_dev_count_table(lhgt_ctx* c, uint64_t* bytes);      /* packed 2-bit counters */
 void*    lhgt_dev_hit_bits(lhgt_ctx* c, int which /*0 single, 1 trio*/, uint64_t* bytes);

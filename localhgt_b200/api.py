@@ -91,6 +91,7 @@ SYMBOLS = {
     "lhgt_dev_hit_bits": (_vp, [_vp, _i, C.POINTER(_u64)]),
     "lhgt_dev_peak_filter": (_vp, [_vp, C.POINTER(_u64)]),
     "lhgt_count_merge": (_i, [_vp, _vp, _u64, _u64]),
+    "lhgt_count_table_histogram": (_i, [_vp, _vp]),
     "lhgt_count_table_ipc": (_i, [_vp, _vp]),
     "lhgt_peers_open": (_i, [_vp, _i, _i, _vp]),
     "lhgt_count_exchange_p2p": (_i, [_vp]),
@@ -361,6 +362,12 @@ class Screen:
 
     def count_merge(self, dev_other: int, nbytes: int, word_offset: int = 0) -> None:
         _check(self._L.lhgt_count_merge(self._h, dev_other, nbytes, word_offset))
+
+    def count_table_histogram(self) -> np.ndarray:
+        """[v] = number of counters holding v (0..3); empty rate = [0] / 2^k (count_diff_kmer.cpp:26-50)."""
+        out = np.zeros(4, dtype=np.uint64)
+        _check(self._L.lhgt_count_table_histogram(self._h, _ptr(out)))
+        return out
 
     def count_table_ipc(self) -> bytes:
         buf = C.create_string_buffer(64)

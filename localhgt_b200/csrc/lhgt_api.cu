@@ -1298,6 +1298,20 @@ extern "C" int lhgt_count_table_copy(lhgt_ctx* c, uint8_t* dst) {
     return 0;
 }
 
+extern "C" int lhgt_count_table_histogram(lhgt_ctx* c, uint64_t* out4) {
+    if (!c || !out4) return fail(LHGT_E_ARG, "null pointer");
+    CU(cudaSetDevice(c->device));
+    unsigned long long h[4] = {0, 0, 0, 0};
+    CU(cudaMemsetAsync(c->d_counter, 0, 4 * sizeof(unsigned long long), c->st));
+    c->launches += launch_count_histogram(c->d_count, c->count_words, c->d_counter, c->st);
+    CU(cudaMemcpyAsync(h, c->d_counter, sizeof h, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    CU(cudaMemsetAsync(c->d_counter, 0, 4 * sizeof(unsigned long long), c->st));
+    out4[1] = h[1]; out4[2] = h[2]; out4[3] = h[3];
+    out4[0] = (1ull << c->k) - h[1] - h[2] - h[3];
+    return 0;
+}
+
 extern "C" long lhgt_peaks_copy(lhgt_ctx* c, int32_t* loci, uint8_t* filter, long cap) {
     if (!c) return fail(LHGT_E_ARG, "null ctx");
     if (c->n_peaks < 0) return fail(LHGT_E_STATE, "run S2 first");

@@ -1793,6 +1793,29 @@ __global__ void count_merge_kernel(uint32_t* __restrict__ count, const uint32_t*
         count[i] = sat_add2(count[i], other[i]);
 }
 
+// how many counters hold 0, 1, 2, 3 (the occupancy figures of src/count_diff_kmer.cpp:26-50: empty = [0], weak = [0]+[1]+[2])
+__global__ void count_histogram_kernel(const uint32_t* __restrict__ count, uint64_t words, unsigned long long* __restrict__ out4) {
+    unsigned long long n1 = 0, n2 = 0, n3 = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t w = count[i], lo = w & 0x55555555u, hi = (w >> 1) & 0x55555555u;
+        n1 += __popc(lo & ~hi); n2 += __popc(~lo & hi); n3 += __popc(lo & hi);
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        n1 += __shfl_xor_sync(kFull, n1, d); n2 += __shfl_xor_sync(kFull, n2, d); n3 += __shfl_xor_sync(kFull, n3, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (n1) atomicAdd(out4 + 1, n1);
+        if (n2) atomicAdd(out4 + 2, n2);
+        if (n3) atomicAdd(out4 + 3, n3);
+    }
+}
+
+int launch_count_histogram(const uint32_t* count, uint64_t words, unsigned long long* out4, cudaStream_t st) {
+    count_histogram_kernel<<<kSMs * 8, 256, 0, st>>>(count, words, out4);
+    return 1;
+}
+
 int launch_count_merge(uint32_t* count, const uint32_t* other, uint64_t words, cudaStream_t st) {
     count_merge_kernel<<<kSMs * 8, 256, 0, st>>>(count, other, words);
     return 1;

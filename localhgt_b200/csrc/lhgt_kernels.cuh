@@ -152,6 +152,8 @@ int s3_warps_per_block();
 int launch_sample_bits(const uint32_t* m, uint64_t n, uint32_t m_star, uint32_t* bits, uint64_t words, cudaStream_t st);
 int launch_count_unpack(const uint32_t* count, uint64_t entries, const HashP& hp, uint8_t* out, cudaStream_t st);
 int launch_count_merge(uint32_t* count, const uint32_t* other, uint64_t words, cudaStream_t st);
+// out4[1..3] += number of counters equal to 1, 2, 3 (out4 zeroed by the caller; [0] follows from the table size)
+int launch_count_histogram(const uint32_t* count, uint64_t words, unsigned long long* out4, cudaStream_t st);
 
 constexpr int kMaxPeers = 8;           // GPUs of one box
 struct PeerTables { uint32_t* table[kMaxPeers]; };   // every rank's count table, own included, as mapped in this process

@@ -461,3 +461,21 @@ def test_large_run_matches_reference_binary_on_this_box(big, tmp_path):
     assert fixtures.sha256(fa_r + ".k32.h3.index.dat") == fixtures.sha256(fa_g + ".k32.h3.index.dat")
     assert _read(fa_r + ".genome.len.txt") == _read(fa_g + ".genome.len.txt")
     assert _read(os.path.join(d, "r.txt")) == _read(os.path.join(d, "g.txt"))
+
+
+@pytest.mark.parametrize("k", [3, 20, 24])
+def test_count_table_histogram(k, workdir):
+    """the occupancy diagnostic of count_diff_kmer.cpp as a reduction over the packed table."""
+    rng = np.random.default_rng(k)
+    fq = os.path.join(workdir, f"hist_{k}.fq")
+    n = _low_complexity_fastq(fq, rng, n_random=1500)
+    raw = _read(fq)
+    with api.Screen(k, 3) as s:
+        h0 = s.count_table_histogram()
+        assert h0.tolist() == [1 << k, 0, 0, 0]
+        s.reads_upload(0, raw)
+        s.set_sampling(100.0, 1, 0)
+        assert s.s1_count(0, len(raw)) == n
+        want = np.bincount(s.count_table(), minlength=4)
+        assert s.count_table_histogram().tolist() == want.tolist()
+        assert want[3] > 0
