@@ -479,3 +479,53 @@ def test_count_table_histogram(k, workdir):
         want = np.bincount(s.count_table(), minlength=4)
         assert s.count_table_histogram().tolist() == want.tolist()
         assert want[3] > 0
+
+
+def test_ordinal_base_makes_shards_equal_the_whole_sample(workdir):
+    """The multi-GPU plan gives every rank a record range and the ordinal of its first record (multi.Shard.screen);
+    with a sampling ratio below 100 % the sampled subset must be the whole run's.  One GPU, two shards fed one after
+    the other into the same table: counts, sampled-read totals and the S3 verdicts must match the unsharded run."""
+    case = fixtures.BY_NAME["half_build"]
+    fa, fq1, fq2 = fixtures.materialize(case.data, workdir)
+    k, e, seed, ratio = 20, 3, 7, 37.5
+    b1, b2 = _read(fq1), _read(fq2)
+    cc, skip = api.random_coder(seed, k, e)
+
+    def cut(buf, n_rec):
+        pos = 0
+        for _ in range(4 * n_rec):
+            pos = buf.index(b"\n", pos) + 1
+        return buf[:pos], buf[pos:]
+
+    n_rec = b1.count(b"\n") // 4
+    first = n_rec * 3 // 7
+    a1, z1 = cut(b1, first)
+    a2, z2 = cut(b2, first)
+    with api.Screen(k, e) as whole, api.Screen(k, e) as parts:
+        for s in (whole, parts):
+            s.set_coder(cc)
+            s.index_build(_read(fa))
+        whole.reads_upload(0, b1); whole.reads_upload(1, b2)
+        whole.set_sampling(ratio, seed, skip)
+        n_whole = (whole.s1_count(0, len(b1)), whole.s1_count(1, len(b1)))
+        assert 0 < n_whole[0] < n_rec
+        got = [0, 0]
+        for base, (m1, m2) in ((0, (a1, a2)), (first, (z1, z2))):
+            parts.reads_upload(0, m1); parts.reads_upload(1, m2)
+            parts.set_ordinal_base(base)
+            parts.set_sampling(ratio, seed, skip)
+            got[0] += parts.s1_count(0, len(b1)); got[1] += parts.s1_count(1, len(b1))
+        assert tuple(got) == n_whole
+        assert np.array_equal(whole.count_table(), parts.count_table())
+        assert whole.s2_peaks(case.hit, case.match, case.max_peak) == parts.s2_peaks(case.hit, case.match, case.max_peak)
+        # S3 on the second shard only sees its own pairs; OR-ing the verdicts of both shards gives the whole run's
+        n3_whole = whole.s3_pairs()
+        _, f_whole = whole.peaks()
+        n3 = parts.s3_pairs()                                    # second shard is resident, base = first
+        _, f_b = parts.peaks()
+        parts.reads_upload(0, a1); parts.reads_upload(1, a2)
+        parts.set_ordinal_base(0); parts.set_sampling(ratio, seed, skip)
+        n3 += parts.s3_pairs()
+        _, f_ab = parts.peaks()                                  # the filter accumulates across s3 calls
+        assert n3 == n3_whole
+        assert np.array_equal(f_whole >= 1, f_ab >= 1) and not np.any((f_b >= 1) & ~(f_ab >= 1))
