@@ -143,19 +143,26 @@ class Shard:
         tab = self.eng.table()
         n = tab.numel()
         w = self.world
-        if n % (4 * w):
-            raise ValueError("count table does not split into word-aligned slices")
-        chunk = n // w
-        recv = self.torch.empty_like(tab)
-        self.dist.all_to_all_single(recv, tab)                 # recv[j] = rank j's slice `rank`
+        if n % 4:
+            raise ValueError("count table is not a whole number of 32-bit words")
+        # slice j (whole words; the slices differ by at most one word when w does not divide the table) belongs to rank j
+        spans = [tuple(4 * x for x in split_range(n // 4, w, j)) for j in range(w)]
+        sizes = [hi - lo for lo, hi in spans]
+        lo, mine_n = spans[self.rank][0], sizes[self.rank]
+        recv = self.torch.empty(w * mine_n, dtype=tab.dtype, device=tab.device)
+        self.dist.all_to_all_single(recv, tab, output_split_sizes=[mine_n] * w, input_split_sizes=sizes)   # recv[j] = rank j's slice `rank`
         self._fence(recv)
-        lo = self.rank * chunk
         for j in range(w):
-            if j != self.rank:
-                self.eng.merge_into(lo, recv[j * chunk:(j + 1) * chunk])
+            if j != self.rank and mine_n:
+                self.eng.merge_into(lo, recv[j * mine_n:(j + 1) * mine_n])
         self.eng.sync()
-        mine = tab[lo:lo + chunk].clone()
-        self.dist.all_gather_into_tensor(tab, mine)
+        if w & (w - 1) == 0 and len(set(sizes)) == 1:
+            mine = tab[lo:lo + mine_n].clone()
+            self.dist.all_gather_into_tensor(tab, mine)
+        else:                                                  # uneven slices: one broadcast per owner
+            for j, (a, b) in enumerate(spans):
+                if b > a:
+                    self.dist.broadcast(tab[a:b], src=j)
         self._fence(tab)
 
     def exchange_hit_bits(self, ntiles: int) -> None:

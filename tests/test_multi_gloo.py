@@ -103,15 +103,8 @@ def _worker(rank, world, port, shards, index_path, workdir, out):
         dist.destroy_process_group()
 
 
-def _split_fastq(src, n_first, a, b):
-    with open(src, "rb") as f:
-        lines = f.readlines()
-    open(a, "wb").write(b"".join(lines[: 4 * n_first]))
-    open(b, "wb").write(b"".join(lines[4 * n_first:]))
-
-
-@pytest.mark.parametrize("data", ["base", "fq2long"])
-def test_two_rank_shards_equal_one_run(data, tmp_path):
+@pytest.mark.parametrize("data,world", [("base", 2), ("fq2long", 2), ("base", 3)])
+def test_rank_shards_equal_one_run(data, world, tmp_path):
     work = str(tmp_path)
     fa, fq1, fq2 = fixtures.materialize(data, work)
     idx, lenp = os.path.join(work, "ref.index.dat"), os.path.join(work, "ref.len.txt")
@@ -126,22 +119,25 @@ def test_two_rank_shards_equal_one_run(data, tmp_path):
     o.write_intervals(whole)
     want = open(whole, "rb").read()
     assert n_peaks > 10
-    # two unequal shards
+    # unequal shards, in record order
     n_rec = sum(1 for _ in open(fq1, "rb")) // 4
-    first = n_rec * 2 // 5
+    cuts = [0] + [n_rec * (2 * r + 2) // (2 * world + 1) for r in range(world - 1)] + [n_rec]
+    lines1, lines2 = open(fq1, "rb").readlines(), open(fq2, "rb").readlines()
     shards = []
-    for r in range(2):
-        shards.append((os.path.join(work, f"s{r}.1.fq"), os.path.join(work, f"s{r}.2.fq")))
-    _split_fastq(fq1, first, shards[0][0], shards[1][0])
-    _split_fastq(fq2, first, shards[0][1], shards[1][1])
+    for r in range(world):
+        a, b = os.path.join(work, f"s{r}.1.fq"), os.path.join(work, f"s{r}.2.fq")
+        hi1 = len(lines1) if r == world - 1 else 4 * cuts[r + 1]
+        hi2 = len(lines2) if r == world - 1 else 4 * cuts[r + 1]
+        open(a, "wb").write(b"".join(lines1[4 * cuts[r]:hi1]))
+        open(b, "wb").write(b"".join(lines2[4 * cuts[r]:hi2]))
+        shards.append((a, b))
     out = os.path.join(work, "sharded.txt")
-    mp.spawn(_worker, args=(2, _free_port(), shards, idx, work, out), nprocs=2, join=True)
-    got0, got1 = open(out + ".0", "rb").read(), open(out + ".1", "rb").read()
-    assert got0 == got1 == want
-    peaks0, counts0 = eval(open(out + ".0.meta").read())
-    peaks1, counts1 = eval(open(out + ".1.meta").read())
-    assert peaks0 == peaks1 == n_peaks
-    assert counts0["ordinal_base"] == 0 and counts1["ordinal_base"] == first
+    mp.spawn(_worker, args=(world, _free_port(), shards, idx, work, out), nprocs=world, join=True)
+    texts = [open(out + f".{r}", "rb").read() for r in range(world)]
+    assert all(t == want for t in texts)
+    metas = [eval(open(out + f".{r}.meta").read()) for r in range(world)]
+    assert all(m[0] == n_peaks for m in metas)
+    assert [m[1]["ordinal_base"] for m in metas] == cuts[:-1]
 
 
 def test_split_range_covers_everything():
