@@ -976,8 +976,8 @@ static int check_err_flag(lhgt_ctx* c, int* flag) {
     return 0;
 }
 
-// S1 plan: tables beyond this size are counted through hash streams so that each table slice is L2-resident
-// while it is updated; smaller tables are probed directly (they sit in L2 anyway).
+// S1 plan: tables beyond this size are counted through hash streams (the hashes are partitioned until each partition's
+// table slice fits in shared memory); smaller tables are probed directly -- they sit in L2 anyway.
 static const uint64_t kSliceBytes = (uint64_t)64 << 20;
 
 extern "C" int lhgt_set_s1_mode(lhgt_ctx* c, int mode) {
