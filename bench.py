@@ -1,25 +1,29 @@
 #!/usr/bin/env python
 """bench.py — read pairs/s through the k-mer screen + peak extract (and index build Gbp/s) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|small]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg4|cfg3|cfg2|mini]
 
 A step = one pass of the hot path (LocalHGT extract_ref: FASTQ record location, S1 count of both mates,
 S2 window/peak detection over the resident index, S3 pair confirmation, interval text) over one batch =
-the whole synthetic sample of the workload.  Workload `cfg2` is BASELINE.json configs[1]: a synthetic
-20-species-style reference (40 x 2 Mbp: 20 recipients + 20 absent donors, ~80 Mbp) and 5 M simulated
-150 bp read pairs with planted transfers, k=32 e=3, LocalHGT's default arguments.
+the whole synthetic sample of the workload.  The default workload is `cfg4`, the configuration BASELINE.json's
+target is quoted on (configs[3]): a 5 Gbp synthetic reference (2 000 x 2.5 Mbp, half recipients, half absent
+donors) and 30 M simulated 150 bp read pairs with planted transfers, k=32 e=3, LocalHGT's default arguments
+(`--sample 2e9` => 22.2 % of the pairs are sampled).  It fits one B200 (index image 60 GB).  `cfg3` is configs[2]
+(1 Gbp, 10 M pairs), `cfg2` configs[1] (80 Mbp, 5 M pairs, every pair sampled), `mini` a 1/100 cfg4 for quick checks.
 
-  value      pairs/s with the FASTQ bytes and the index already resident in HBM (CUDA events, max over ranks)
-  e2e        the same metric through the C ABI with HOST (pinned) buffers: FASTQ + index image are copied
-             host->device and the interval text comes back device->host inside the timed region
+  value      input pairs/s with the FASTQ bytes and the index already resident in HBM (CUDA events, max over ranks)
+  e2e        the same metric through the C ABI with HOST (pinned) buffers: both FASTQ images and the reference FASTA are
+             copied host->device inside the timed region (the 60 GB index image is re-built from the 5 GB of FASTA on the
+             device instead of crossing PCIe) and the interval text comes back device->host
   roofline   the dominant kernel against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
-  cpu_baseline  the UNMODIFIED reference binary (oracle/_ref/extract_ref) on this box's host cores, on a
-             bounded sample of the same workload
+  cpu_baseline  the UNMODIFIED reference binary (oracle/_ref/extract_ref) on this box's host cores, on a bounded,
+             self-consistent 1/f scale model of the workload (pairs and contigs), extrapolated linearly and said so
   --impl reference   times only that reference binary (no code of ours on its path)
 
-N > 1 (torchrun): read pairs are partitioned across ranks (each rank screens its own n_pairs: weak
-scaling), the index is replicated, count tables are combined with an all-to-all + all-gather of table
-slices, S2's table gather is sharded over reference tiles, S3's verdicts are max-reduced.
+N > 1 (torchrun): STRONG scaling -- the one sample is split N ways by record ranges (rank r screens pairs [lo_r, hi_r)),
+the index is replicated, count tables are combined over NVLink peer memory, S2's table gather is sharded over reference
+tiles, S3's verdicts are max-reduced.  The result is the N = 1 result bit for bit; rank 0 checks that once, outside the
+timed region, by screening the whole sample alone.
 """
 from __future__ import annotations
 
@@ -48,27 +52,39 @@ READ_LEN = 150
 P = READ_LEN - K + 1
 SECTOR = 32                                                             # bytes per random probe
 
+# name: (n_genomes, genome_len, n_pairs, n_events).  cfg2 is made by the numpy generator (files on disk, so that the
+# unmodified reference could be run on the very same bytes: KNOWN_ANSWERS); the others by the counter-based torch
+# generator (localhgt_b200/synth_dev.py), on the GPU, sliceable by pair range.
 WORKLOADS = {
-    # name: (n_genomes, genome_len, n_pairs, n_events)
     "cfg2": (40, 2_000_000, 5_000_000, 40),
-    "cfg3": (500, 2_000_000, 10_000_000, 200),                          # 1 Gbp reference, 10 M pairs (BASELINE.json configs[2])
+    "cfg3": (500, 2_000_000, 10_000_000, 200),                          # BASELINE.json configs[2]
+    "cfg4": (2000, 2_500_000, 30_000_000, 400),                         # BASELINE.json configs[3]: the headline
+    "mini": (20, 2_500_000, 300_000, 4),
     "small": (8, 500_000, 200_000, 6),
 }
+FILE_WORKLOADS = ("cfg2", "small")
+# sha256 of the interval text the UNMODIFIED reference (oracle/_ref/extract_ref_z, -t 1) wrote for the workload's files
+KNOWN_ANSWERS = {}
 
 
 def _rank_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 
+def split_range(n: int, parts: int, i: int):
+    base, extra = divmod(n, parts)
+    lo = i * base + min(i, extra)
+    return lo, lo + base + (1 if i < extra else 0)
+
+
 # ---------------------------------------------------------------------------------------------- workload
-def workload_dir(name: str, shard: int) -> str:
+def workload_dir(name: str, shard: int = 0) -> str:
     base = os.environ.get("LHGT_BENCH_DIR", os.path.join(tempfile.gettempdir(), "lhgt_bench"))
     return os.path.join(base, f"{name}_s{shard}")
 
 
 def make_workload(name: str, shard: int = 0):
-    """Generates (or reuses) the synthetic files of one rank's shard.  Shards share the reference
-    (same seed) and differ in the read seed."""
+    """File workloads (numpy generator): generates (or reuses) the synthetic files."""
     from localhgt_b200 import synth
     n_genomes, genome_len, n_pairs, n_events = WORKLOADS[name]
     d = workload_dir(name, shard)
@@ -91,6 +107,70 @@ def make_workload(name: str, shard: int = 0):
             "truth": [[t.recipient, t.r_pos] for t in truth]}
     json.dump(meta, open(meta_path, "w"))
     return fa, fq1, fq2, meta
+
+
+def spec_of(name: str, scale: int = 1):
+    """synth_dev.Spec of a generated workload; scale = f gives its self-consistent 1/f model (pairs, contigs, events)."""
+    from localhgt_b200 import synth_dev
+    n_genomes, genome_len, n_pairs, n_events = WORKLOADS[name]
+    return synth_dev.Spec(name if scale == 1 else f"{name}/{scale}", max(4, n_genomes // scale), genome_len, max(1000, n_pairs // scale),
+                          max(2, n_events // scale), seed={"cfg3": 3, "cfg4": 4, "mini": 4}.get(name, 9))
+
+
+class Workload:
+    """What one rank needs of a workload: the reference FASTA and ITS record range of the one sample, as device tensors."""
+
+    def __init__(self, name: str, rank: int, world: int, torch, device):
+        self.name, self.torch, self.device = name, torch, device
+        if name in FILE_WORKLOADS:
+            fa, fq1, fq2, meta = make_workload(name, 0)
+            self.files = (fa, fq1, fq2)
+            self.n_pairs, self.ref_bases, self.n_contigs = meta["n_pairs"], meta["ref_bases"], meta["n_contigs"]
+            # meta's recipient index counts the 20-bp contig that follows g2; the interval file's ordinal does not (Q2)
+            self.truth = [(rec + 1 if rec < 3 else rec, pos) for rec, pos in meta["truth"]]
+            self.lo, self.hi = split_range(self.n_pairs, world, rank)
+            self._fa = np.fromfile(fa, dtype=np.uint8)
+            with open(fq1, "rb") as f:
+                self.stride = len(f.readline() + f.readline() + f.readline() + f.readline())
+            self.spec = None
+        else:
+            from localhgt_b200 import synth_dev
+            self.spec = spec_of(name)
+            self.n_pairs, self.ref_bases, self.n_contigs = self.spec.n_pairs, self.spec.ref_bases, self.spec.n_contigs
+            self.truth = synth_dev.truth_positions(self.spec)
+            self.lo, self.hi = split_range(self.n_pairs, world, rank)
+            self.stride = self.spec.record_bytes
+            self.files = None
+
+    def _padded(self, n):
+        return self.torch.empty(n + 64, dtype=self.torch.uint8, device=self.device)[:n]      # the kernels stage whole 16-byte granules
+
+    def fasta_dev(self):
+        if self.spec is None:
+            t = self._padded(self._fa.size)
+            t.copy_(self.torch.from_numpy(self._fa))
+            return t
+        from localhgt_b200 import synth_dev
+        layout, total = synth_dev.fasta_layout(self.spec)
+        t = self._padded(total)
+        t.copy_(synth_dev.make_fasta(self.spec, self.device))
+        return t
+
+    def reads_dev(self, lo=None, hi=None):
+        lo = self.lo if lo is None else lo
+        hi = self.hi if hi is None else hi
+        n = (hi - lo) * self.stride
+        d1, d2 = self._padded(n), self._padded(n)
+        if self.spec is None:
+            for path, d in ((self.files[1], d1), (self.files[2], d2)):
+                a = np.fromfile(path, dtype=np.uint8, count=n, offset=lo * self.stride)
+                d.copy_(self.torch.from_numpy(a))
+        else:
+            from localhgt_b200 import synth_dev
+            cat, offs = synth_dev.sample_genomes(self.spec, self.device)
+            synth_dev.make_pairs(self.spec, cat, offs, lo, hi, d1, d2)
+            del cat
+        return d1, d2
 
 
 def head_records(src: str, dst: str, n_records: int) -> None:
@@ -192,9 +272,9 @@ def ref_binary() -> str:
     return orc.REF_BIN
 
 
-def run_reference_once(exe, fq1, fq2, fa, out, threads):
+def run_reference_once(exe, fq1, fq2, fa, out, threads, sample=SAMPLE):
     argv = [exe, fq1, fq2, fa, out, repr(HIT), repr(MATCH), str(threads), str(K), str(MAX_PEAK), str(E), str(SEED),
-            repr(SAMPLE)]
+            repr(float(sample))]
     t = time.perf_counter()
     r = subprocess.run(argv, capture_output=True, text=True)
     dt = time.perf_counter() - t
@@ -203,20 +283,96 @@ def run_reference_once(exe, fq1, fq2, fa, out, threads):
     return dt, r.stdout
 
 
-def reference_sample(name: str, sample_pairs: int):
-    """Bounded sample: the first sample_pairs records of shard 0 + the FULL reference (symlinked so the
-    reference's side files <ref>.k32.h3.index.dat / <ref>.genome.len.txt land in the sample's own directory)."""
-    fa, fq1, fq2, meta = make_workload(name, 0)
-    d = os.path.join(workload_dir(name, 0), f"cpu_{sample_pairs}")
-    os.makedirs(d, exist_ok=True)
-    s1, s2, sfa = os.path.join(d, "s.1.fq"), os.path.join(d, "s.2.fq"), os.path.join(d, "ref.fa")
-    n = min(sample_pairs, meta["n_pairs"])
-    if not os.path.exists(s2):
-        head_records(fq1, s1, n); head_records(fq2, s2, n)
-    if not os.path.lexists(sfa):
-        os.symlink(fa, sfa)
-    idx = f"{sfa}.k{K}.h{E}.index.dat"
-    return s1, s2, sfa, idx, n, meta
+def sampled_fraction(n_pairs: int) -> float:
+    """E:1392-1398 with fixed-length reads: ratio = sample / (2 * bases of fq1)."""
+    return min(1.0, SAMPLE / (2.0 * READ_LEN * n_pairs))
+
+
+class CpuModel:
+    """The bounded sample the reference binary is timed on, and the linear model that scales it to the full workload.
+
+    CPU cost is linear in sampled pairs and in reference bases:
+        T(run) = fixed + c_base * R + c_pair * sampled_pairs
+    File workloads (cfg2): the first n pairs of the very files + the full reference (R is not scaled; it sits in `fixed`).
+    Generated workloads (cfg3/cfg4): a self-consistent scale model from the same generator -- a `small` reference of 4
+    contigs with `n` pairs drawn from ITS recipients (same read model, same sampled fraction, passed as a fraction so that
+    the smaller file does not change it), and a `big` reference of 40 contigs that is only slid (S2) to measure c_base.
+    """
+
+    def __init__(self, name: str, n_pairs: int):
+        self.name, self.n = name, n_pairs
+        self.full_pairs = WORKLOADS[name][2]
+        self.full_bases = WORKLOADS[name][0] * WORKLOADS[name][1]
+        self.frac = sampled_fraction(self.full_pairs)
+        self.dir = os.path.join(workload_dir(name, 0), f"cpu_{n_pairs}")
+        os.makedirs(self.dir, exist_ok=True)
+        j = lambda x: os.path.join(self.dir, x)
+        self.fq = (j("s.1.fq"), j("s.2.fq"))
+        self.tiny = (j("tiny.1.fq"), j("tiny.2.fq"))
+        self.small_fa, self.big_fa = j("small.fa"), j("big.fa")
+        self.generated = name not in FILE_WORKLOADS
+        if self.generated:
+            self._generate()
+            self.sample_arg = self.frac if self.frac < 1 else SAMPLE
+        else:
+            fa, fq1, fq2, meta = make_workload(name, 0)
+            self.n = min(self.n, meta["n_pairs"])
+            if not os.path.exists(self.fq[1]):
+                head_records(fq1, self.fq[0], self.n); head_records(fq2, self.fq[1], self.n)
+            for link in (self.small_fa,):
+                if not os.path.lexists(link):
+                    os.symlink(fa, link)
+            self.big_fa = None
+            self.small_bases, self.big_bases = meta["ref_bases"], 0
+            self.sample_arg = SAMPLE
+        if not os.path.exists(self.tiny[1]):
+            head_records(self.fq[0], self.tiny[0], 4); head_records(self.fq[1], self.tiny[1], 4)
+
+    def _generate(self):
+        import torch
+        from localhgt_b200 import synth_dev
+        g, L, _, _ = WORKLOADS[self.name]
+        seed = spec_of(self.name).seed
+        small = synth_dev.Spec(self.name + "/model", 4, L, self.n, 2, seed=seed)
+        big = synth_dev.Spec(self.name + "/model-big", min(g, 40), L, 1000, 2, seed=seed)
+        self.small_bases, self.big_bases = small.ref_bases, big.ref_bases
+        if not os.path.exists(self.small_fa):
+            synth_dev.make_fasta(small, "cpu").numpy().tofile(self.small_fa)
+        if not os.path.exists(self.big_fa):
+            synth_dev.make_fasta(big, "cpu").numpy().tofile(self.big_fa)
+        if not os.path.exists(self.fq[1]):
+            cat, offs = synth_dev.sample_genomes(small, "cpu")
+            o1 = torch.empty(self.n * small.record_bytes, dtype=torch.uint8); o2 = torch.empty_like(o1)
+            synth_dev.make_pairs(small, cat, offs, 0, self.n, o1, o2, chunk=1 << 16)
+            o1.numpy().tofile(self.fq[0]); o2.numpy().tofile(self.fq[1])
+
+    @staticmethod
+    def index_of(fa):
+        return f"{fa}.k{K}.h{E}.index.dat"
+
+    def describe(self, cores):
+        if self.generated:
+            return (f"scale model of {self.name}: {self.n} pairs ({self.frac:.4f} of them sampled, as in the full workload) from the recipients of a "
+                    f"{self.small_bases} bp / 4-contig reference made by the same generator, S2 cost per base from sliding a {self.big_bases} bp / "
+                    f"40-contig reference; unmodified reference binary -t {cores}, index files present; value = full workload "
+                    f"({self.full_pairs} pairs, {self.full_bases} bp) under T = fixed + c_base*R + c_pair*sampled_pairs fitted to these runs")
+        return (f"first {self.n} of {self.full_pairs} pairs of the workload's own files, full {self.small_bases} bp reference, unmodified reference "
+                f"binary -t {cores}, index file present; value = full workload under T = fixed + c_pair*pairs fitted to these runs")
+
+    def estimate(self, t_tiny_small, t_pairs_small, t_tiny_big=None):
+        """Returns (pairs/s of the full workload, model dict)."""
+        sampled_model = self.n * (self.frac if self.generated else 1.0)
+        c_pair = max(t_pairs_small - t_tiny_small, 1e-9) / sampled_model
+        if self.generated and t_tiny_big is not None:
+            c_base = max(t_tiny_big - t_tiny_small, 0.0) / max(self.big_bases - self.small_bases, 1)
+            fixed = max(t_tiny_small - c_base * self.small_bases, 0.0)
+            total = fixed + c_base * self.full_bases + c_pair * self.frac * self.full_pairs
+        else:
+            c_base, fixed = None, t_tiny_small
+            total = fixed + c_pair * self.full_pairs
+        return self.full_pairs / total, {"fixed_s": fixed, "c_base_s_per_base": c_base, "c_pair_s_per_sampled_pair": c_pair,
+                                         "full_workload_seconds": total, "t_tiny_small": t_tiny_small, "t_pairs_small": t_pairs_small,
+                                         "t_tiny_big": t_tiny_big}
 
 
 def reference_arm(args) -> None:
@@ -230,53 +386,54 @@ def reference_arm(args) -> None:
         print(json.dumps({"impl": "reference", "unavailable": str(ex)[:200]}))
         return
     steps, warm = args.steps, args.warmup
-    sample_pairs = args.ref_pairs or (400_000 if steps + warm <= 3 else 200_000 if steps + warm <= 6 else 100_000)
-    s1, s2, sfa, idx, n, meta = reference_sample(args.workload, sample_pairs)
-    out = os.path.join(os.path.dirname(s1), "ref.interval.txt")
+    n = args.ref_pairs or (400_000 if steps + warm <= 3 else 200_000 if steps + warm <= 6 else 100_000)
+    m = CpuModel(args.workload, n)
+    out = os.path.join(m.dir, "ref.interval.txt")
+    # the reference builds its own indexes (single-threaded by construction, E:1409): timed as its IB figure
     ib = None
-    if not os.path.exists(idx):
-        # the reference builds its own index (single-threaded by construction, E:1409); timed as its IB figure
-        tiny1 = os.path.join(os.path.dirname(s1), "tiny.1.fq"); tiny2 = os.path.join(os.path.dirname(s1), "tiny.2.fq")
-        head_records(s1, tiny1, 4); head_records(s2, tiny2, 4)
-        t_build, _ = run_reference_once(exe, tiny1, tiny2, sfa, out + ".ib", cores)
-        t_reuse, _ = run_reference_once(exe, tiny1, tiny2, sfa, out + ".ib", cores)
-        ib = {"gbp_per_s": meta["ref_bases"] / 1e9 / max(t_build - t_reuse, 1e-9), "seconds": t_build - t_reuse,
-              "bases": meta["ref_bases"], "fixed_seconds_per_run": t_reuse, "threads": 1,
-              "how": "wall(first run, builds index) - wall(second run, reuses it), 4 read pairs"}
+    t_build = None
+    if not os.path.exists(m.index_of(m.small_fa)):
+        t_build, _ = run_reference_once(exe, *m.tiny, m.small_fa, out + ".ib", cores, m.sample_arg)
+    t_tiny_small, _ = run_reference_once(exe, *m.tiny, m.small_fa, out + ".ib", cores, m.sample_arg)
+    if t_build is not None:
+        ib = {"gbp_per_s": m.small_bases / 1e9 / max(t_build - t_tiny_small, 1e-9), "seconds": t_build - t_tiny_small, "bases": m.small_bases,
+              "threads": 1, "how": "wall(run that builds the index) - wall(run that reuses it), 4 read pairs"}
+    t_tiny_big = None
+    if m.generated:
+        if not os.path.exists(m.index_of(m.big_fa)):
+            run_reference_once(exe, *m.tiny, m.big_fa, out + ".ib", cores, m.sample_arg)
+        t_tiny_big, _ = run_reference_once(exe, *m.tiny, m.big_fa, out + ".ib", cores, m.sample_arg)
     times = []
     for i in range(warm + steps):
-        dt, _ = run_reference_once(exe, s1, s2, sfa, out, cores)
+        dt, _ = run_reference_once(exe, *m.fq, m.small_fa, out, cores, m.sample_arg)
         if i >= warm:
             times.append(dt)
     total = sum(times)
-    value = n * steps / total
+    value, model = m.estimate(t_tiny_small, total / steps, t_tiny_big)
     line = {
         "impl": "reference", "metric": "read pairs/sec through k-mer screen+peak extract", "value": value, "unit": "pairs/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1000 * total / steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": config_dict(args.workload, meta, args.gpus),
-        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "reference",
-                         "sample": f"first {n} of {meta['n_pairs']} pairs per step, full {meta['ref_bases']} bp reference, "
-                                   f"-t {cores}, index file present; one process per step, wall clock incl. its fixed table setup"},
+        "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": config_dict(args.workload),
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "reference", "sample": m.describe(cores), "model": model,
+                         "measured_on_sample": {"pairs_per_s": m.n / (total / steps), "seconds_per_step": total / steps}},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     if ib:
         line["index_build"] = ib
-        fixed = ib["fixed_seconds_per_run"]
-        per_pair = max(total / steps - fixed, 1e-9) / n
-        line["full_workload_estimate"] = {"value": meta["n_pairs"] / (fixed + per_pair * meta["n_pairs"]), "unit": "pairs/s",
-                                          "how": "fixed + per-pair linear model from this run's own timings"}
     print(json.dumps(line))
 
 
-def config_dict(name, meta, n_gpus):
-    return {"workload": f"{name}: synthetic {meta['n_contigs']}-contig reference ({meta['ref_bases']} bp) + {meta['n_pairs']} "
-                        f"simulated {READ_LEN} bp read pairs per GPU with planted HGT breakpoints",
+def config_dict(name):
+    g, L, n_pairs, _ = WORKLOADS[name]
+    frac = sampled_fraction(n_pairs)
+    return {"workload": f"{name}: synthetic {g} x {L} bp reference ({g * L} bp) + ONE sample of {n_pairs} simulated {READ_LEN} bp read pairs "
+                        f"with planted HGT breakpoints ({frac:.4f} of the pairs sampled by --sample 2e9); N GPUs split the sample N ways",
             "k": K, "e": E, "seed": SEED, "hit_ratio": HIT, "match_ratio": MATCH, "sample": SAMPLE, "max_peak": MAX_PEAK,
-            "pairs_per_gpu": meta["n_pairs"], "ref_bases": meta["ref_bases"], "parallelism": f"pairs-sharded x{n_gpus}, index replicated",
-            "l2": "inputs larger than L2: FASTQ images %.1f GB, count table 1 GiB, peak table 16 GiB" %
-                  (meta["n_pairs"] * 2 * 331 / 1e9)}
+            "pairs": n_pairs, "ref_bases": g * L, "sampled_fraction": frac,
+            "l2": "inputs larger than L2 (no flush needed): FASTQ images %.1f GB, index image %.1f GB, count table 1 GiB, peak table 16 GiB" %
+                  (n_pairs * 2 * 318 / 1e9, g * L * 4 * E / 1e9)}
 
 
 # ---------------------------------------------------------------------------------------------- our arm
@@ -288,71 +445,66 @@ def ours(args) -> None:
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (liblhgt has no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    fa, fq1, fq2, meta = make_workload(args.workload, rank)
-    n_pairs = meta["n_pairs"]
-    b1 = np.fromfile(fq1, dtype=np.uint8); b2 = np.fromfile(fq2, dtype=np.uint8)
-    fasta = np.fromfile(fa, dtype=np.uint8)
+        dist.init_process_group("nccl", device_id=dev)
+    t_setup = time.perf_counter()
+    wl = Workload(args.workload, rank, world, torch, dev)
+    d_fa = wl.fasta_dev()
+    d1, d2 = wl.reads_dev()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    gen_s = time.perf_counter() - t_setup
 
     stream = torch.cuda.Stream()
     scr = api.Screen(K, E, device=local_rank)
     cc, skip = api.random_coder(SEED, K, E)
     scr.set_coder(cc)
     scr.set_s1_mode(args.s1_mode)
+    size1_total = wl.n_pairs * wl.stride                                   # E:1419: size(fq1) of the whole sample (Q15 budget)
 
     with torch.cuda.stream(stream):
         scr.set_stream(stream.cuda_stream)
-        # ---- index build (the IB half of the metric): kernel time and host->host time
-        ib_ms_kernel, ib_ms_e2e = [], []
-        scr.index_build(fasta)
-        image = scr.index_download()                                   # the image the e2e steps upload again
-        scr.stage_ms()
-        pinned_image = torch.empty(image.size, dtype=torch.uint8).pin_memory()
+        # ---- index build (the IB half of the metric): kernel time, and FASTA-on-device -> image-on-device time
+        ib_ms_kernel, ib_ms_dev = [], []
         for i in range(3):
+            torch.cuda.synchronize()
             t = time.perf_counter()
-            scr.index_build(fasta)
-            scr.index_download_ptr(pinned_image.data_ptr(), pinned_image.numel())
-            ib_ms_e2e.append(1000 * (time.perf_counter() - t))
+            scr.index_build_device(d_fa.data_ptr(), d_fa.numel())
+            scr.sync()
+            ib_ms_dev.append(1000 * (time.perf_counter() - t))
             ib_ms_kernel.append(float(scr.stage_ms()[5]))
-            scr.reset()
-        assert bytes(pinned_image.numpy()[:4096]) == bytes(image[:4096]) and bytes(pinned_image.numpy()[-4096:]) == bytes(image[-4096:])
-        del pinned_image
-        index_bases = scr.index_bases()
+        index_bases, index_bytes = scr.index_bases(), scr.index_bytes()
         index_build = {"gbp_per_s": index_bases / 1e6 / min(ib_ms_kernel), "kernel_ms": min(ib_ms_kernel),
-                       "e2e_gbp_per_s": index_bases / 1e6 / min(ib_ms_e2e), "e2e_ms": min(ib_ms_e2e), "bases": index_bases,
-                       "index_bytes": int(image.size), "e2e_how": "host FASTA bytes -> header scan on the host, H2D, sequence compaction + hashing on the device -> D2H index image (pinned)",
+                       "device_gbp_per_s": index_bases / 1e6 / min(ib_ms_dev), "device_ms": min(ib_ms_dev), "bases": index_bases,
+                       "index_bytes": int(index_bytes),
+                       "device_how": "FASTA text resident in HBM -> header scan, sequence compaction, hashing -> index image resident in HBM (wall clock of lhgt_index_build_device)",
                        "roofline": {"bound": "hbm", "achieved": index_bases * (1 + 4 * E) / 1e6 / min(ib_ms_kernel),
                                     "unit": "GB/s", "bytes_per_base": 1 + 4 * E}}
 
-        # ---- resident inputs for `value`; pinned host copies for `e2e`
-        d1 = torch.from_numpy(b1).cuda(non_blocking=False); d2 = torch.from_numpy(b2).cuda(non_blocking=False)
-        h1 = torch.from_numpy(b1).pin_memory(); h2 = torch.from_numpy(b2).pin_memory()
-        himg = torch.from_numpy(image).pin_memory()
-        del image
-
         shard = multi.Shard(scr, rank, world, dist, torch)
+        solo = multi.Shard(scr, 0, 1, None, torch) if world > 1 else shard
 
         def step_resident():
             scr.reads_attach_device(0, d1.data_ptr(), d1.numel())
             scr.reads_attach_device(1, d2.data_ptr(), d2.numel())
-            return shard.screen(size1=d1.numel(), sample_arg=SAMPLE, seed=SEED, rand_skip=0, hit=HIT, match=MATCH,
-                                max_peak=MAX_PEAK)
+            return shard.screen(size1=d1.numel(), sample_arg=SAMPLE, seed=SEED, rand_skip=0, hit=HIT, match=MATCH, max_peak=MAX_PEAK)
 
-        def step_e2e():
-            # all three host->device copies are queued on the copy stream up front, in the order the stages need them;
-            # each stage adopts its input when it gets there (fq2 lands behind S1 of fq1, the index behind S1 of fq2)
-            scr.reads_prefetch_ptr(0, h1.data_ptr(), h1.numel())
-            scr.reads_prefetch_ptr(1, h2.data_ptr(), h2.numel())
-            scr.index_prefetch_ptr(himg.data_ptr(), himg.numel())
-            scr.reads_upload_ptr(0, h1.data_ptr(), h1.numel())
-            return shard.screen(size1=h1.numel(), size2=h2.numel(), sample_arg=SAMPLE, seed=SEED, rand_skip=0, hit=HIT, match=MATCH,
-                                max_peak=MAX_PEAK,
-                                before_mate2=lambda: scr.reads_upload_ptr(1, h2.data_ptr(), h2.numel()),
-                                before_s2=lambda: scr.index_upload_ptr(himg.data_ptr(), himg.numel()))
+        # ---- N > 1: the answer of the sharded run must be the answer of the whole sample on one GPU
+        text_whole = None
+        if world > 1:
+            text_sharded = step_resident()
+            if rank == 0 and not args.no_whole_check:
+                w1, w2 = wl.reads_dev(0, wl.n_pairs)
+                scr.reads_attach_device(0, w1.data_ptr(), w1.numel()); scr.reads_attach_device(1, w2.data_ptr(), w2.numel())
+                text_whole = solo.screen(size1=w1.numel(), sample_arg=SAMPLE, seed=SEED, rand_skip=0, hit=HIT, match=MATCH, max_peak=MAX_PEAK)
+                del w1, w2
+                torch.cuda.empty_cache()
+                assert text_whole == text_sharded, "the sharded screen and the single-GPU screen of the same sample disagree"
+            dist.barrier()
 
         def timed(fn, steps, warm, sampler=None):
             for _ in range(warm):
@@ -386,6 +538,40 @@ def ours(args) -> None:
         ms, res, stage, launches, clocks = timed(step_resident, args.steps, args.warmup, sampler)
         text_resident = res
         wall_resident = dict(shard.last_wall_ms)
+        counts_resident = dict(shard.last_counts)
+
+        # ---- e2e: host (pinned) FASTQ + FASTA -> result.  The resident copies go first (HBM budget at cfg4).
+        h1 = torch.empty(d1.numel(), dtype=torch.uint8, pin_memory=True); h1.copy_(d1)
+        h2 = torch.empty(d2.numel(), dtype=torch.uint8, pin_memory=True); h2.copy_(d2)
+        hfa = torch.empty(d_fa.numel(), dtype=torch.uint8, pin_memory=True); hfa.copy_(d_fa)
+        torch.cuda.synchronize()
+        n1, n2, nfa = d1.numel(), d2.numel(), d_fa.numel()
+        del d1, d2, d_fa
+        torch.cuda.empty_cache()
+        fa_bcast = torch.empty(nfa + 64, dtype=torch.uint8, device=dev)[:nfa] if world > 1 else None
+
+        def build_index_e2e():
+            if world == 1:
+                scr.index_build_ptr(hfa.data_ptr(), nfa)                # adopts the prefetch issued at the top of the step
+                return
+            # the FASTA crosses PCIe once per box: rank 0 uploads it, NVLink carries it to the others
+            if rank == 0:
+                fa_bcast.copy_(hfa, non_blocking=True)
+            dist.broadcast(fa_bcast, src=0)
+            torch.cuda.current_stream().synchronize()
+            scr.index_build_device(fa_bcast.data_ptr(), nfa)
+
+        def step_e2e():
+            # the host->device copies are queued on the copy stream up front, in the order the stages need them; each stage
+            # adopts its input when it gets there (fq2 lands behind S1 of fq1, the FASTA behind S1 of fq2)
+            scr.reads_prefetch_ptr(0, h1.data_ptr(), n1)
+            scr.reads_prefetch_ptr(1, h2.data_ptr(), n2)
+            if world == 1:
+                scr.fasta_prefetch_ptr(hfa.data_ptr(), nfa)
+            scr.reads_upload_ptr(0, h1.data_ptr(), n1)
+            return shard.screen(size1=n1, size2=n2, sample_arg=SAMPLE, seed=SEED, rand_skip=0, hit=HIT, match=MATCH, max_peak=MAX_PEAK,
+                                before_mate2=lambda: scr.reads_upload_ptr(1, h2.data_ptr(), n2), before_s2=build_index_e2e)
+
         ms_e2e, res_e2e, stage_e2e, _, _ = timed(step_e2e, args.steps, max(1, min(args.warmup, 2)))
         assert res_e2e == text_resident, "resident and host-buffer passes disagree"
 
@@ -395,40 +581,51 @@ def ours(args) -> None:
             dist.destroy_process_group()
         return
 
-    total_pairs = n_pairs * world
-    value = total_pairs * args.steps / (ms / 1000)
-    e2e_value = total_pairs * args.steps / (ms_e2e / 1000)
+    sha = hashlib.sha256(text_resident).hexdigest()
+    known = KNOWN_ANSWERS.get(args.workload)
+    if known:
+        assert sha == known, f"interval text of {args.workload} differs from the unmodified reference's ({sha} != {known})"
+    value = wl.n_pairs * args.steps / (ms / 1000)
+    e2e_value = wl.n_pairs * args.steps / (ms_e2e / 1000)
     peak, peak_src = measured_peak_gbs()
     names = ["fastq_record_scan", "s1_count", "s2_gather", "s2_finish", "s3_pairs", "index_build", "exchange", "host_setup",
              "s1_hash_streams", "s1_split_streams", "s1_apply_leaves"]
     stage_ms = {nm: round(float(v), 3) for nm, v in zip(names, stage)}
-    roofline = make_roofline(stage, n_pairs, meta, peak, peak_src, b1.size + b2.size, args)
+    frac = sampled_fraction(wl.n_pairs)
+    roofline = make_roofline(stage, wl, frac, world, peak, peak_src, n1 + n2)
     roofline["stage_ms_per_step"] = stage_ms
+    h2d = n1 + n2 + (nfa if rank == 0 else 0)
     line = {
         "metric": "read pairs/sec through k-mer screen+peak extract", "value": value, "unit": "pairs/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": dict(config_dict(args.workload, meta, world),
-                       count_exchange=("one kernel over NVLink peer memory (CUDA IPC)" if shard.p2p else "NCCL all-to-all + merge + all-gather")
-                       if world > 1 else "none (1 GPU)"),
+        "config": config_dict(args.workload),
+        "parallelism": {"plan": f"one sample split {world} ways by record ranges, index replicated" if world > 1 else "1 GPU",
+                        "count_exchange": ("one kernel over NVLink peer memory (CUDA IPC)" if shard.p2p else "NCCL all-to-all + merge + all-gather")
+                        if world > 1 else "none",
+                        "whole_sample_check": ("rank 0 screened the whole sample alone: identical text" if text_whole is not None else
+                                               "skipped" if world > 1 else "n/a")},
+        "sampled_pairs_per_s": {"value": frac * value, "e2e": frac * e2e_value, "sampled_fraction": frac},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "pairs/s", "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": int(h1.numel() + h2.numel() + himg.numel()), "d2h_bytes_per_step": len(text_resident) + 64,
-                "pcie_gbs": (h1.numel() + h2.numel() + himg.numel()) / 1e6 / (ms_e2e / args.steps),
-                "what": "pinned host FASTQ x2 + index image -> HBM (copy stream, overlapping S1) -> S1,S2,S3 -> interval text on host, "
-                        "through the C ABI; every byte crosses PCIe inside the timed region.  The step is bound by that copy "
-                        "(`pcie_gbs` = h2d bytes / step time; running two samples back to back on two contexts was measured "
-                        "and is no faster, profiles/README.md r01j)"},
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": len(text_resident) + 64,
+                "pcie_gbs": h2d / 1e6 / (ms_e2e / args.steps),
+                "what": "pinned host FASTQ x2 + reference FASTA -> HBM (copy stream, overlapping S1) -> index image re-built on the device -> S1,S2,S3 "
+                        "-> interval text on host, through the C ABI; every input byte crosses PCIe inside the timed region (rank 0's figure; "
+                        "at N > 1 the FASTA crosses PCIe once and is broadcast over NVLink)",
+                "stage_ms_per_step": {nm: round(float(v), 3) for nm, v in zip(names, stage_e2e)}},
         "gpu_launches": int(launches), "roofline": roofline, "index_build": index_build,
-        "result": {"interval_lines": len(text_resident.splitlines()), "interval_sha256": hashlib.sha256(text_resident).hexdigest()[:16],
-                   "planted_recovered": recovered(text_resident, meta), "peaks": shard.last_peaks,
-                   "sampled": shard.last_counts},
+        "result": {"interval_lines": len(text_resident.splitlines()), "interval_sha256": sha,
+                   "matches_unmodified_reference": bool(known) or None,
+                   "planted_recovered": recovered(text_resident, wl.truth), "peaks": shard.last_peaks,
+                   "sampled": counts_resident},
         "host_wall_ms_last_step": {k: round(v, 3) for k, v in shard.last_wall_ms.items()},
         "host_wall_ms_last_resident_step": {k: round(v, 3) for k, v in wall_resident.items()},
+        "setup_seconds": {"generate_inputs": round(gen_s, 2)},
     }
     if world == 1 and not args.no_cpu:
         try:
-            line["cpu_baseline"] = cpu_baseline(args, scr, fa)
+            line["cpu_baseline"] = cpu_baseline(args, scr)
         except Exception as ex:
             line["cpu_baseline"] = {"value": None, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "reference",
                                     "sample": "failed: " + str(ex)[:200]}
@@ -438,33 +635,35 @@ def ours(args) -> None:
         dist.destroy_process_group()
 
 
-def make_roofline(stage, n_pairs, meta, peak, peak_src, fastq_bytes, args):
-    """Roofline of the dominant kernel (by device time inside the timed region), against the measured HBM copy bandwidth.
+def make_roofline(stage, wl, frac, world, peak, peak_src, fastq_bytes):
+    """Roofline of the dominant kernel (by device time inside the timed region, rank 0), against the measured HBM copy bandwidth.
 
     Algorithmic bytes.  SURVEY §8(d) counts a table probe as one 32-byte DRAM sector:
-      S1 direct  : sampled reads x P x e probes x 32 B, one launch per mate
+      S1         : sampled reads x P x e probes x 32 B, one launch (set) per mate
       S3         : sampled pairs x 2 x P x e probes x 32 B
       S2 gather  : reference bases x (4e stored-hash bytes + 32e)
     With hash streams S1 is three kernels whose own DRAM bytes are different (that is the point of the design):
-      s1_bin_kernel   : FASTQ bytes read + 4 B per hash written
+      s1_bin_kernel   : sampled FASTQ bytes read + 4 B per hash written
       s1_split_kernel : 4 B per hash read + 4 B per hash written
       s1_leaf_kernel  : 4 B per hash read + the 2^k x 2 bit table read and written back once
-    one launch each per mate.  For those the figure under the 32 B/probe convention is reported next to it as
-    `probe_convention`; it can exceed the HBM peak because no probe goes to DRAM.
+    For those the figure under the 32 B/probe convention is reported next to it as `probe_convention`; it can exceed the
+    HBM peak because no probe goes to DRAM.  Units are this rank's share (pairs / world, tiles / world).
     """
-    probes_per_mate = n_pairs * P * E                                   # s = 1 on this workload (ratio >= 100 %)
+    pairs_rank = wl.n_pairs / world
+    probes_per_mate = pairs_rank * frac * P * E
+    ref_share = wl.ref_bases / world
     traffic = load_traffic()
     kernels = {}
     streams = stage[8] > 0 or stage[9] > 0 or stage[10] > 0
     if streams:
         table_bytes = (1 << K) // 4
-        kernels["s1_bin_kernel<3>"] = (stage[8] / 2, fastq_bytes / 2 + 4 * probes_per_mate, probes_per_mate * SECTOR)
+        kernels["s1_bin_kernel<3>"] = (stage[8] / 2, fastq_bytes * frac / 2 + 4 * probes_per_mate, probes_per_mate * SECTOR)
         kernels["s1_split_kernel"] = (stage[9] / 2, 8 * probes_per_mate, probes_per_mate * SECTOR)
         kernels["s1_leaf_kernel"] = (stage[10] / 2, 4 * probes_per_mate + 2 * table_bytes, probes_per_mate * SECTOR)
     else:
         kernels["s1_count_kernel<3>"] = (stage[1] / 2, probes_per_mate * SECTOR, probes_per_mate * SECTOR)
     kernels["s3_pairs_kernel<3>"] = (stage[4], 2 * probes_per_mate * SECTOR, 2 * probes_per_mate * SECTOR)
-    kernels["s2_gather_kernel<3>"] = (stage[2], meta["ref_bases"] * (E * SECTOR + 4 * E), meta["ref_bases"] * (E * SECTOR + 4 * E))
+    kernels["s2_gather_kernel<3>"] = (stage[2], ref_share * (E * SECTOR + 4 * E), ref_share * (E * SECTOR + 4 * E))
     share = {"s1_bin_kernel<3>": stage[8], "s1_split_kernel": stage[9], "s1_leaf_kernel": stage[10], "s1_count_kernel<3>": stage[1],
              "s3_pairs_kernel<3>": stage[4], "s2_gather_kernel<3>": stage[2]}
     dom = max(kernels, key=lambda k: share[k])
@@ -476,12 +675,14 @@ def make_roofline(stage, n_pairs, meta, peak, peak_src, fastq_bytes, args):
                          "achieved": nbytes / 1e6 / ms, "frac": nbytes / 1e6 / ms / peak,
                          "probe_convention": {"bytes_per_launch": int(conv), "achieved": conv / 1e6 / ms, "frac": conv / 1e6 / ms / peak}}
     d = per_kernel[dom]
-    s1_conv = 2 * probes_per_mate * SECTOR / 1e6 / max(stage[1], 1e-9)
+    device_ms = float(stage[0] + stage[1] + stage[2] + stage[3] + stage[4])
+    whole_bytes = pairs_rank * frac * 2 * 2 * P * E * SECTOR + ref_share * (E * SECTOR + 4 * E)
     return {"bound": "hbm", "kernel": dom, "achieved": d["achieved"], "peak": peak, "unit": "GB/s", "frac": d["frac"],
             "traffic": (traffic or {}).get(dom), "peak_source": peak_src, "algorithmic_bytes_per_launch": d["algorithmic_bytes_per_launch"],
             "ms_per_launch": d["ms_per_launch"], "kernels": per_kernel,
-            "s1_stage_probe_convention": {"achieved": s1_conv, "frac": s1_conv / peak, "unit": "GB/s",
-                                          "what": "S1 as a whole at SURVEY 8(d)'s 32 B per probe: 2 mates x reads x P x e x 32 B / S1 device time"},
+            "whole_step": {"algorithmic_bytes": int(whole_bytes), "device_ms": device_ms, "achieved": whole_bytes / 1e6 / max(device_ms, 1e-9),
+                           "frac": whole_bytes / 1e6 / max(device_ms, 1e-9) / peak,
+                           "what": "SURVEY 8(d): sampled pairs x 45 696 B + reference bases x 108 B over the summed device time of the step's stages"},
             "s1_mode": "hash streams (two-level split, table slices updated in shared memory)" if streams else "direct probes"}
 
 
@@ -497,49 +698,41 @@ def load_traffic():
     return None
 
 
-def recovered(text: bytes, meta) -> str:
+def recovered(text: bytes, truth) -> str:
     """Planted recipient junctions strictly inside an emitted interval with 50 bp margin (paper_results/evaluation.py:64-76)."""
-    ivs = [tuple(map(int, ln.split(b"\t"))) for ln in text.splitlines()]
-    # contig ordinals in the interval file count indexed contigs only (Q2); the workload's one short contig sits after g2
-    found = 0
-    for rec, pos in meta["truth"]:
-        ordinal = rec + 1 if rec < 3 else rec   # meta's index counts the 20-bp contig that follows g2; the interval file does not (Q2)
-        found += any(c == ordinal and a + 50 < pos < b - 50 for c, a, b in ivs)
-    return f"{found}/{len(meta['truth'])}"
+    by_contig = {}
+    for ln in text.splitlines():
+        c, a, b = map(int, ln.split(b"\t"))
+        by_contig.setdefault(c, []).append((a, b))
+    found = sum(any(a + 50 < pos < b - 50 for a, b in by_contig.get(ordinal, ())) for ordinal, pos in truth)
+    return f"{found}/{len(truth)}"
 
 
-def cpu_baseline(args, scr, fa):
-    """Times the unmodified reference binary on a bounded sample (rank 0, N=1)."""
+def cpu_baseline(args, scr):
+    """Times the unmodified reference binary on a bounded sample (rank 0, N=1) and scales it with CpuModel."""
     exe = ref_binary()
     cores = os.cpu_count() or 1
-    n_want = args.ref_pairs or 200_000
-    # index file: the bit-identical image our IB produced (tests/ prove the equality); the reference 'detects' and reuses it
-    s1, s2, sfa, idx, n, meta = reference_sample(args.workload, n_want)
-    if not os.path.exists(idx):
-        scr.index_build_file(fa, idx, sfa + ".genome.len.txt")
-    out = os.path.join(os.path.dirname(s1), "cpu.interval.txt")
-    dt, log = run_reference_once(exe, s1, s2, sfa, out, cores)
-    res = {"value": n / dt, "unit": "pairs/s", "cores": cores, "kind": "reference", "seconds": dt,
-           "sample": f"first {n} of {meta['n_pairs']} pairs, full {meta['ref_bases']} bp reference, unmodified reference binary "
-                     f"-t {cores}, index file present (built by our IB, bit-identical); wall clock of the whole process"}
-    # IB on a bounded reference sample: first 4 contigs
-    d = os.path.dirname(s1)
-    fa4 = os.path.join(d, "ref4.fa")
-    bases = head_contigs(fa, fa4, 4)
-    for f in os.listdir(d):
-        if f.startswith("ref4.fa."):
-            os.remove(os.path.join(d, f))
-    tiny1, tiny2 = os.path.join(d, "tiny.1.fq"), os.path.join(d, "tiny.2.fq")
-    head_records(s1, tiny1, 4); head_records(s2, tiny2, 4)
-    t_build, _ = run_reference_once(exe, tiny1, tiny2, fa4, out + ".ib", cores)
-    t_reuse, _ = run_reference_once(exe, tiny1, tiny2, fa4, out + ".ib", cores)
-    res["index_build"] = {"gbp_per_s": bases / 1e9 / max(t_build - t_reuse, 1e-9), "bases": bases, "threads": 1,
-                          "fixed_seconds_per_run": t_reuse,
-                          "how": "wall(run that builds the index) - wall(run that reuses it), first 4 contigs"}
-    fixed = t_reuse
-    per_pair = max(dt - fixed, 1e-9) / n
-    res["full_workload_estimate"] = {"value": meta["n_pairs"] / (fixed + per_pair * meta["n_pairs"]), "unit": "pairs/s",
-                                     "how": "fixed + per-pair linear model from the two timings above"}
+    m = CpuModel(args.workload, args.ref_pairs or 200_000)
+    out = os.path.join(m.dir, "cpu.interval.txt")
+    # index files: the bit-identical images our IB writes (tests/ prove the equality); the reference 'detects' and reuses them
+    ib = None
+    small_idx = m.index_of(m.small_fa)
+    if m.generated and not os.path.exists(small_idx):                     # the small reference: let the reference build it once = its IB figure
+        t_build, _ = run_reference_once(exe, *m.tiny, m.small_fa, out + ".ib", cores, m.sample_arg)
+        t_reuse, _ = run_reference_once(exe, *m.tiny, m.small_fa, out + ".ib", cores, m.sample_arg)
+        ib = {"gbp_per_s": m.small_bases / 1e9 / max(t_build - t_reuse, 1e-9), "bases": m.small_bases, "threads": 1,
+              "how": "wall(run that builds the index) - wall(run that reuses it), 4 read pairs"}
+    for fa in (m.small_fa, m.big_fa):
+        if fa and not os.path.exists(m.index_of(fa)):
+            scr.index_build_file(fa, m.index_of(fa), fa + ".genome.len.txt")
+    t_tiny_small, _ = run_reference_once(exe, *m.tiny, m.small_fa, out, cores, m.sample_arg)
+    t_pairs_small, _ = run_reference_once(exe, *m.fq, m.small_fa, out, cores, m.sample_arg)
+    t_tiny_big = run_reference_once(exe, *m.tiny, m.big_fa, out, cores, m.sample_arg)[0] if m.generated else None
+    value, model = m.estimate(t_tiny_small, t_pairs_small, t_tiny_big)
+    res = {"value": value, "unit": "pairs/s", "cores": cores, "kind": "reference", "sample": m.describe(cores), "model": model,
+           "measured_on_sample": {"pairs_per_s": m.n / t_pairs_small, "seconds": t_pairs_small}}
+    if ib:
+        res["index_build"] = ib
     return res
 
 
@@ -549,9 +742,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--ref-pairs", type=int, default=0, help="pairs in the CPU reference's bounded sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-whole-check", action="store_true", help="N > 1: skip rank 0's single-GPU screen of the whole sample")
     ap.add_argument("--s1-mode", type=int, default=0, help="0 auto (hash streams for tables > 64 MiB), 1 direct probes, 2 streams")
     args = ap.parse_args()
     _, _, world = _rank_env()

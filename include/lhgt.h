@@ -85,11 +85,22 @@ int lhgt_hash_seq(lhgt_ctx* c, const uint8_t* ascii, size_t n, uint32_t* out, ui
 /* Builds the index image in HBM from FASTA text held in host memory.  The image is byte-identical
  * to <ref>.k<k>.h<e>.index.dat.  genome.len.txt text is returned through lhgt_index_len_text(). */
 int      lhgt_index_build(lhgt_ctx* c, const uint8_t* fasta, size_t n);
+/* The same from FASTA text that already lives on this device (16-byte aligned; the caller keeps it alive during the
+ * call).  The whole of read_ref's line loop (E:761-831) runs on the device either way: header lines are found,
+ * sequence bytes compacted and contig lengths derived there, with 64-bit offsets (a 5 Gbp reference is a 5.06 GB file). */
+int      lhgt_index_build_device(lhgt_ctx* c, const void* dev_fasta, size_t n);
+/* Starts the host->device copy of FASTA text on the copy stream; a later lhgt_index_build with the SAME pointer and
+ * size adopts it (see lhgt_reads_prefetch).  A context that was given a prefetch keeps its FASTA buffer between builds:
+ * re-building a 60 GB image from 5 GB of FASTA per sample is cheaper than shipping the image over PCIe. */
+int      lhgt_fasta_prefetch(lhgt_ctx* c, const uint8_t* fasta, size_t n);
 uint64_t lhgt_index_bytes(const lhgt_ctx* c);
 uint64_t lhgt_index_bases(const lhgt_ctx* c);            /* sum of indexed contig lengths */
 long     lhgt_index_contigs(const lhgt_ctx* c);
 int      lhgt_index_download(lhgt_ctx* c, uint8_t* dst, uint64_t cap);
 int      lhgt_index_len_text(const lhgt_ctx* c, char* dst, size_t cap, size_t* n);
+/* One record of the resident image (E:921-931: u32 len, then (len-k+1)*e hashes) by its ordinal among the indexed
+ * contigs; dst = NULL returns the number of 32-bit words. */
+long     lhgt_index_record(lhgt_ctx* c, long record, uint32_t* dst, uint64_t cap_words);
 /* Makes an existing image HBM-resident (read_index's input, E:888-979) and adopts its coder
  * (E:1417).  lhgt_index_attach_device uses an image that already lives on this device. */
 int      lhgt_index_upload(lhgt_ctx* c, const uint8_t* image, uint64_t n);

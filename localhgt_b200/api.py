@@ -56,11 +56,14 @@ SYMBOLS = {
     "lhgt_sync": (_i, [_vp]),
     "lhgt_hash_seq": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "lhgt_index_build": (_i, [_vp, _vp, _sz]),
+    "lhgt_index_build_device": (_i, [_vp, _vp, _sz]),
+    "lhgt_fasta_prefetch": (_i, [_vp, _vp, _sz]),
     "lhgt_index_bytes": (_u64, [_vp]),
     "lhgt_index_bases": (_u64, [_vp]),
     "lhgt_index_contigs": (_l, [_vp]),
     "lhgt_index_download": (_i, [_vp, _vp, _u64]),
     "lhgt_index_len_text": (_i, [_vp, _vp, _sz, C.POINTER(_sz)]),
+    "lhgt_index_record": (_l, [_vp, _l, _vp, _u64]),
     "lhgt_index_upload": (_i, [_vp, _vp, _u64]),
     "lhgt_index_build_file": (_i, [_vp, _s, _s, _s]),
     "lhgt_index_load_file": (_i, [_vp, _s]),
@@ -222,6 +225,16 @@ class Screen:
         buf = np.frombuffer(fasta, dtype=np.uint8)
         _check(self._L.lhgt_index_build(self._h, _ptr(buf) if len(buf) else None, len(buf)))
 
+    def index_build_ptr(self, host_ptr: int, n: int) -> None:
+        _check(self._L.lhgt_index_build(self._h, host_ptr, n))
+
+    def index_build_device(self, dev_ptr: int, n: int) -> None:
+        """FASTA text already resident on this device (16-byte aligned)."""
+        _check(self._L.lhgt_index_build_device(self._h, dev_ptr, n))
+
+    def fasta_prefetch_ptr(self, host_ptr: int, n: int) -> None:
+        _check(self._L.lhgt_fasta_prefetch(self._h, host_ptr, n))
+
     def index_bytes(self) -> int: return int(self._L.lhgt_index_bytes(self._h))
     def index_bases(self) -> int: return int(self._L.lhgt_index_bases(self._h))
     def index_contigs(self) -> int: return int(self._L.lhgt_index_contigs(self._h))
@@ -241,6 +254,13 @@ class Screen:
         buf = C.create_string_buffer(max(1, n.value))
         _check(self._L.lhgt_index_len_text(self._h, buf, n.value, C.byref(n)))
         return buf.raw[: n.value]
+
+    def index_record(self, record: int) -> np.ndarray:
+        """[len, hashes...] of one indexed contig, from the resident image."""
+        n = _check(self._L.lhgt_index_record(self._h, record, None, 0))
+        out = np.zeros(n, dtype=np.uint32)
+        _check(self._L.lhgt_index_record(self._h, record, _ptr(out), n))
+        return out
 
     def index_upload(self, image) -> None:
         buf = np.frombuffer(image, dtype=np.uint8)

@@ -120,7 +120,8 @@ struct lhgt_ctx {
     cudaStream_t own = nullptr, st = nullptr;
     cudaStream_t copy_st = nullptr;              // host->device prefetches run here, beside the kernels on `st`
     struct Prefetch { const void* host = nullptr; uint64_t n = 0; cudaEvent_t done = nullptr; bool active = false; };
-    Prefetch pf_reads[2], pf_index;
+    Prefetch pf_reads[2], pf_index, pf_fasta;
+    DevBuf<uint8_t> fasta_buf; bool keep_fasta_buf = false;   // raw FASTA bytes of lhgt_index_build (kept when prefetched: a context that re-builds per sample)
 
     uint32_t* d_count = nullptr; uint64_t count_words = 0;
     uint32_t* d_peak_kmer = nullptr;
@@ -165,6 +166,9 @@ struct lhgt_ctx {
     std::vector<TimedSpan> spans;
     long launches = 0;
 };
+
+static int start_prefetch(lhgt_ctx* c, lhgt_ctx::Prefetch& p, void* dst, const void* host, uint64_t n);
+static bool adopt_prefetch(lhgt_ctx* c, lhgt_ctx::Prefetch& p, const void* host, uint64_t n);
 
 static void make_hashp(lhgt_ctx* c) {
     HashP& hp = c->hp;
@@ -356,9 +360,10 @@ extern "C" void lhgt_destroy(lhgt_ctx* c) {
     c->rand_m_buf.release(); delete c->rand_gen;
     dev_free(c->d_cands); dev_free(c->d_tally); dev_free(c->d_vote_table); dev_free(c->d_counter); dev_free(c->d_err);
     dev_free(c->d_bin_pool_a); dev_free(c->d_bin_pool_b); dev_free(c->d_bin_cursor);
+    c->fasta_buf.release();
     peers_close(c);
     if (c->copy_st) { cudaStreamSynchronize(c->copy_st); cudaStreamDestroy(c->copy_st); }
-    for (lhgt_ctx::Prefetch* p : {&c->pf_reads[0], &c->pf_reads[1], &c->pf_index}) if (p->done) cudaEventDestroy(p->done);
+    for (lhgt_ctx::Prefetch* p : {&c->pf_reads[0], &c->pf_reads[1], &c->pf_index, &c->pf_fasta}) if (p->done) cudaEventDestroy(p->done);
     if (c->own) cudaStreamDestroy(c->own);
     delete c;
 }
@@ -431,51 +436,9 @@ static size_t read_id_len(const uint8_t* s, size_t n) {
 }
 
 struct ParsedFasta {
-    std::vector<uint8_t> seq;          // indexed contigs only, back to back
-    std::vector<Contig> contigs;
+    std::vector<Contig> contigs;       // indexed contigs only; seq_off = offset in the compacted sequence buffer
     std::string len_text;
 };
-
-// The getline loop of read_ref (E:761-831 + the tail E:833-880) without the hashing.
-static void parse_fasta(const uint8_t* fa, size_t n, int k, int e, ParsedFasta& out) {
-    out.seq.reserve(n);
-    std::string name = "start";                               // E:747
-    long ordinal = 0, cumulative = 0;
-    size_t cur_begin = 0;                                     // start of the current contig inside out.seq
-    uint64_t word = LHGT_CODER_SLOTS;
-    auto close_contig = [&]() {
-        size_t len = out.seq.size() - cur_begin;
-        cumulative += (long)len;
-        if (len > (size_t)k) {                                // E:772, 836
-            char buf[96];
-            snprintf(buf, sizeof buf, "\t%ld\t%zu\t%ld\n", ordinal, len, cumulative);
-            out.len_text += name; out.len_text += buf;
-            Contig c{};
-            c.hash_word = word + 1; c.seq_off = cur_begin; c.len = (uint32_t)len; c.tile0 = 0;
-            out.contigs.push_back(c);
-            word += 1 + (uint64_t)(len - k + 1) * e;
-            cur_begin = out.seq.size();
-        } else {
-            out.seq.resize(cur_begin);                        // skipped contig leaves no bytes behind
-        }
-    };
-    size_t pos = 0;
-    while (pos < n) {
-        const uint8_t* nl = (const uint8_t*)memchr(fa + pos, '\n', n - pos);
-        size_t end = nl ? (size_t)(nl - fa) : n;
-        size_t len = end - pos;
-        if (len > 0 && fa[pos] == '>') {
-            close_contig();
-            ++ordinal;                                        // E:825: every header counts (Q2)
-            size_t idl = read_id_len(fa + pos, len);
-            name.assign((const char*)fa + pos + 1, idl > 0 ? idl - 1 : 0);   // E:764
-        } else if (len) {
-            out.seq.insert(out.seq.end(), fa + pos, fa + end);
-        }
-        pos = nl ? end + 1 : n;
-    }
-    close_contig();
-}
 
 static int alloc_image(lhgt_ctx* c, uint64_t words) {
     int rc = c->image_buf.reserve(words);
@@ -484,49 +447,63 @@ static int alloc_image(lhgt_ctx* c, uint64_t words) {
     return 0;
 }
 
-// The same loop with the sequence bytes left where they are: the host only finds the header lines (few) and the
-// device compacts the rest (launch_fasta_compact).  Fills `pf.contigs` / `pf.len_text`; the compacted bytes end up in
-// *d_seq (caller frees).  Used for files whose sequence-byte count fits the 32-bit tile scan.
-static int ingest_fasta_device(lhgt_ctx* c, const uint8_t* fa, size_t n, ParsedFasta& pf, uint8_t** d_seq) {
-    std::vector<ByteSpan> spans;
-    std::vector<std::string> names;
-    for (size_t pos = 0; pos < n;) {
-        const uint8_t* gt = (const uint8_t*)memchr(fa + pos, '>', n - pos);
-        if (!gt) break;
-        size_t at = (size_t)(gt - fa);
-        if (at && fa[at - 1] != '\n') { pos = at + 1; continue; }                // a '>' inside a line is a (bad) base
-        const uint8_t* nl = (const uint8_t*)memchr(gt, '\n', n - at);
-        size_t end = nl ? (size_t)(nl - fa) : n;                                  // header text is [at, end)
-        size_t idl = read_id_len(gt, end - at);
-        names.emplace_back((const char*)gt + 1, idl > 0 ? idl - 1 : 0);           // E:764
-        spans.push_back({(uint64_t)at, (uint64_t)(nl ? end : n - 1)});
-        pos = nl ? end + 1 : n;
-    }
-    const uint32_t ns = (uint32_t)spans.size();
-    uint64_t tiles = fastq_index_tiles(n);
-    std::vector<uint64_t> q(ns + 1), before(ns + 1, 0);
-    for (uint32_t i = 0; i < ns; ++i) q[i] = spans[i].lo;
-    q[ns] = n;
-    uint8_t* d_fa = nullptr; ByteSpan* d_spans = nullptr; uint64_t *d_q = nullptr, *d_before = nullptr;
-    uint32_t *d_cnt = nullptr, *d_base = nullptr, *d_tmp = nullptr;
+// read_ref's getline loop (E:761-831 + the tail E:833-880) without the hashing, on the device: the raw file bytes stay
+// where they are (d_fa, n bytes, 16-byte aligned); one kernel finds the header lines, the host sorts their spans and
+// reads their text (names), the device compacts everything else except newlines (launch_fasta_compact) and reports
+// how many sequence bytes precede each header -- which is all the host needs for contig lengths, genome.len.txt and the
+// image layout.  Fills `pf`; the compacted bytes end up in *d_seq (caller frees).  File offsets and sequence counts
+// are 64-bit throughout (a 5 Gbp reference is a 5.06 GB file).
+static int ingest_fasta_device(lhgt_ctx* c, const uint8_t* d_fa, size_t n, ParsedFasta& pf, uint8_t** d_seq) {
     *d_seq = nullptr;
+    uint64_t tiles = fastq_index_tiles(n);
+    ByteSpan* d_spans = nullptr; uint64_t *d_off = nullptr, *d_before = nullptr, *d_cnt = nullptr, *d_base = nullptr, *d_tmp = nullptr;
+    uint8_t* d_text = nullptr;
+    unsigned long long* d_count = nullptr;
+    auto cleanup = [&]() { dev_free(d_spans); dev_free(d_off); dev_free(d_before); dev_free(d_cnt); dev_free(d_base); dev_free(d_tmp); dev_free(d_text); dev_free(d_count); };
     int rc = 0;
-    auto cleanup = [&]() { dev_free(d_fa); dev_free(d_spans); dev_free(d_q); dev_free(d_before); dev_free(d_cnt); dev_free(d_base); dev_free(d_tmp); };
-    if ((rc = dev_alloc(&d_fa, n + 64)) || (rc = dev_alloc(&d_spans, (size_t)ns + 1)) || (rc = dev_alloc(&d_q, (size_t)ns + 1)) ||
-        (rc = dev_alloc(&d_before, (size_t)ns + 1)) || (rc = dev_alloc(&d_cnt, tiles + 1)) || (rc = dev_alloc(&d_base, tiles + 1)) ||
-        (rc = dev_alloc(&d_tmp, scan_tmp_words(tiles))) || (rc = dev_alloc(d_seq, n + 64))) {
-        cleanup();
+    std::vector<ByteSpan> spans;
+    if ((rc = dev_alloc(&d_count, 1))) return rc;
+    for (uint32_t cap = 1u << 16;;) {                                             // header spans, unordered
+        if ((rc = dev_alloc(&d_spans, cap))) { cleanup(); return rc; }
+        unsigned long long found = 0;
+        cudaMemsetAsync(d_count, 0, sizeof found, c->st);
+        c->launches += launch_fasta_headers(d_fa, n, d_spans, cap, d_count, c->st);
+        cudaMemcpyAsync(&found, d_count, sizeof found, cudaMemcpyDeviceToHost, c->st);
+        cudaError_t e0 = cudaStreamSynchronize(c->st);
+        if (e0 != cudaSuccess) { cleanup(); return fail(LHGT_E_CUDA, "FASTA header scan failed: %s", cudaGetErrorString(e0)); }
+        if (found > 0xfffffff0ull) { cleanup(); return fail(LHGT_E_FORMAT, "FASTA holds more than 2^32 header lines"); }
+        if (found <= cap) {
+            spans.resize((size_t)found);
+            if (found && cudaMemcpy(spans.data(), d_spans, (size_t)found * sizeof(ByteSpan), cudaMemcpyDeviceToHost) != cudaSuccess) {
+                cleanup();
+                return fail(LHGT_E_CUDA, "FASTA header download failed");
+            }
+            break;
+        }
+        dev_free(d_spans);
+        cap = (uint32_t)found;
+    }
+    std::sort(spans.begin(), spans.end(), [](const ByteSpan& x, const ByteSpan& y) { return x.lo < y.lo; });
+    const uint32_t ns = (uint32_t)spans.size();
+    std::vector<uint64_t> off(ns + 1, 0), before(ns + 1, 0);
+    for (uint32_t i = 0; i < ns; ++i) off[i + 1] = off[i] + (spans[i].hi - spans[i].lo + 1);   // the newline (or last byte) travels too; trimmed below
+    std::vector<uint8_t> text((size_t)off[ns] + 1);
+    if ((rc = dev_alloc(&d_off, (size_t)ns + 1)) || (rc = dev_alloc(&d_before, (size_t)ns + 1)) || (rc = dev_alloc(&d_cnt, tiles + 1)) ||
+        (rc = dev_alloc(&d_base, tiles + 1)) || (rc = dev_alloc(&d_tmp, scan_tmp_words(tiles))) || (rc = dev_alloc(&d_text, (size_t)off[ns] + 1)) ||
+        (rc = dev_alloc(d_seq, n + 64))) {
+        cleanup(); dev_free(*d_seq);
         return rc;
     }
-    cudaMemcpyAsync(d_fa, fa, n, cudaMemcpyHostToDevice, c->st);
-    if (ns) cudaMemcpyAsync(d_spans, spans.data(), ns * sizeof(ByteSpan), cudaMemcpyHostToDevice, c->st);
-    cudaMemcpyAsync(d_q, q.data(), (ns + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->st);
-    c->launches += launch_fasta_compact(d_fa, n, d_spans, ns, d_cnt, d_base, d_tmp, *d_seq, d_q, ns + 1, d_before, 0, c->st);
-    c->launches += launch_fasta_compact(d_fa, n, d_spans, ns, d_cnt, d_base, d_tmp, *d_seq, d_q, ns + 1, d_before, 1, c->st);
+    if (ns) cudaMemcpyAsync(d_spans, spans.data(), ns * sizeof(ByteSpan), cudaMemcpyHostToDevice, c->st);   // now in file order
+    cudaMemcpyAsync(d_off, off.data(), (ns + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->st);
+    c->launches += launch_fasta_header_text(d_fa, d_spans, ns, d_off, d_text, c->st);
+    c->launches += launch_fasta_compact(d_fa, n, d_spans, ns, d_cnt, d_base, d_tmp, *d_seq, d_before, 0, c->st);
+    c->launches += launch_fasta_compact(d_fa, n, d_spans, ns, d_cnt, d_base, d_tmp, *d_seq, d_before, 1, c->st);
+    if (off[ns]) cudaMemcpyAsync(text.data(), d_text, (size_t)off[ns], cudaMemcpyDeviceToHost, c->st);
     cudaMemcpyAsync(before.data(), d_before, (ns + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->st);
     cudaError_t e1 = cudaStreamSynchronize(c->st);
     cleanup();
-    if (e1 != cudaSuccess) { dev_free(*d_seq); *d_seq = nullptr; return fail(LHGT_E_CUDA, "FASTA compaction failed: %s", cudaGetErrorString(e1)); }
+    if (e1 != cudaSuccess) { dev_free(*d_seq); return fail(LHGT_E_CUDA, "FASTA compaction failed: %s", cudaGetErrorString(e1)); }
     // contig 0 is what precedes the first header (name "start", E:747); contig i >= 1 follows header i
     uint64_t word = LHGT_CODER_SLOTS;
     long cumulative = 0;
@@ -535,12 +512,20 @@ static int ingest_fasta_device(lhgt_ctx* c, const uint8_t* fa, size_t n, ParsedF
         size_t len = (size_t)(hi - lo);
         cumulative += (long)len;
         if (len > (size_t)c->k) {                                                 // E:772, 836
+            std::string name = "start";
+            if (i) {
+                const uint8_t* h = text.data() + off[i - 1];
+                size_t hl = (size_t)(off[i] - off[i - 1]);
+                if (hl && h[hl - 1] == '\n') --hl;                                // header text is the line without its newline
+                size_t idl = read_id_len(h, hl);
+                name.assign((const char*)h + 1, idl > 0 ? idl - 1 : 0);           // E:764
+            }
             char buf[96];
             snprintf(buf, sizeof buf, "\t%ld\t%zu\t%ld\n", (long)i, len, cumulative);
-            pf.len_text += i ? names[i - 1] : std::string("start"); pf.len_text += buf;
+            pf.len_text += name; pf.len_text += buf;
             Contig g{};
             g.hash_word = word + 1; g.seq_off = lo; g.len = (uint32_t)len; g.tile0 = 0;
-            if (len > 178000000u) { dev_free(*d_seq); *d_seq = nullptr; return fail(LHGT_E_FORMAT, "contig longer than the reference's int buffers allow (E:925)"); }
+            if (len > 178000000u) { dev_free(*d_seq); return fail(LHGT_E_FORMAT, "contig longer than the reference's int buffers allow (E:925)"); }
             pf.contigs.push_back(g);
             word += 1 + (uint64_t)(len - c->k + 1) * c->e;
         }
@@ -548,23 +533,13 @@ static int ingest_fasta_device(lhgt_ctx* c, const uint8_t* fa, size_t n, ParsedF
     return 0;
 }
 
-extern "C" int lhgt_index_build(lhgt_ctx* c, const uint8_t* fasta, size_t n) {
-    if (!c || (!fasta && n)) return fail(LHGT_E_ARG, "lhgt_index_build: null pointer");
-    CU(cudaSetDevice(c->device));
+static int index_build_from_device(lhgt_ctx* c, const uint8_t* d_fa, size_t n) {
     if (!coder_ok(c->cc, c->k, c->e)) return fail(LHGT_E_STATE, "set the coder before building an index");
     drop_index(c);
     ParsedFasta pf;
     uint8_t* d_seq = nullptr;
     int rc;
-    if (n > 0 && n < 0xf0000000ull) {
-        if ((rc = ingest_fasta_device(c, fasta, n, pf, &d_seq))) return rc;
-    } else {                                                                      // host getline loop, then one upload
-        parse_fasta(fasta, n, c->k, c->e, pf);
-        for (auto& g : pf.contigs)
-            if (g.len > 178000000u) return fail(LHGT_E_FORMAT, "contig longer than the reference's int buffers allow (E:925)");
-        if ((rc = dev_alloc(&d_seq, pf.seq.size() + 64))) return rc;
-        CU(cudaMemcpyAsync(d_seq, pf.seq.data(), pf.seq.size(), cudaMemcpyHostToDevice, c->st));
-    }
+    if (n) { if ((rc = ingest_fasta_device(c, d_fa, n, pf, &d_seq))) return rc; }
     c->contigs = pf.contigs;
     c->len_text = pf.len_text;
     uint64_t words = LHGT_CODER_SLOTS;
@@ -581,6 +556,33 @@ extern "C" int lhgt_index_build(lhgt_ctx* c, const uint8_t* fasta, size_t n) {
     cudaFree(d_seq);
     if (e1 != cudaSuccess) return fail(LHGT_E_CUDA, "index build kernel failed: %s", cudaGetErrorString(e1));
     return 0;
+}
+
+extern "C" int lhgt_index_build(lhgt_ctx* c, const uint8_t* fasta, size_t n) {
+    if (!c || (!fasta && n)) return fail(LHGT_E_ARG, "lhgt_index_build: null pointer");
+    CU(cudaSetDevice(c->device));
+    int rc = c->fasta_buf.reserve(n + 64);
+    if (rc) return rc;
+    if (n && !adopt_prefetch(c, c->pf_fasta, fasta, n)) CU(cudaMemcpyAsync(c->fasta_buf.p, fasta, n, cudaMemcpyHostToDevice, c->st));
+    rc = index_build_from_device(c, c->fasta_buf.p, n);
+    if (!c->keep_fasta_buf) c->fasta_buf.release();                               // a context that re-builds per sample keeps it
+    return rc;
+}
+
+extern "C" int lhgt_index_build_device(lhgt_ctx* c, const void* dev_fasta, size_t n) {
+    if (!c || (!dev_fasta && n)) return fail(LHGT_E_ARG, "lhgt_index_build_device: null pointer");
+    if ((uintptr_t)dev_fasta % 16) return fail(LHGT_E_ARG, "device FASTA buffer must be 16-byte aligned");
+    CU(cudaSetDevice(c->device));
+    return index_build_from_device(c, (const uint8_t*)dev_fasta, n);
+}
+
+extern "C" int lhgt_fasta_prefetch(lhgt_ctx* c, const uint8_t* fasta, size_t n) {
+    if (!c || (!fasta && n)) return fail(LHGT_E_ARG, "lhgt_fasta_prefetch: null pointer");
+    CU(cudaSetDevice(c->device));
+    c->keep_fasta_buf = true;
+    int rc = c->fasta_buf.reserve(n + 64);
+    if (rc) return rc;
+    return start_prefetch(c, c->pf_fasta, c->fasta_buf.p, fasta, n);
 }
 
 // Test hook: the index-build kernel over one anonymous contig.
@@ -626,6 +628,20 @@ extern "C" int lhgt_index_download(lhgt_ctx* c, uint8_t* dst, uint64_t cap) {
     CU(cudaMemcpyAsync(dst, c->d_image, c->image_words * 4, cudaMemcpyDeviceToHost, c->st));
     CU(cudaStreamSynchronize(c->st));
     return 0;
+}
+
+extern "C" long lhgt_index_record(lhgt_ctx* c, long record, uint32_t* dst, uint64_t cap_words) {
+    if (!c) return fail(LHGT_E_ARG, "null ctx");
+    if (!c->index_ready) return fail(LHGT_E_STATE, "no index resident");
+    if (record < 0 || record >= (long)c->contigs.size()) return fail(LHGT_E_ARG, "index record %ld out of range", record);
+    const Contig& g = c->contigs[(size_t)record];
+    uint64_t words = 1 + (uint64_t)(g.len - c->k + 1) * c->e;
+    if (!dst) return (long)words;
+    if (cap_words < words) return fail(LHGT_E_ARG, "buffer too small for the index record");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(dst, c->d_image + g.hash_word - 1, words * 4, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    return (long)words;
 }
 
 extern "C" int lhgt_index_len_text(const lhgt_ctx* c, char* dst, size_t cap, size_t* n) {

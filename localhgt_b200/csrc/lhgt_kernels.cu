@@ -250,23 +250,44 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* t
     return res;
 }
 
-__global__ void __launch_bounds__(kScanBlock) scan_block_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
-                                                                uint64_t n, uint32_t* __restrict__ block_sums) {
+template <class T>
+__global__ void __launch_bounds__(kScanBlock) scan_block_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                                uint64_t n, T* __restrict__ block_sums) {
     __shared__ uint32_t sm[33];
+    __shared__ T wide[9];
     uint64_t base = (uint64_t)blockIdx.x * kScanSpan + (uint64_t)threadIdx.x * kScanItems;
-    uint32_t v[kScanItems], sum = 0;
+    T v[kScanItems], sum = 0;
 #pragma unroll
-    for (int i = 0; i < kScanItems; ++i) { v[i] = base + i < n ? in[base + i] : 0u; sum += v[i]; }
-    uint32_t total, ex = block_exclusive_scan(sum, &total, sm);
+    for (int i = 0; i < kScanItems; ++i) { v[i] = base + i < n ? in[base + i] : (T)0; sum += v[i]; }
+    T ex;
+    if constexpr (sizeof(T) == 4) {
+        uint32_t total, e32 = block_exclusive_scan((uint32_t)sum, &total, sm);
+        ex = e32;
+        if (threadIdx.x == 0 && block_sums) block_sums[blockIdx.x] = total;
+    } else {                                                     // 64-bit sums: warp scan in registers, warp totals through shared memory
+        int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        T inc = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            T t = __shfl_up_sync(kFull, inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (lane == 31) wide[warp] = inc;
+        __syncthreads();
+        T before = 0, total = 0;
+#pragma unroll
+        for (int q = 0; q < kScanBlock / 32; ++q) { T w = wide[q]; before += q < warp ? w : (T)0; total += w; }
+        ex = before + inc - sum;
+        if (threadIdx.x == 0 && block_sums) block_sums[blockIdx.x] = total;
+    }
 #pragma unroll
     for (int i = 0; i < kScanItems; ++i) { if (base + i < n) out[base + i] = ex; ex += v[i]; }
-    if (threadIdx.x == 0 && block_sums) block_sums[blockIdx.x] = total;
 }
 
-__global__ void __launch_bounds__(kScanBlock) scan_add_kernel(uint32_t* __restrict__ out, uint64_t n,
-                                                              const uint32_t* __restrict__ block_prefix) {
+template <class T>
+__global__ void __launch_bounds__(kScanBlock) scan_add_kernel(T* __restrict__ out, uint64_t n, const T* __restrict__ block_prefix) {
     uint64_t base = (uint64_t)blockIdx.x * kScanSpan + (uint64_t)threadIdx.x * kScanItems;
-    uint32_t add = block_prefix[blockIdx.x];
+    T add = block_prefix[blockIdx.x];
 #pragma unroll
     for (int i = 0; i < kScanItems; ++i) if (base + i < n) out[base + i] += add;
 }
@@ -277,21 +298,30 @@ size_t scan_tmp_words(uint64_t n) {
     return words + 2;
 }
 
-int launch_scan_exclusive(const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* tmp, cudaStream_t st) {
+template <class T>
+static int scan_exclusive_t(const T* in, T* out, uint64_t n, T* tmp, cudaStream_t st) {
     if (n == 0) return 0;
     uint64_t blocks = (n + kScanSpan - 1) / kScanSpan;
     int launches = 0;
     if (blocks == 1) {
-        scan_block_kernel<<<1, kScanBlock, 0, st>>>(in, out, n, nullptr);
+        scan_block_kernel<T><<<1, kScanBlock, 0, st>>>(in, out, n, (T*)nullptr);
         return 1;
     }
-    uint32_t* sums = tmp;
-    uint32_t* sums_scanned = tmp + blocks;
-    scan_block_kernel<<<(unsigned)blocks, kScanBlock, 0, st>>>(in, out, n, sums);
+    T* sums = tmp;
+    T* sums_scanned = tmp + blocks;
+    scan_block_kernel<T><<<(unsigned)blocks, kScanBlock, 0, st>>>(in, out, n, sums);
     launches += 1;
-    launches += launch_scan_exclusive(sums, sums_scanned, blocks, tmp + 2 * blocks, st);
-    scan_add_kernel<<<(unsigned)blocks, kScanBlock, 0, st>>>(out, n, sums_scanned);
+    launches += scan_exclusive_t<T>(sums, sums_scanned, blocks, tmp + 2 * blocks, st);
+    scan_add_kernel<T><<<(unsigned)blocks, kScanBlock, 0, st>>>(out, n, sums_scanned);
     return launches + 1;
+}
+
+int launch_scan_exclusive(const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* tmp, cudaStream_t st) {
+    return scan_exclusive_t<uint32_t>(in, out, n, tmp, st);
+}
+// 64-bit sums (FASTA files beyond 4 GB of sequence); tmp holds scan_tmp_words(n) elements of 8 bytes
+int launch_scan_exclusive64(const uint64_t* in, uint64_t* out, uint64_t n, uint64_t* tmp, cudaStream_t st) {
+    return scan_exclusive_t<unsigned long long>((const unsigned long long*)in, (unsigned long long*)out, n, (unsigned long long*)tmp, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -453,7 +483,7 @@ __device__ __forceinline__ uint32_t fa_keep_mask(const uint8_t* __restrict__ fa,
 }
 
 __global__ void __launch_bounds__(kFqThreads) fa_count_kernel(const uint8_t* __restrict__ fa, uint64_t n, const ByteSpan* __restrict__ spans,
-                                                              uint32_t nspans, uint32_t* __restrict__ tile_cnt) {
+                                                              uint32_t nspans, uint64_t* __restrict__ tile_cnt) {
     __shared__ uint32_t sm[8];
     uint64_t tile0 = (uint64_t)blockIdx.x * kFqTile;
     uint32_t c = 0;
@@ -472,7 +502,7 @@ __global__ void __launch_bounds__(kFqThreads) fa_count_kernel(const uint8_t* __r
 }
 
 __global__ void __launch_bounds__(kFqThreads) fa_compact_kernel(const uint8_t* __restrict__ fa, uint64_t n, const ByteSpan* __restrict__ spans,
-                                                                uint32_t nspans, const uint32_t* __restrict__ tile_base,
+                                                                uint32_t nspans, const uint64_t* __restrict__ tile_base,
                                                                 uint8_t* __restrict__ out) {
     __shared__ uint32_t wsum[kFqIter][kFqThreads / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -504,10 +534,14 @@ __global__ void __launch_bounds__(kFqThreads) fa_compact_kernel(const uint8_t* _
         uint64_t g = running + before + inc[it] - c[it];
         uint64_t off = tile0 + (uint64_t)it * kFqSub + (uint64_t)threadIdx.x * kFqChunk;
         uint32_t mm = keep[it];
-        while (mm) {
-            int b = __ffs(mm) - 1;
-            mm &= mm - 1;
-            out[g++] = fa[off + b];
+        if (mm == 0xffffu && (g & 15u) == 0) {                  // a whole kept chunk landing on a 16-byte boundary: one vector store
+            *reinterpret_cast<uint4*>(out + g) = *reinterpret_cast<const uint4*>(fa + off);
+        } else {
+            while (mm) {
+                int b = __ffs(mm) - 1;
+                mm &= mm - 1;
+                out[g++] = fa[off + b];
+            }
         }
         running += total;
     }
@@ -515,10 +549,10 @@ __global__ void __launch_bounds__(kFqThreads) fa_compact_kernel(const uint8_t* _
 
 // out[i] = number of kept bytes before byte position pos[i] (pos[i] <= n); one CTA per query
 __global__ void __launch_bounds__(kFqThreads) fa_offsets_kernel(const uint8_t* __restrict__ fa, uint64_t n, const ByteSpan* __restrict__ spans,
-                                                                uint32_t nspans, const uint32_t* __restrict__ tile_base, uint64_t ntiles,
-                                                                const uint64_t* __restrict__ pos, uint64_t* __restrict__ out) {
+                                                                uint32_t nspans, const uint64_t* __restrict__ tile_base, uint64_t ntiles,
+                                                                uint64_t* __restrict__ out) {
     __shared__ uint32_t sm[8];
-    uint64_t q = pos[blockIdx.x];
+    uint64_t q = blockIdx.x < nspans ? spans[blockIdx.x].lo : n;   // query i < nspans: header i's first byte; query nspans: end of file
     uint64_t tile = q / kFqTile;
     uint32_t c = 0;
     uint64_t base = 0;
@@ -533,7 +567,7 @@ __global__ void __launch_bounds__(kFqThreads) fa_offsets_kernel(const uint8_t* _
             c += __popc(m);
         }
     } else if (ntiles) {                                       // q == n on a tile boundary: everything
-        base = (uint64_t)tile_base[ntiles - 1];
+        base = tile_base[ntiles - 1];
         uint64_t tile0 = (ntiles - 1) * kFqTile;
         for (int it = 0; it < kFqIter; ++it)
             c += __popc(fa_keep_mask(fa, tile0 + (uint64_t)it * kFqSub + (uint64_t)threadIdx.x * kFqChunk, n, spans, nspans));
@@ -549,15 +583,69 @@ __global__ void __launch_bounds__(kFqThreads) fa_offsets_kernel(const uint8_t* _
     }
 }
 
-int launch_fasta_compact(const uint8_t* fa, uint64_t n, const ByteSpan* spans, uint32_t nspans, uint32_t* tile_cnt, uint32_t* tile_base,
-                         uint32_t* scan_tmp, uint8_t* out, const uint64_t* pos, uint32_t npos, uint64_t* pos_out, int phase, cudaStream_t st) {
+// Header lines (E:762: a line whose first byte is '>'): every '>' that follows a newline or opens the file.  They are
+// few, so the thread that meets one walks to the end of its line itself and appends the span; the host sorts the list.
+__global__ void __launch_bounds__(kFqThreads) fa_headers_kernel(const uint8_t* __restrict__ fa, uint64_t n, ByteSpan* __restrict__ spans,
+                                                                uint32_t cap, unsigned long long* __restrict__ count) {
+    uint64_t tile0 = (uint64_t)blockIdx.x * kFqTile;
+#pragma unroll
+    for (int it = 0; it < kFqIter; ++it) {
+        uint64_t off = tile0 + (uint64_t)it * kFqSub + (uint64_t)threadIdx.x * kFqChunk;
+        if (off >= n) continue;
+        uint32_t w[4];
+        load16(fa, off, n, w);
+        uint32_t gt = 0, nl = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            gt |= ((__vcmpeq4(w[q], 0x3e3e3e3eu) & 0x01010101u) * 0x01020408u >> 24 & 0xfu) << (q * 4);
+            nl |= ((__vcmpeq4(w[q], 0x0a0a0a0au) & 0x01010101u) * 0x01020408u >> 24 & 0xfu) << (q * 4);
+        }
+        if (!gt) continue;
+        uint32_t prev_nl = off == 0 ? 1u : (uint32_t)(fa[off - 1] == '\n');
+        uint32_t starts = gt & ((nl << 1) | prev_nl) & 0xffffu;
+        if (off + 16 > n) starts &= (1u << (uint32_t)(n - off)) - 1u;
+        while (starts) {
+            int b = __ffs(starts) - 1;
+            starts &= starts - 1;
+            uint64_t lo = off + b, hi = lo;
+            while (hi < n && fa[hi] != '\n') ++hi;
+            if (hi == n) hi = n - 1;                             // last line without a newline
+            unsigned long long at = atomicAdd(count, 1ull);
+            if (at < cap) spans[at] = ByteSpan{lo, hi};
+        }
+    }
+}
+
+// packed[off[i] .. ) = the bytes of header i (its newline excluded), at most `limit` of them; one CTA per header
+__global__ void __launch_bounds__(128) fa_header_text_kernel(const uint8_t* __restrict__ fa, const ByteSpan* __restrict__ spans,
+                                                             const uint64_t* __restrict__ off, uint8_t* __restrict__ packed) {
+    ByteSpan sp = spans[blockIdx.x];
+    uint64_t len = off[blockIdx.x + 1] - off[blockIdx.x];
+    for (uint64_t i = threadIdx.x; i < len; i += blockDim.x) packed[off[blockIdx.x] + i] = fa[sp.lo + i];
+}
+
+int launch_fasta_headers(const uint8_t* fa, uint64_t n, ByteSpan* spans, uint32_t cap, unsigned long long* count, cudaStream_t st) {
+    uint64_t tiles = fastq_index_tiles(n);
+    if (tiles == 0) return 0;
+    fa_headers_kernel<<<(unsigned)tiles, kFqThreads, 0, st>>>(fa, n, spans, cap, count);
+    return 1;
+}
+
+int launch_fasta_header_text(const uint8_t* fa, const ByteSpan* spans, uint32_t nspans, const uint64_t* off, uint8_t* packed, cudaStream_t st) {
+    if (!nspans) return 0;
+    fa_header_text_kernel<<<nspans, 128, 0, st>>>(fa, spans, off, packed);
+    return 1;
+}
+
+int launch_fasta_compact(const uint8_t* fa, uint64_t n, const ByteSpan* spans, uint32_t nspans, uint64_t* tile_cnt, uint64_t* tile_base,
+                         uint64_t* scan_tmp, uint8_t* out, uint64_t* pos_out, int phase, cudaStream_t st) {
     uint64_t tiles = fastq_index_tiles(n);
     if (tiles == 0) return 0;
     if (phase == 0) {
         fa_count_kernel<<<(unsigned)tiles, kFqThreads, 0, st>>>(fa, n, spans, nspans, tile_cnt);
-        int l = 1 + launch_scan_exclusive(tile_cnt, tile_base, tiles, scan_tmp, st);
-        if (npos) { fa_offsets_kernel<<<npos, kFqThreads, 0, st>>>(fa, n, spans, nspans, tile_base, tiles, pos, pos_out); ++l; }
-        return l;
+        int l = 1 + launch_scan_exclusive64(tile_cnt, tile_base, tiles, scan_tmp, st);
+        fa_offsets_kernel<<<nspans + 1, kFqThreads, 0, st>>>(fa, n, spans, nspans, tile_base, tiles, pos_out);
+        return l + 1;
     }
     fa_compact_kernel<<<(unsigned)tiles, kFqThreads, 0, st>>>(fa, n, spans, nspans, tile_base, out);
     return 1;

@@ -98,12 +98,17 @@ int launch_fastq_index(const uint8_t* fq, uint64_t n, uint32_t* tile_cnt, uint32
 uint64_t fastq_index_tiles(uint64_t n);
 size_t scan_tmp_words(uint64_t n);
 int launch_scan_exclusive(const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* tmp, cudaStream_t st);
-// FASTA ingest: phase 0 counts the sequence bytes per 16 KiB tile, scans, and answers `npos` "sequence bytes before
-// byte pos[i]" queries; phase 1 writes the sequence bytes back to back into `out`.
+int launch_scan_exclusive64(const uint64_t* in, uint64_t* out, uint64_t n, uint64_t* tmp, cudaStream_t st);
+// FASTA ingest, all on the device.  launch_fasta_headers appends the byte span of every header line (unordered; *count may
+// exceed cap: enlarge and repeat).  With the spans sorted by position: phase 0 counts the sequence bytes per 16 KiB tile,
+// scans (64-bit), and answers nspans + 1 "sequence bytes before header i / before the end of the file" queries; phase 1
+// writes the sequence bytes back to back into `out`.  scan_tmp holds scan_tmp_words(tiles) 8-byte elements.
 struct ByteSpan { uint64_t lo, hi; };  // a header line: bytes [lo, hi] (hi = its newline, or the last byte of the file)
-int launch_fasta_compact(const uint8_t* fa, uint64_t n, const ByteSpan* spans, uint32_t nspans, uint32_t* tile_cnt,
-                         uint32_t* tile_base, uint32_t* scan_tmp, uint8_t* out, const uint64_t* pos, uint32_t npos,
-                         uint64_t* pos_out, int phase, cudaStream_t st);
+int launch_fasta_headers(const uint8_t* fa, uint64_t n, ByteSpan* spans, uint32_t cap, unsigned long long* count, cudaStream_t st);
+int launch_fasta_header_text(const uint8_t* fa, const ByteSpan* spans, uint32_t nspans, const uint64_t* off, uint8_t* packed,
+                             cudaStream_t st);
+int launch_fasta_compact(const uint8_t* fa, uint64_t n, const ByteSpan* spans, uint32_t nspans, uint64_t* tile_cnt,
+                         uint64_t* tile_base, uint64_t* scan_tmp, uint8_t* out, uint64_t* pos_out, int phase, cudaStream_t st);
 int launch_sum_lengths(const uint64_t* rec_start, const uint64_t* rec_end, uint64_t nrec,
                        unsigned long long* out, cudaStream_t st);
 

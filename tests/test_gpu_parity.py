@@ -322,7 +322,7 @@ def test_s3_vote_with_many_contigs(k, n_genomes, workdir):
 
 @pytest.mark.parametrize("shape", ["leading_sequence", "no_final_newline", "gt_inside_line", "blank_lines_crlf", "long_lines", "headers_only"])
 def test_fasta_shapes_match_oracle_index(shape, workdir):
-    """The FASTA is compacted on the device (header spans found by the host); the oracle walks it line by line."""
+    """The FASTA is parsed on the device (header lines found, sequence compacted there); the oracle walks it line by line."""
     rng = np.random.default_rng(len(shape))
     acgt = np.frombuffer(b"ACGTacgtN", dtype=np.uint8)
     def seq(n):
@@ -353,6 +353,47 @@ def test_fasta_shapes_match_oracle_index(shape, workdir):
         s.index_build(text)
         assert s.index_len_text() == _read(lenp)
         assert bytes(s.index_download()) == _read(idx)
+        # the same from text that already lives on the device
+        import torch
+        t = torch.empty(len(text) + 64, dtype=torch.uint8, device="cuda")
+        t[:len(text)] = torch.frombuffer(bytearray(text), dtype=torch.uint8).cuda()
+        s.index_build_device(t.data_ptr(), len(text))
+        assert s.index_len_text() == _read(lenp)
+        assert bytes(s.index_download()) == _read(idx)
+
+
+@pytest.mark.slow
+def test_fasta_beyond_4_gib_keeps_64_bit_offsets():
+    """A 4.4 GB FASTA (64-bit file offsets and sequence counts in the device scan): 2 200 contigs whose
+    bases are a function of their ordinal; lengths, names and a sample of index records -- including the last contig's,
+    which sits beyond byte 2^32 of the file and of the compacted sequence -- are checked against the oracle's hashes of
+    the same bases.  k = 20, e = 1 keeps the image at 17 GB."""
+    import torch
+    from localhgt_b200 import synth_dev
+    spec = synth_dev.Spec("wide", 2200, 2_000_000, 10, 2, seed=6)
+    fa = synth_dev.make_fasta(spec, "cuda")
+    assert fa.numel() > (1 << 32)
+    k, e = 20, 1
+    o = orc.Oracle(k, e); o.srand(3); cc = o.random_coder()
+    buf = torch.empty(fa.numel() + 64, dtype=torch.uint8, device="cuda")
+    buf[:fa.numel()] = fa
+    del fa
+    with api.Screen(k, e) as s:
+        s.set_coder(cc)
+        s.index_build_device(buf.data_ptr(), buf.numel() - 64)
+        lens = s.index_len_text().decode().splitlines()
+        assert len(lens) == 2200 and s.index_bases() == 2200 * 2_000_000
+        assert lens[0] == "g0\t1\t2000000\t2000000" and lens[3] == "g3\t5\t2000000\t8000020"
+        assert lens[-1] == f"g2199\t2201\t2000000\t{2200 * 2000000 + 20}"
+        per = 1 + (2_000_000 - k + 1) * e
+        assert s.index_bytes() == 1200 + 4 * per * 2200
+        for gi in (0, 1100, 2199):
+            seq = synth_dev.contig_bases(spec, gi, "cpu").numpy().tobytes()
+            want, _ = o.hash_seq(seq)
+            got = s.index_record(gi)
+            assert got[0] == 2_000_000
+            assert np.array_equal(got[1:], want.reshape(-1))
+    o.close()
 
 
 # ------------------------------------------------------------------ properties at a size the oracle cannot do in seconds
