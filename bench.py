@@ -485,8 +485,8 @@ def ours(args) -> None:
                        "roofline": {"bound": "hbm", "achieved": index_bases * (1 + 4 * E) / 1e6 / min(ib_ms_kernel),
                                     "unit": "GB/s", "bytes_per_base": 1 + 4 * E}}
 
-        shard = multi.Shard(scr, rank, world, dist, torch)
-        solo = multi.Shard(scr, 0, 1, None, torch) if world > 1 else shard
+        shard = multi.Shard(scr, rank, world, dist, torch, same_stream=True)     # scr launches on `stream`, torch's current stream
+        solo = multi.Shard(scr, 0, 1, None, torch, same_stream=True) if world > 1 else shard
 
         def step_resident():
             scr.reads_attach_device(0, d1.data_ptr(), d1.numel())
@@ -516,7 +516,7 @@ def ours(args) -> None:
                 sampler.start()
             l0 = scr.launch_count()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            stage = np.zeros(11)
+            stage = np.zeros(13)
             a.record(stream)
             res = None
             for _ in range(steps):
@@ -589,7 +589,7 @@ def ours(args) -> None:
     e2e_value = wl.n_pairs * args.steps / (ms_e2e / 1000)
     peak, peak_src = measured_peak_gbs()
     names = ["fastq_record_scan", "s1_count", "s2_gather", "s2_finish", "s3_pairs", "index_build", "exchange", "host_setup",
-             "s1_hash_streams", "s1_split_streams", "s1_apply_leaves"]
+             "s1_hash_streams", "s1_split_streams", "s1_apply_leaves", "s2_register", "s3_vote"]
     stage_ms = {nm: round(float(v), 3) for nm, v in zip(names, stage)}
     frac = sampled_fraction(wl.n_pairs)
     roofline = make_roofline(stage, wl, frac, world, peak, peak_src, n1 + n2)
@@ -675,7 +675,7 @@ def make_roofline(stage, wl, frac, world, peak, peak_src, fastq_bytes):
                          "achieved": nbytes / 1e6 / ms, "frac": nbytes / 1e6 / ms / peak,
                          "probe_convention": {"bytes_per_launch": int(conv), "achieved": conv / 1e6 / ms, "frac": conv / 1e6 / ms / peak}}
     d = per_kernel[dom]
-    device_ms = float(stage[0] + stage[1] + stage[2] + stage[3] + stage[4])
+    device_ms = float(stage[0] + stage[1] + stage[2] + stage[3] + stage[4] + stage[6] + stage[11])
     whole_bytes = pairs_rank * frac * 2 * 2 * P * E * SECTOR + ref_share * (E * SECTOR + 4 * E)
     return {"bound": "hbm", "kernel": dom, "achieved": d["achieved"], "peak": peak, "unit": "GB/s", "frac": d["frac"],
             "traffic": (traffic or {}).get(dom), "peak_source": peak_src, "algorithmic_bytes_per_launch": d["algorithmic_bytes_per_launch"],

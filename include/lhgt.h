@@ -170,16 +170,28 @@ long lhgt_peaks_copy(lhgt_ctx* c, int32_t* loci /* 2 per peak */, uint8_t* filte
 long lhgt_flagged_positions(const lhgt_ctx* c);          /* positions fed to add_peak */
 int  lhgt_peak_kmer_copy(lhgt_ctx* c, uint32_t* dst /* 2^k */);
 
-/* S2 split for multi-GPU: gather the table for tiles [tile_begin, tile_end) only, exchange the two
- * bit arrays, then finish on every rank. */
+/* S2 in its steps (lhgt_s2_peaks runs them all over the whole reference); tiles are runs of 1024 reference positions.
+ *   gather   [tile_begin, tile_end): per position, trio = all e stored hashes saturated (E:573-595), found with a
+ *            short-circuit AND (~1.1 table probes per position instead of e), and hash 0's hit as the lower bound of single
+ *   mark     hot tiles (some window sum of trio reaches floor(500 * match_ratio), E:560,610) and the tiles within reach of
+ *            one (two either side): the only ones where good windows, intervals or peaks can exist
+ *   complete [tile_begin, tile_end): single = some hash saturated, made exact on the marked tiles
+ *   finish   window sums, intervals, coverage-edge peaks, peak ids, registration in peak_kmer -- on the marked tiles
+ * Multi-GPU: gather and complete run on a tile range per rank, with the trio/single bit arrays exchanged after each
+ * (lhgt_dev_hit_bits); mark and finish run replicated. */
 long     lhgt_s2_tiles(const lhgt_ctx* c);
 int      lhgt_s2_gather(lhgt_ctx* c, long tile_begin, long tile_end);
+int      lhgt_s2_mark(lhgt_ctx* c, float match_ratio);
+int      lhgt_s2_complete(lhgt_ctx* c, long tile_begin, long tile_end);
 int      lhgt_s2_finish(lhgt_ctx* c, float hit_ratio, float match_ratio, long max_peak, long* n_peaks);
+long     lhgt_s2_needed_tiles(const lhgt_ctx* c);        /* marked tiles of the last finish */
 /* Occupancy of the count table (the diagnostic of src/count_diff_kmer.cpp:26-50): out4[v] = number of the
  * 2^k counters holding v.  Its "empty" figure is out4[0] / 2^k, its "weak" figure (out4[0] + out4[1] + out4[2]) / 2^k. */
 int      lhgt_count_table_histogram(lhgt_ctx* c, uint64_t* out4);
 /* Raw device pointers for the exchange steps (NCCL / peer loads run by the caller). */
 void*    lhgt_dev_count_table(lhgt_ctx* c, uint64_t* bytes);      /* packed 2-bit counters */
+/* 128 bytes per tile (1024 positions, one bit each), tile-major; *bytes = the allocation, which covers lhgt_s2_tiles() + 8
+ * tiles so that equal per-rank tile blocks can be all-gathered in place. */
 void*    lhgt_dev_hit_bits(lhgt_ctx* c, int which /*0 single, 1 trio*/, uint64_t* bytes);
 void*    lhgt_dev_peak_filter(lhgt_ctx* c, uint64_t* bytes);
 /* count := min(3, count + other) field-wise on packed tables (other: device pointer, same size). */
@@ -194,13 +206,19 @@ int      lhgt_count_table_ipc(lhgt_ctx* c, void* handle64);
 int      lhgt_peers_open(lhgt_ctx* c, int rank, int world, const void* handles);
 int      lhgt_count_exchange_p2p(lhgt_ctx* c);
 
+/* Deferred counters: with on != 0, lhgt_s1_count and lhgt_s3_pairs only enqueue their kernels and return 0; the sampled
+ * read / pair counts and the read-too-long flags stay on the device until lhgt_deferred_counts copies them back
+ * (out3 = sampled reads of mate 0, of mate 1, sampled pairs of S3) with the step's one synchronisation. */
+int      lhgt_set_deferred(lhgt_ctx* c, int on);
+int      lhgt_deferred_counts(lhgt_ctx* c, long* out3);
+
 /* Device time spent in each stage since the previous lhgt_stage_ms call (read-and-clear), measured
  * with CUDA events on the context's stream:
  * [0] FASTQ record scan  [1] S1  [2] S2 gather  [3] S2 finish  [4] S3  [5] IB kernel. */
 int  lhgt_stage_ms(const lhgt_ctx* c, float* ms6);
 /* Same with n_stages slots: [6] S1 hash-stream kernel  [7] S1 stream-split kernel  [8] S1 leaf-apply kernel
- * ([1] holds their sum)  [9] peer-memory count exchange. */
-#define LHGT_STAGES 10
+ * ([1] holds their sum)  [9] peer-memory count exchange  [10] S2 peak registration (not in [3])  [11] S3 vote (in [4]). */
+#define LHGT_STAGES 12
 int  lhgt_stage_ms_ex(const lhgt_ctx* c, float* ms, int n_stages);
 /* Kernels launched by this context since creation. */
 long lhgt_launch_count(const lhgt_ctx* c);

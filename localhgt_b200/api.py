@@ -90,6 +90,9 @@ SYMBOLS = {
     "lhgt_s2_tiles": (_l, [_vp]),
     "lhgt_s2_gather": (_i, [_vp, _l, _l]),
     "lhgt_s2_finish": (_i, [_vp, _f, _f, _l, C.POINTER(_l)]),
+    "lhgt_s2_mark": (_i, [_vp, _f]),
+    "lhgt_s2_complete": (_i, [_vp, _l, _l]),
+    "lhgt_s2_needed_tiles": (_l, [_vp]),
     "lhgt_dev_count_table": (_vp, [_vp, C.POINTER(_u64)]),
     "lhgt_dev_hit_bits": (_vp, [_vp, _i, C.POINTER(_u64)]),
     "lhgt_dev_peak_filter": (_vp, [_vp, C.POINTER(_u64)]),
@@ -98,6 +101,8 @@ SYMBOLS = {
     "lhgt_count_table_ipc": (_i, [_vp, _vp]),
     "lhgt_peers_open": (_i, [_vp, _i, _i, _vp]),
     "lhgt_count_exchange_p2p": (_i, [_vp]),
+    "lhgt_set_deferred": (_i, [_vp, _i]),
+    "lhgt_deferred_counts": (_i, [_vp, _vp]),
     "lhgt_stage_ms": (_i, [_vp, _vp]),
     "lhgt_stage_ms_ex": (_i, [_vp, _vp, _i]),
     "lhgt_launch_count": (_l, [_vp]),
@@ -326,6 +331,14 @@ class Screen:
     def s2_gather(self, tile_begin: int = 0, tile_end: int = -1) -> None:
         _check(self._L.lhgt_s2_gather(self._h, tile_begin, tile_end))
 
+    def s2_mark(self, match_ratio: float = 0.08) -> None:
+        _check(self._L.lhgt_s2_mark(self._h, match_ratio))
+
+    def s2_complete(self, tile_begin: int = 0, tile_end: int = -1) -> None:
+        _check(self._L.lhgt_s2_complete(self._h, tile_begin, tile_end))
+
+    def s2_needed_tiles(self) -> int: return int(self._L.lhgt_s2_needed_tiles(self._h))
+
     def s2_finish(self, hit_ratio: float = 0.1, match_ratio: float = 0.08, max_peak: int = 300000000) -> int:
         n = _l(0)
         _check(self._L.lhgt_s2_finish(self._h, hit_ratio, match_ratio, max_peak, C.byref(n)))
@@ -401,11 +414,20 @@ class Screen:
     def count_exchange_p2p(self) -> None:
         _check(self._L.lhgt_count_exchange_p2p(self._h))
 
+    def set_deferred(self, on: bool) -> None:
+        _check(self._L.lhgt_set_deferred(self._h, int(on)))
+
+    def deferred_counts(self):
+        out = np.zeros(3, dtype=np.int64)
+        _check(self._L.lhgt_deferred_counts(self._h, _ptr(out)))
+        return int(out[0]), int(out[1]), int(out[2])
+
     def stage_ms(self) -> np.ndarray:
         """Device ms per stage since the last call: [0] FASTQ record scan [1] S1 [2] S2 gather [3] S2 finish [4] S3
-        [5] IB [6] S1 hash-stream kernel [7] S1 stream-split kernel [8] S1 leaf-apply kernel [9] peer-memory count exchange."""
-        ms = np.zeros(10, dtype=np.float32)
-        _check(self._L.lhgt_stage_ms_ex(self._h, _ptr(ms), 10))
+        [5] IB [6] S1 hash-stream kernel [7] S1 stream-split kernel [8] S1 leaf-apply kernel [9] peer-memory count exchange
+        [10] S2 peak registration [11] S3 vote."""
+        ms = np.zeros(12, dtype=np.float32)
+        _check(self._L.lhgt_stage_ms_ex(self._h, _ptr(ms), 12))
         return ms
 
     def launch_count(self) -> int: return int(self._L.lhgt_launch_count(self._h))

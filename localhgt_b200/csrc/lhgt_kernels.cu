@@ -440,14 +440,22 @@ int launch_fastq_index(const uint8_t* fq, uint64_t n, uint32_t* tile_cnt, uint32
     return 1;
 }
 
+// out[0] += sum of sequence-line lengths, out[1] = max(out[1], longest)
 __global__ void sum_lengths_kernel(const uint64_t* __restrict__ s, const uint64_t* __restrict__ e, uint64_t n,
                                    unsigned long long* out) {
-    unsigned long long acc = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-        acc += e[i] - s[i];
+    unsigned long long acc = 0, longest = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        unsigned long long l = e[i] - s[i];
+        acc += l;
+        longest = l > longest ? l : longest;
+    }
 #pragma unroll
-    for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(kFull, acc, d);
-    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+    for (int d = 16; d; d >>= 1) {
+        acc += __shfl_xor_sync(kFull, acc, d);
+        unsigned long long o = __shfl_xor_sync(kFull, longest, d);
+        longest = o > longest ? o : longest;
+    }
+    if ((threadIdx.x & 31) == 0 && acc) { atomicAdd(out, acc); atomicMax(out + 1, longest); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1200,12 +1208,15 @@ int launch_s1_binned(const uint8_t* fq, const uint64_t* rec_start, const uint64_
 // Bit arrays are little-endian in bit order: tile t, local position x -> word t*32 + x/32, bit x%32.
 // ------------------------------------------------------------------------------------------------
 
-// pass a: gather the count table at the stored hashes; single = some hash saturated, trio = all (E:573-595)
+// pass a: trio = ALL e stored hashes of the position saturated (E:573-595; stored 0 = no hit, Q4, E:936-941), evaluated
+// as a short-circuit AND: hash i+1 is only looked up where hashes 0..i were saturated.  A table probe is a 128-byte DRAM
+// fill on this part (profiles/r01p), so the pass costs ~1.1 probes per position instead of e.  `sat0` (hash 0 saturated)
+// is a lower bound of `single` (SOME hash saturated) and becomes exact in pass d, only where it can matter.
 template <int E>
-__global__ void __launch_bounds__(256) s2_gather_kernel(const uint32_t* __restrict__ image, const Contig* __restrict__ contigs,
-                                                        const Tile* __restrict__ tiles, uint64_t tile_begin, HashP hp,
-                                                        const uint32_t* __restrict__ count, uint32_t* __restrict__ single,
-                                                        uint32_t* __restrict__ trio) {
+__global__ void __launch_bounds__(256) s2_trio_kernel(const uint32_t* __restrict__ image, const Contig* __restrict__ contigs,
+                                                      const Tile* __restrict__ tiles, uint64_t tile_begin, HashP hp,
+                                                      const uint32_t* __restrict__ count, uint32_t* __restrict__ single,
+                                                      uint32_t* __restrict__ trio) {
     const int e = E ? E : hp.e;
     uint64_t tix = tile_begin + blockIdx.x;
     Tile t = tiles[tix];
@@ -1213,34 +1224,154 @@ __global__ void __launch_bounds__(256) s2_gather_kernel(const uint32_t* __restri
     long np = (long)c.len - hp.k + 1;
     const uint32_t* hashes = image + c.hash_word;
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t h[4][E ? E : kMaxE], w[4][E ? E : kMaxE];
+    uint32_t h[4];
+    bool sat[4], first[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         long j = (long)t.j0 + r * 256 + threadIdx.x;
-#pragma unroll
-        for (int i = 0; i < (E ? E : kMaxE); ++i)
-            if (i < e) h[r][i] = j < np ? ld_stream(hashes + (size_t)j * e + i) : 0u;
+        h[r] = j < np ? ld_stream(hashes + (size_t)j * e) : 0u;
     }
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int r = 0; r < 4; ++r) {
+        uint32_t g = tbl_index(h[r], hp);
+        sat[r] = h[r] && ((ld_stream(count + (g >> 4)) >> ((g & 15u) * 2)) & 3u) == 3u;
+        first[r] = sat[r];
+    }
+    for (int i = 1; i < e; ++i) {
 #pragma unroll
-        for (int i = 0; i < (E ? E : kMaxE); ++i)
-            if (i < e) {                                           // stored 0 = no hit (Q4, E:936-941)
-                uint32_t g = tbl_index(h[r][i], hp);
-                w[r][i] = h[r][i] ? (ld_stream(count + (g >> 4)) >> ((g & 15u) * 2)) & 3u : 0u;
+        for (int r = 0; r < 4; ++r) {
+            long j = (long)t.j0 + r * 256 + threadIdx.x;
+            h[r] = sat[r] ? ld_stream(hashes + (size_t)j * e + i) : 0u;
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            if (sat[r]) {
+                uint32_t g = tbl_index(h[r], hp);
+                sat[r] = h[r] && ((ld_stream(count + (g >> 4)) >> ((g & 15u) * 2)) & 3u) == 3u;
             }
+    }
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-        int full = 0;
-#pragma unroll
-        for (int i = 0; i < (E ? E : kMaxE); ++i)
-            if (i < e) full += w[r][i] == 3u;
-        uint32_t ws = __ballot_sync(kFull, full > 0);
-        uint32_t wt = __ballot_sync(kFull, full == e);
+        uint32_t ws = __ballot_sync(kFull, first[r]);
+        uint32_t wt = __ballot_sync(kFull, sat[r]);
         if (lane == 0) {
             size_t word = (size_t)tix * kTileWords + r * 8 + warp;
             single[word] = ws;
             trio[word] = wt;
+        }
+    }
+}
+
+// pass b: a tile is HOT when some position j of it has three[j] = sum trio[j-499..j] >= three_min -- the only positions
+// that can be good windows (E:610).  One warp per tile: lane l holds word l of the tile and of its predecessor.
+__global__ void __launch_bounds__(256) s2_hot_kernel(const Contig* __restrict__ contigs, const Tile* __restrict__ tiles, uint64_t ntiles,
+                                                     const uint32_t* __restrict__ trio, int three_min, uint8_t* __restrict__ hot) {
+    int lane = threadIdx.x & 31;
+    uint64_t tix = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (tix >= ntiles) return;
+    Tile t = tiles[tix];
+    uint32_t len = contigs[t.contig].len;
+    uint32_t cur = trio[tix * kTileWords + lane];
+    uint32_t prev = t.j0 > 0 ? trio[(tix - 1) * kTileWords + lane] : 0u;
+    int pc = __popc(cur), pp = __popc(prev);
+    int ic = pc, ip = pp;                                      // inclusive scans
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int a = __shfl_up_sync(kFull, ic, d), b = __shfl_up_sync(kFull, ip, d);
+        if (lane >= d) { ic += a; ip += b; }
+    }
+    int tot_p = __shfl_sync(kFull, ip, 31), tot_c = __shfl_sync(kFull, ic, 31);
+    bool is_hot = false;
+    if (three_min <= 0) is_hot = true;
+    else if (tot_p + tot_c >= three_min) {
+        int cum_c = tot_p + ic - pc, cum_p = ip - pp;          // set bits before this lane's word, counted from the start of prev
+        // position x = 32 * lane + bit of the tile sits at b = 1024 + x of the two-tile window; b - 500 = 32 * (16 + lane) + 12 + bit
+        int sa = (lane + 16) & 31, sb = (lane + 17) & 31;
+        uint32_t pa = __shfl_sync(kFull, prev, sa), ca = __shfl_sync(kFull, cur, sa);
+        uint32_t pb = __shfl_sync(kFull, prev, sb), cb = __shfl_sync(kFull, cur, sb);
+        int cpa = __shfl_sync(kFull, cum_p, sa), cca = __shfl_sync(kFull, cum_c, sa);
+        int cpb = __shfl_sync(kFull, cum_p, sb), ccb = __shfl_sync(kFull, cum_c, sb);
+        uint32_t wa = lane < 16 ? pa : ca, wb = lane < 15 ? pb : cb;
+        int ca_ = lane < 16 ? cpa : cca, cb_ = lane < 15 ? cpb : ccb;
+        long j = (long)t.j0 + 32 * lane;
+#pragma unroll 4
+        for (int bit = 0; bit < 32; ++bit) {
+            int hi = cum_c + __popc(cur & (0xffffffffu >> (31 - bit)));
+            int o = 12 + bit;
+            int lo = o < 32 ? ca_ + __popc(wa & (0xffffffffu >> (31 - o))) : cb_ + __popc(wb & (0xffffffffu >> (63 - o)));
+            is_hot |= j + bit < (long)len && hi - lo >= three_min;
+        }
+    }
+    uint32_t any = __ballot_sync(kFull, is_hot);
+    if (lane == 0) hot[tix] = any != 0u;
+}
+
+// pass c: the tiles the remaining passes have to look at = those within two tiles of a hot one on the same contig: a good
+// window reaches 499 positions back for `one` (E:597-608), an interval 1000 positions either side of a good window
+// (E:617-638) and the coverage-edge test 2k+9 further (E:640-671).  Everywhere else good = flagged = 0 whatever `single`
+// holds.  The list is unordered (appended with one atomic per warp); every consumer treats tiles independently.
+__global__ void __launch_bounds__(256) s2_need_kernel(const Tile* __restrict__ tiles, uint64_t ntiles, const uint8_t* __restrict__ hot,
+                                                      uint32_t* __restrict__ need_list, uint32_t* __restrict__ n_need) {
+    uint64_t tix = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool need = false;
+    if (tix < ntiles) {
+        uint32_t contig = tiles[tix].contig;
+        for (long u = (long)tix - 2; u <= (long)tix + 2; ++u)
+            if (u >= 0 && u < (long)ntiles && hot[u] && tiles[u].contig == contig) need = true;
+    }
+    uint32_t m = __ballot_sync(kFull, need);
+    if (!m) return;
+    int lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(n_need, (uint32_t)__popc(m));
+    base = __shfl_sync(kFull, base, 0);
+    if (need) need_list[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)tix;
+}
+
+// pass d: `single` made exact on the needed tiles of [tile_begin, tile_end): a short-circuit OR over hashes 1..e-1 for the
+// positions whose hash 0 was not saturated.
+template <int E>
+__global__ void __launch_bounds__(256) s2_single_kernel(const uint32_t* __restrict__ image, const Contig* __restrict__ contigs,
+                                                        const Tile* __restrict__ tiles, const uint32_t* __restrict__ need_list,
+                                                        const uint32_t* __restrict__ n_need, uint64_t tile_begin, uint64_t tile_end,
+                                                        HashP hp, const uint32_t* __restrict__ count, uint32_t* __restrict__ single) {
+    const int e = E ? E : hp.e;
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t n = *n_need;
+    for (uint32_t it = blockIdx.x; it < n; it += gridDim.x) {
+        uint64_t tix = need_list[it];
+        if (tix < tile_begin || tix >= tile_end) continue;
+        Tile t = tiles[tix];
+        Contig c = contigs[t.contig];
+        long np = (long)c.len - hp.k + 1;
+        const uint32_t* hashes = image + c.hash_word;
+        bool open[4], sat[4];
+        uint32_t h[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            int xl = r * 256 + threadIdx.x;
+            long j = (long)t.j0 + xl;
+            uint32_t w = single[(size_t)tix * kTileWords + (xl >> 5)];
+            sat[r] = (w >> (xl & 31)) & 1u;
+            open[r] = !sat[r] && j < np;
+        }
+        for (int i = 1; i < e; ++i) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                long j = (long)t.j0 + r * 256 + threadIdx.x;
+                h[r] = open[r] ? ld_stream(hashes + (size_t)j * e + i) : 0u;
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (open[r] && h[r]) {
+                    uint32_t g = tbl_index(h[r], hp);
+                    if (((ld_stream(count + (g >> 4)) >> ((g & 15u) * 2)) & 3u) == 3u) { sat[r] = true; open[r] = false; }
+                }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            uint32_t ws = __ballot_sync(kFull, sat[r]);
+            if (lane == 0) single[(size_t)tix * kTileWords + r * 8 + warp] = ws;
         }
     }
 }
@@ -1252,49 +1383,70 @@ __device__ __forceinline__ int bits_upto(const uint32_t* words, const int* cum, 
     return cum[q] + __popc(words[q] & (0xffffffffu >> (31 - (x & 31))));
 }
 
-__device__ __forceinline__ void prefix_words(const uint32_t* words, int* cum, int n) {
-    // n <= 96: one warp's worth of serial work is cheaper than a scan here
-    if (threadIdx.x == 0) {
-        int acc = 0;
-        for (int i = 0; i < n; ++i) { cum[i] = acc; acc += __popc(words[i]); }
-        cum[n] = acc;
+// cum[i] = set bits in words[0..i), cum[n] = total; n <= 96.  Call with all threads: warp `w` does the work (a shuffle scan).
+__device__ __forceinline__ void prefix_words(const uint32_t* words, int* cum, int n, int w = 0) {
+    if ((int)(threadIdx.x >> 5) != w) return;
+    int lane = threadIdx.x & 31;
+    int c[3], sum = 0;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        int idx = lane * 3 + q;
+        c[q] = idx < n ? __popc(words[idx]) : 0;
+        sum += c[q];
     }
+    int inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(kFull, inc, d);
+        if (lane >= d) inc += t;
+    }
+    int ex = inc - sum;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        int idx = lane * 3 + q;
+        if (idx < n) cum[idx] = ex;
+        ex += c[q];
+    }
+    if (lane == 31) cum[n] = inc;
 }
 
-// pass b: 500-wide window sums and the good-window flag (E:597-615)
+// pass e: 500-wide window sums and the good-window flag (E:597-615), on the needed tiles
 __global__ void __launch_bounds__(256) s2_good_kernel(const Contig* __restrict__ contigs, const Tile* __restrict__ tiles,
+                                                      const uint32_t* __restrict__ need_list, const uint32_t* __restrict__ n_need,
                                                       const uint32_t* __restrict__ single, const uint32_t* __restrict__ trio,
                                                       int one_min, int three_min, uint32_t* __restrict__ good) {
     __shared__ uint32_t ws[2 * kTileWords], wt[2 * kTileWords];
     __shared__ int cs[2 * kTileWords + 1], ct[2 * kTileWords + 1];
-    Tile t = tiles[blockIdx.x];
-    Contig c = contigs[t.contig];
-    bool has_prev = t.j0 > 0;
-    if (threadIdx.x < 2 * kTileWords) {
-        int q = threadIdx.x;
-        bool take = q >= kTileWords || has_prev;
-        size_t word = (size_t)blockIdx.x * kTileWords + q - kTileWords;
-        ws[q] = take ? single[word] : 0u;
-        wt[q] = take ? trio[word] : 0u;
-    }
-    __syncthreads();
-    prefix_words(ws, cs, 2 * kTileWords);
-    if (threadIdx.x == 32) {
-        int acc = 0;
-        for (int i = 0; i < 2 * kTileWords; ++i) { ct[i] = acc; acc += __popc(wt[i]); }
-    }
-    __syncthreads();
-    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t n = *n_need;
+    for (uint32_t it = blockIdx.x; it < n; it += gridDim.x) {
+        const uint64_t tix = need_list[it];
+        Tile t = tiles[tix];
+        Contig c = contigs[t.contig];
+        bool has_prev = t.j0 > 0;
+        if (threadIdx.x < 2 * kTileWords) {
+            int q = threadIdx.x;
+            bool take = q >= kTileWords || has_prev;
+            size_t word = (size_t)tix * kTileWords + q - kTileWords;
+            ws[q] = take ? single[word] : 0u;
+            wt[q] = take ? trio[word] : 0u;
+        }
+        __syncthreads();
+        prefix_words(ws, cs, 2 * kTileWords, 0);
+        prefix_words(wt, ct, 2 * kTileWords, 1);
+        __syncthreads();
+        int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        int xl = r * 256 + threadIdx.x;
-        long j = (long)t.j0 + xl;
-        int b = kTile + xl;
-        int one = bits_upto(ws, cs, b) - bits_upto(ws, cs, b - 500);
-        int three = bits_upto(wt, ct, b) - bits_upto(wt, ct, b - 500);
-        bool g = j < (long)c.len && one >= one_min && three >= three_min;
-        uint32_t wg = __ballot_sync(kFull, g);
-        if (lane == 0) good[(size_t)blockIdx.x * kTileWords + r * 8 + warp] = wg;
+        for (int r = 0; r < 4; ++r) {
+            int xl = r * 256 + threadIdx.x;
+            long j = (long)t.j0 + xl;
+            int b = kTile + xl;
+            int one = bits_upto(ws, cs, b) - bits_upto(ws, cs, b - 500);
+            int three = bits_upto(wt, ct, b) - bits_upto(wt, ct, b - 500);
+            bool g = j < (long)c.len && one >= one_min && three >= three_min;
+            uint32_t wg = __ballot_sync(kFull, g);
+            if (lane == 0) good[(size_t)tix * kTileWords + r * 8 + warp] = wg;
+        }
+        __syncthreads();
     }
 }
 
@@ -1303,65 +1455,77 @@ __global__ void __launch_bounds__(256) s2_good_kernel(const Contig* __restrict__
 //   D(x) = sum single[x-4..x],  C(j) = D(j-5) - D(j-k-5) - D(j),  diff_t(j) = C(j) + D(j-k-5-t), t in [0,k)
 //   peak[j] if some diff_t(j) <= -2;  peak[j-k-5-t] if diff_t(j) >= 2;  only for 2k+10 < j < len.
 __global__ void __launch_bounds__(256) s2_flag_kernel(const Contig* __restrict__ contigs, const Tile* __restrict__ tiles,
-                                                      uint64_t ntiles, int k, const uint32_t* __restrict__ single,
+                                                      uint64_t ntiles, const uint32_t* __restrict__ need_list,
+                                                      const uint32_t* __restrict__ n_need, int k, const uint32_t* __restrict__ single,
                                                       const uint32_t* __restrict__ good, uint32_t* __restrict__ flagged) {
     __shared__ uint32_t ws[3 * kTileWords + 1], wg[3 * kTileWords];
     __shared__ int cg[3 * kTileWords + 1];
     __shared__ signed char D[3 * kTile], C[3 * kTile];
-    Tile t = tiles[blockIdx.x];
-    Contig c = contigs[t.contig];
-    bool has_prev = t.j0 > 0;
-    bool has_next = blockIdx.x + 1 < ntiles && tiles[blockIdx.x + 1].contig == t.contig;
-    if (threadIdx.x < 3 * kTileWords) {
-        int q = threadIdx.x;
-        bool take = (q >= kTileWords || has_prev) && (q < 2 * kTileWords || has_next);
-        size_t word = (size_t)blockIdx.x * kTileWords + q - kTileWords;
-        ws[q] = take ? single[word] : 0u;
-        wg[q] = take ? good[word] : 0u;
-    }
-    if (threadIdx.x == 0) ws[3 * kTileWords] = 0;
-    __syncthreads();
-    prefix_words(wg, cg, 3 * kTileWords);
-    for (int x = threadIdx.x; x < 3 * kTile; x += 256) {
-        int d = 0;
-        if (x >= 4) {
-            int lo = x - 4, q = lo >> 5, s = lo & 31;
-            uint64_t two = ((uint64_t)ws[q + 1] << 32) | ws[q];
-            d = __popc((uint32_t)(two >> s) & 31u);
+    const uint32_t n = *n_need;
+    for (uint32_t it = blockIdx.x; it < n; it += gridDim.x) {
+        const uint64_t tix = need_list[it];
+        Tile t = tiles[tix];
+        Contig c = contigs[t.contig];
+        bool has_prev = t.j0 > 0;
+        bool has_next = tix + 1 < ntiles && tiles[tix + 1].contig == t.contig;
+        if (threadIdx.x < 3 * kTileWords) {
+            int q = threadIdx.x;
+            bool take = (q >= kTileWords || has_prev) && (q < 2 * kTileWords || has_next);
+            size_t word = (size_t)tix * kTileWords + q - kTileWords;
+            ws[q] = take ? single[word] : 0u;
+            wg[q] = take ? good[word] : 0u;
         }
-        D[x] = (signed char)d;
-    }
-    __syncthreads();
-    for (int x = kTile + threadIdx.x; x < 3 * kTile; x += 256) {
-        long j = (long)t.j0 - kTile + x;
-        bool okj = j > 2 * k + 10 && j < (long)c.len;
-        C[x] = okj ? (signed char)(D[x - 5] - D[x - k - 5] - D[x]) : (signed char)-100;
-    }
-    __syncthreads();
-    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        int xl = r * 256 + threadIdx.x;
-        int x = kTile + xl;
-        long j = (long)t.j0 + xl;
-        bool f = false;
-        if (j < (long)c.len && j >= 1) {
-            int lo = x - 1000, hi = x + 1000;
-            bool in_iv = bits_upto(wg, cg, hi) - bits_upto(wg, cg, lo - 1) > 0;
-            if (in_iv) {
-                int cj = C[x], dq = D[x];
-                bool pk = false;
-                if (cj != -100) {
-                    int m = 100;
-                    for (int tt = 0; tt < k; ++tt) m = min(m, (int)D[x - k - 5 - tt]);
-                    pk = cj + m <= -2;
-                }
-                for (int tt = 0; tt < k && !pk; ++tt) pk = (int)C[x + k + 5 + tt] + dq >= 2;
-                f = pk;
+        if (threadIdx.x == 0) ws[3 * kTileWords] = 0;
+        __syncthreads();
+        prefix_words(wg, cg, 3 * kTileWords);
+        __syncthreads();
+        int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (cg[3 * kTileWords] == 0) {                          // no good window within reach: nothing is flagged here
+            if (threadIdx.x < kTileWords) flagged[(size_t)tix * kTileWords + threadIdx.x] = 0u;
+            __syncthreads();
+            continue;
+        }
+        for (int x = threadIdx.x; x < 3 * kTile; x += 256) {
+            int d = 0;
+            if (x >= 4) {
+                int lo = x - 4, q = lo >> 5, s = lo & 31;
+                uint64_t two = ((uint64_t)ws[q + 1] << 32) | ws[q];
+                d = __popc((uint32_t)(two >> s) & 31u);
             }
+            D[x] = (signed char)d;
         }
-        uint32_t wf = __ballot_sync(kFull, f);
-        if (lane == 0) flagged[(size_t)blockIdx.x * kTileWords + r * 8 + warp] = wf;
+        __syncthreads();
+        for (int x = kTile + threadIdx.x; x < 3 * kTile; x += 256) {
+            long j = (long)t.j0 - kTile + x;
+            bool okj = j > 2 * k + 10 && j < (long)c.len;
+            C[x] = okj ? (signed char)(D[x - 5] - D[x - k - 5] - D[x]) : (signed char)-100;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            int xl = r * 256 + threadIdx.x;
+            int x = kTile + xl;
+            long j = (long)t.j0 + xl;
+            bool f = false;
+            if (j < (long)c.len && j >= 1) {
+                int lo = x - 1000, hi = x + 1000;
+                bool in_iv = bits_upto(wg, cg, hi) - bits_upto(wg, cg, lo - 1) > 0;
+                if (in_iv) {
+                    int cj = C[x], dq = D[x];
+                    bool pk = false;
+                    if (cj != -100) {
+                        int m = 100;
+                        for (int tt = 0; tt < k; ++tt) m = min(m, (int)D[x - k - 5 - tt]);
+                        pk = cj + m <= -2;
+                    }
+                    for (int tt = 0; tt < k && !pk; ++tt) pk = (int)C[x + k + 5 + tt] + dq >= 2;
+                    f = pk;
+                }
+            }
+            uint32_t wf = __ballot_sync(kFull, f);
+            if (lane == 0) flagged[(size_t)tix * kTileWords + r * 8 + warp] = wf;
+        }
+        __syncthreads();
     }
 }
 
@@ -1379,29 +1543,33 @@ __device__ __forceinline__ bool opens_peak(const uint32_t* __restrict__ flagged,
     return true;
 }
 
-__global__ void __launch_bounds__(256) s2_count_new_kernel(const Contig* __restrict__ contigs, const Tile* __restrict__ tiles,
-                                                           const uint32_t* __restrict__ flagged, uint32_t* __restrict__ tile_new,
-                                                           unsigned long long* __restrict__ flagged_total) {
+__global__ void __launch_bounds__(256) s2_count_new_kernel(const Tile* __restrict__ tiles, const uint32_t* __restrict__ need_list,
+                                                           const uint32_t* __restrict__ n_need, const uint32_t* __restrict__ flagged,
+                                                           uint32_t* __restrict__ tile_new, unsigned long long* __restrict__ flagged_total) {
     __shared__ uint32_t n_new, n_flag;
-    if (threadIdx.x == 0) { n_new = 0; n_flag = 0; }
-    __syncthreads();
-    Tile t = tiles[blockIdx.x];
-    uint32_t mine = 0, mine_f = 0;
+    const uint32_t n = *n_need;
+    for (uint32_t it = blockIdx.x; it < n; it += gridDim.x) {
+        const uint64_t tix = need_list[it];
+        if (threadIdx.x == 0) { n_new = 0; n_flag = 0; }
+        __syncthreads();
+        Tile t = tiles[tix];
+        uint32_t mine = 0, mine_f = 0;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        int xl = r * 256 + threadIdx.x;
-        uint32_t w = flagged[(size_t)blockIdx.x * kTileWords + (xl >> 5)];
-        if ((w >> (xl & 31)) & 1u) {
-            ++mine_f;
-            mine += opens_peak(flagged, blockIdx.x, t.j0, (long)t.j0 + xl);
+        for (int r = 0; r < 4; ++r) {
+            int xl = r * 256 + threadIdx.x;
+            uint32_t w = flagged[(size_t)tix * kTileWords + (xl >> 5)];
+            if ((w >> (xl & 31)) & 1u) {
+                ++mine_f;
+                mine += opens_peak(flagged, tix, t.j0, (long)t.j0 + xl);
+            }
         }
-    }
-    if (mine) atomicAdd(&n_new, mine);
-    if (mine_f) atomicAdd(&n_flag, mine_f);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        tile_new[blockIdx.x] = n_new;
-        if (n_flag) atomicAdd(flagged_total, (unsigned long long)n_flag);
+        if (mine) atomicAdd(&n_new, mine);
+        if (mine_f) atomicAdd(&n_flag, mine_f);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            tile_new[tix] = n_new;
+            if (n_flag) atomicAdd(flagged_total, (unsigned long long)n_flag);
+        }
     }
 }
 
@@ -1410,103 +1578,127 @@ __global__ void __launch_bounds__(256) s2_count_new_kernel(const Contig* __restr
 // peak_kmer[h] = max id (E:246-270 executed in order).  Id 0 is the reference's "none" (Q10).
 template <int E>
 __global__ void __launch_bounds__(256) s2_register_kernel(const uint32_t* __restrict__ image, const Contig* __restrict__ contigs,
-                                                          const Tile* __restrict__ tiles, HashP hp,
+                                                          const Tile* __restrict__ tiles, const uint32_t* __restrict__ need_list,
+                                                          const uint32_t* __restrict__ n_need, HashP hp,
                                                           const uint32_t* __restrict__ count, const uint32_t* __restrict__ flagged,
-                                                          const uint32_t* __restrict__ tile_base, int32_t* __restrict__ loci,
+                                                          const uint32_t* __restrict__ tile_base, int32_t* __restrict__ loci, uint32_t loci_cap,
                                                           uint32_t* __restrict__ peak_kmer, uint32_t* __restrict__ prefilter,
                                                           int mode) {
     __shared__ uint32_t opener[kTileWords];
     __shared__ int cum[kTileWords + 1];
     const int e = E ? E : hp.e;
-    Tile t = tiles[blockIdx.x];
-    Contig c = contigs[t.contig];
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    bool fl[4], op[4];
-    bool any = false;
+    const uint32_t n = *n_need;
+    for (uint32_t it = blockIdx.x; it < n; it += gridDim.x) {
+        const uint64_t tix = need_list[it];
+        Tile t = tiles[tix];
+        Contig c = contigs[t.contig];
+        bool fl[4], op[4];
+        bool any = false;
+        __syncthreads();                                        // the previous tile's readers of opener/cum are done
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        int xl = r * 256 + threadIdx.x;
-        uint32_t w = flagged[(size_t)blockIdx.x * kTileWords + (xl >> 5)];
-        fl[r] = (w >> (xl & 31)) & 1u;
-        op[r] = fl[r] && opens_peak(flagged, blockIdx.x, t.j0, (long)t.j0 + xl);
-        uint32_t wo = __ballot_sync(kFull, op[r]);
-        if (lane == 0) opener[r * 8 + warp] = wo;
-        any |= fl[r];
-    }
-    if (!__syncthreads_or(any)) return;
-    prefix_words(opener, cum, kTileWords);
-    __syncthreads();
-    long np = (long)c.len - hp.k + 1;
-    uint32_t base = tile_base[blockIdx.x];
+        for (int r = 0; r < 4; ++r) {
+            int xl = r * 256 + threadIdx.x;
+            uint32_t w = flagged[(size_t)tix * kTileWords + (xl >> 5)];
+            fl[r] = (w >> (xl & 31)) & 1u;
+            op[r] = fl[r] && opens_peak(flagged, tix, t.j0, (long)t.j0 + xl);
+            uint32_t wo = __ballot_sync(kFull, op[r]);
+            if (lane == 0) opener[r * 8 + warp] = wo;
+            any |= fl[r];
+        }
+        if (!__syncthreads_or(any)) continue;
+        prefix_words(opener, cum, kTileWords);
+        __syncthreads();
+        long np = (long)c.len - hp.k + 1;
+        uint32_t base = tile_base[tix];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        if (!fl[r]) continue;
-        int xl = r * 256 + threadIdx.x;
-        long j = (long)t.j0 + xl;
-        uint32_t id = base + (uint32_t)bits_upto(opener, cum, xl) - 1u;   // wraps to 0xffffffff only if no opener yet: impossible for a flagged bit
-        if (op[r] && mode == 0) { loci[2 * (size_t)id] = (int32_t)t.contig + 1; loci[2 * (size_t)id + 1] = (int32_t)j; }
-        if (j < np && id != 0u) {                                         // j = len-k+1 reads the zero tail (Q6)
-            const uint32_t* hashes = image + c.hash_word + (size_t)j * e;
-            for (int i = 0; i < e; ++i) {
-                uint32_t h = hashes[i];
-                if (!h) continue;
-                uint32_t g = tbl_index(h, hp);
-                uint32_t cnt = (count[g >> 4] >> ((g & 15u) * 2)) & 3u;
-                if (!cnt) continue;                                        // E:250,265: hit > 0
-                uint32_t slot = prefilter_slot(h);
-                if (mode == 0) {
-                    atomicMax(peak_kmer + h, id);
-                    atomicOr(prefilter + (slot >> 5), 1u << (slot & 31));
-                } else {
-                    peak_kmer[h] = 0u;
-                    prefilter[slot >> 5] = 0u;
+        for (int r = 0; r < 4; ++r) {
+            if (!fl[r]) continue;
+            int xl = r * 256 + threadIdx.x;
+            long j = (long)t.j0 + xl;
+            uint32_t id = base + (uint32_t)bits_upto(opener, cum, xl) - 1u;   // wraps to 0xffffffff only if no opener yet: impossible for a flagged bit
+            if (op[r] && mode == 0 && id < loci_cap) { loci[2 * (size_t)id] = (int32_t)t.contig + 1; loci[2 * (size_t)id + 1] = (int32_t)j; }
+            if (j < np && id != 0u) {                                         // j = len-k+1 reads the zero tail (Q6)
+                const uint32_t* hashes = image + c.hash_word + (size_t)j * e;
+                for (int i = 0; i < e; ++i) {
+                    uint32_t h = hashes[i];
+                    if (!h) continue;
+                    uint32_t g = tbl_index(h, hp);
+                    uint32_t cnt = (count[g >> 4] >> ((g & 15u) * 2)) & 3u;
+                    if (!cnt) continue;                                        // E:250,265: hit > 0
+                    uint32_t slot = prefilter_slot(h);
+                    if (mode == 0) {
+                        atomicMax(peak_kmer + h, id);
+                        atomicOr(prefilter + (slot >> 5), 1u << (slot & 31));
+                    } else {
+                        peak_kmer[h] = 0u;
+                        prefilter[slot >> 5] = 0u;
+                    }
                 }
             }
         }
     }
 }
 
+constexpr int kS2Grid = kSMs * 8;                              // persistent grids over the needed-tile list
+
 int launch_s2_gather(const uint32_t* image, const Contig* contigs, const Tile* tiles, uint64_t tile_begin, uint64_t tile_end,
                      const HashP& hp, const uint32_t* count, uint32_t* single, uint32_t* trio, cudaStream_t st) {
     if (tile_end <= tile_begin) return 0;
     unsigned grid = (unsigned)(tile_end - tile_begin);
     switch (hp.e) {
-        case 1: s2_gather_kernel<1><<<grid, 256, 0, st>>>(image, contigs, tiles, tile_begin, hp, count, single, trio); break;
-        case 2: s2_gather_kernel<2><<<grid, 256, 0, st>>>(image, contigs, tiles, tile_begin, hp, count, single, trio); break;
-        case 3: s2_gather_kernel<3><<<grid, 256, 0, st>>>(image, contigs, tiles, tile_begin, hp, count, single, trio); break;
-        case 4: s2_gather_kernel<4><<<grid, 256, 0, st>>>(image, contigs, tiles, tile_begin, hp, count, single, trio); break;
-        default: s2_gather_kernel<0><<<grid, 256, 0, st>>>(image, contigs, tiles, tile_begin, hp, count, single, trio); break;
+        case 1: s2_trio_kernel<1><<<grid, 256, 0, st>>>(image, contigs, tiles, tile_begin, hp, count, single, trio); break;
+        case 2: s2_trio_kernel<2><<<grid, 256, 0, st>>>(image, contigs, tiles, tile_begin, hp, count, single, trio); break;
+        case 3: s2_trio_kernel<3><<<grid, 256, 0, st>>>(image, contigs, tiles, tile_begin, hp, count, single, trio); break;
+        case 4: s2_trio_kernel<4><<<grid, 256, 0, st>>>(image, contigs, tiles, tile_begin, hp, count, single, trio); break;
+        default: s2_trio_kernel<0><<<grid, 256, 0, st>>>(image, contigs, tiles, tile_begin, hp, count, single, trio); break;
     }
     return 1;
 }
 
-int launch_s2_good(const Contig* contigs, const Tile* tiles, uint64_t ntiles, const uint32_t* single, const uint32_t* trio,
-                   int one_min, int three_min, uint32_t* good, cudaStream_t st) {
+int launch_s2_mark(const Contig* contigs, const Tile* tiles, uint64_t ntiles, const uint32_t* trio, int three_min, uint8_t* hot,
+                   uint32_t* need_list, uint32_t* n_need, cudaStream_t st) {
     if (!ntiles) return 0;
-    s2_good_kernel<<<(unsigned)ntiles, 256, 0, st>>>(contigs, tiles, single, trio, one_min, three_min, good);
+    s2_hot_kernel<<<(unsigned)((ntiles + 7) / 8), 256, 0, st>>>(contigs, tiles, ntiles, trio, three_min, hot);
+    s2_need_kernel<<<(unsigned)((ntiles + 255) / 256), 256, 0, st>>>(tiles, ntiles, hot, need_list, n_need);
+    return 2;
+}
+
+int launch_s2_single(const uint32_t* image, const Contig* contigs, const Tile* tiles, const uint32_t* need_list, const uint32_t* n_need,
+                     uint64_t tile_begin, uint64_t tile_end, const HashP& hp, const uint32_t* count, uint32_t* single, cudaStream_t st) {
+    if (tile_end <= tile_begin || hp.e < 2) return 0;
+    switch (hp.e) {
+        case 2: s2_single_kernel<2><<<kS2Grid, 256, 0, st>>>(image, contigs, tiles, need_list, n_need, tile_begin, tile_end, hp, count, single); break;
+        case 3: s2_single_kernel<3><<<kS2Grid, 256, 0, st>>>(image, contigs, tiles, need_list, n_need, tile_begin, tile_end, hp, count, single); break;
+        case 4: s2_single_kernel<4><<<kS2Grid, 256, 0, st>>>(image, contigs, tiles, need_list, n_need, tile_begin, tile_end, hp, count, single); break;
+        default: s2_single_kernel<0><<<kS2Grid, 256, 0, st>>>(image, contigs, tiles, need_list, n_need, tile_begin, tile_end, hp, count, single); break;
+    }
     return 1;
 }
 
-int launch_s2_flag(const Contig* contigs, const Tile* tiles, uint64_t ntiles, int k, const uint32_t* single,
-                   const uint32_t* good, uint32_t* flagged, cudaStream_t st) {
-    if (!ntiles) return 0;
-    s2_flag_kernel<<<(unsigned)ntiles, 256, 0, st>>>(contigs, tiles, ntiles, k, single, good, flagged);
+int launch_s2_good(const Contig* contigs, const Tile* tiles, const uint32_t* need_list, const uint32_t* n_need, const uint32_t* single,
+                   const uint32_t* trio, int one_min, int three_min, uint32_t* good, cudaStream_t st) {
+    s2_good_kernel<<<kS2Grid, 256, 0, st>>>(contigs, tiles, need_list, n_need, single, trio, one_min, three_min, good);
     return 1;
 }
 
-int launch_s2_count_new(const Contig* contigs, const Tile* tiles, uint64_t ntiles, const uint32_t* flagged,
+int launch_s2_flag(const Contig* contigs, const Tile* tiles, uint64_t ntiles, const uint32_t* need_list, const uint32_t* n_need, int k,
+                   const uint32_t* single, const uint32_t* good, uint32_t* flagged, cudaStream_t st) {
+    s2_flag_kernel<<<kS2Grid / 2, 256, 0, st>>>(contigs, tiles, ntiles, need_list, n_need, k, single, good, flagged);
+    return 1;
+}
+
+int launch_s2_count_new(const Tile* tiles, const uint32_t* need_list, const uint32_t* n_need, const uint32_t* flagged,
                         uint32_t* tile_new, unsigned long long* flagged_total, cudaStream_t st) {
-    if (!ntiles) return 0;
-    s2_count_new_kernel<<<(unsigned)ntiles, 256, 0, st>>>(contigs, tiles, flagged, tile_new, flagged_total);
+    s2_count_new_kernel<<<kS2Grid, 256, 0, st>>>(tiles, need_list, n_need, flagged, tile_new, flagged_total);
     return 1;
 }
 
-int launch_s2_register(const uint32_t* image, const Contig* contigs, const Tile* tiles, uint64_t ntiles, const HashP& hp,
-                       const uint32_t* count, const uint32_t* flagged, const uint32_t* tile_base, int32_t* loci,
-                       uint32_t* peak_kmer, uint32_t* prefilter, int mode, cudaStream_t st) {
-    if (!ntiles) return 0;
-    s2_register_kernel<0><<<(unsigned)ntiles, 256, 0, st>>>(image, contigs, tiles, hp, count, flagged, tile_base, loci,
-                                                           peak_kmer, prefilter, mode);
+int launch_s2_register(const uint32_t* image, const Contig* contigs, const Tile* tiles, const uint32_t* need_list, const uint32_t* n_need,
+                       const HashP& hp, const uint32_t* count, const uint32_t* flagged, const uint32_t* tile_base, int32_t* loci,
+                       uint32_t loci_cap, uint32_t* peak_kmer, uint32_t* prefilter, int mode, cudaStream_t st) {
+    s2_register_kernel<0><<<kS2Grid, 256, 0, st>>>(image, contigs, tiles, need_list, n_need, hp, count, flagged, tile_base, loci, loci_cap,
+                                                  peak_kmer, prefilter, mode);
     return 1;
 }
 
@@ -1526,11 +1718,23 @@ constexpr int kS3Warps = LHGT_S3_WARPS;
 int s3_warps_per_block() { return kS3Warps; }
 int s3_grid_blocks(int) { return kSMs * LHGT_S3_CTAS; }
 
+// Peak ids are handed out in (contig, position) order, so the contig of a peak is a search in the first-id-per-contig
+// array (n_contigs + 1 entries, a few KB: on chip) instead of a random gather from the per-peak loci.  Returns the 1-based
+// record ordinal = the largest c with contig_first[c - 1] <= id (contigs without peaks share their successor's first id).
+__device__ __forceinline__ int contig_of_peak(const uint32_t* __restrict__ contig_first, uint32_t n_contigs, uint32_t id) {
+    uint32_t lo = 0, hi = n_contigs;                             // invariant: contig_first[lo] <= id (peak 0 opens contig_first[.] = 0)
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(contig_first + mid) <= id) lo = mid; else hi = mid;
+    }
+    return (int)lo + 1;
+}
+
 // src points into the warp's shared-memory stage (s3_pairs_kernel).
 template <int E>
 __device__ __forceinline__ int s3_scan_mate(const uint8_t* src, int len, const uint8_t* lut, const HashP& hp,
                                             const uint32_t* __restrict__ prefilter,
-                                            const uint32_t* __restrict__ peak_kmer, const int32_t* __restrict__ loci,
+                                            const uint32_t* __restrict__ peak_kmer, const uint32_t* __restrict__ contig_first, uint32_t n_contigs,
                                             uint32_t* __restrict__ cands, int32_t* __restrict__ cont, int n_listed, int lane) {
     const int e = E ? E : hp.e;
     int np = len - hp.k + 1;
@@ -1552,7 +1756,7 @@ __device__ __forceinline__ int s3_scan_mate(const uint8_t* src, int len, const u
             if (i < e) {
                 h[i] = le_hash(kw, hp, i);
                 uint32_t slot = prefilter_slot(h[i]);
-                fw[i] = kw.valid ? ld_table(prefilter + (slot >> 5)) >> (slot & 31) : 0u;
+                fw[i] = !kw.valid ? 0u : prefilter ? ld_table(prefilter + (slot >> 5)) >> (slot & 31) : 1u;   // no filter: it is saturated
             }
         bool any = false;
 #pragma unroll
@@ -1567,9 +1771,9 @@ __device__ __forceinline__ int s3_scan_mate(const uint8_t* src, int len, const u
                 int slot = n_listed + __popc(mask & ((1u << lane) - 1u));
 #pragma unroll
                 for (int i = 0; i < (E ? E : kMaxE); ++i)
-                    if (i < e) {                                  // the lane that found the peak also fetches its contig
+                    if (i < e) {                                  // the lane that found the peak also names its contig
                         cands[(size_t)slot * e + i] = pk[i];
-                        cont[(size_t)slot * e + i] = pk[i] ? loci[2 * (size_t)pk[i]] : 0;
+                        cont[(size_t)slot * e + i] = pk[i] ? contig_of_peak(contig_first, n_contigs, pk[i]) : 0;
                     }
             }
             n_listed += __popc(mask);
@@ -1730,6 +1934,8 @@ __global__ void __launch_bounds__(kS3Warps * 32, LHGT_S3_CTAS) s3_pairs_kernel(
     uint64_t ordinal_base, HashP hp, const uint32_t* __restrict__ prefilter, const uint32_t* __restrict__ peak_kmer,
     const int32_t* __restrict__ loci, uint8_t* __restrict__ peak_filter, S3Scratch scratch,
     unsigned long long* __restrict__ n_sampled, int* __restrict__ err) {
+    const uint32_t* __restrict__ contig_first = scratch.contig_first;
+    const uint32_t n_contigs = scratch.n_contigs;
     __shared__ uint8_t lut[256];
     __shared__ __align__(16) uint8_t stage[kS3Warps][4][kStageBytes];
     __shared__ __align__(8) uint64_t sbar[kS3Warps][2];        // "pair staged", one per slot pair
@@ -1793,14 +1999,31 @@ __global__ void __launch_bounds__(kS3Warps * 32, LHGT_S3_CTAS) s3_pairs_kernel(
         __syncwarp();                                           // every lane is done with the other slot pair
         if (rn < last && on.ok) { stage_pair(on, slot ^ 1); nstaged = true; }
         uint32_t m1 = (uint32_t)cur.a0 & 15u, m2 = (uint32_t)cur.b0 & 15u;
-        int n_listed = s3_scan_mate<E>(stage[warp][2 * slot] + m1, (int)cur.l1, lut, hp, prefilter, peak_kmer, loci, cands, cont, 0, lane);
-        n_listed = s3_scan_mate<E>(stage[warp][2 * slot + 1] + m2, (int)cur.l2, lut, hp, prefilter, peak_kmer, loci, cands, cont, n_listed, lane);
+        int n_listed = s3_scan_mate<E>(stage[warp][2 * slot] + m1, (int)cur.l1, lut, hp, prefilter, peak_kmer, contig_first, n_contigs, cands, cont, 0, lane);
+        n_listed = s3_scan_mate<E>(stage[warp][2 * slot + 1] + m2, (int)cur.l2, lut, hp, prefilter, peak_kmer, contig_first, n_contigs, cands, cont, n_listed, lane);
         if (n_listed >= 6) {                                 // base_hits >= MIN_BASE_NUM (E:496)
             __syncwarp();
-            if (!s3_vote_warp<E>(cands, cont, n_listed, e, peak_filter, lane)) {        // more than 32 contigs in one pair
+            // The order-dependent vote is handed to s3_vote_kernel (one THREAD per pair, 32 pairs per warp in flight): the
+            // pair's candidates move to the arena and the pair joins the queue.  When either is full the warp votes itself.
+            bool queued = false;
+            if (scratch.arena) {
+                uint32_t words = (uint32_t)n_listed * (uint32_t)e, off = 0, q = 0;
+                if (lane == 0) {
+                    off = atomicAdd(scratch.arena_cursor, words);
+                    q = off + words <= scratch.arena_cap ? atomicAdd(scratch.queue_count, 1u) : 0xffffffffu;
+                }
+                off = __shfl_sync(kFull, off, 0); q = __shfl_sync(kFull, q, 0);
+                if (q < scratch.queue_cap) {
+                    uint2* dst = scratch.arena + off;
+                    for (uint32_t x = lane; x < words; x += 32) dst[x] = make_uint2(__ldcg(cands + x), (uint32_t)__ldcg(cont + x));
+                    if (lane == 0) scratch.queue[q] = make_uint2(off, (uint32_t)n_listed);
+                    queued = true;
+                }
+            }
+            if (!queued && !s3_vote_warp<E>(cands, cont, n_listed, e, peak_filter, lane)) {        // more than 32 contigs in one pair
                 if (lane == 0) {
                     if (scratch.vote_table) s3_vote_table(cands, cont, n_listed, e, scratch.vote_table + gwarp * scratch.vote_stride,
-                                                          scratch.n_contigs, tally, peak_filter);
+                                                          scratch.vote_contigs, tally, peak_filter);
                     else s3_vote(cands, n_listed, e, loci, tally, peak_filter);
                 }
             }
@@ -1808,6 +2031,77 @@ __global__ void __launch_bounds__(kS3Warps * 32, LHGT_S3_CTAS) s3_pairs_kernel(
         }
     }
     if (lane == 0 && mine) atomicAdd(n_sampled, mine);
+}
+
+// The vote of the queued pairs (judge_base + check_split, E:118-202), one thread per pair.  The tally is an open-addressed
+// table of `tsize` 32-bit slots per thread (contig << 10 | votes; 0 = empty; tsize a power of two >= twice the longest
+// list) in global memory sized to stay L2-resident; it is left clean: the slots a pair fills are remembered, together
+// with the first peak voted for that contig, in the arena space of candidates already consumed, and zeroed at the end.
+__global__ void __launch_bounds__(128) s3_vote_kernel(uint2* __restrict__ arena, const uint2* __restrict__ queue,
+                                                      const uint32_t* __restrict__ queue_count, uint32_t queue_cap, int e,
+                                                      uint32_t* __restrict__ tables, uint32_t tsize, uint8_t* __restrict__ peak_filter) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+    uint32_t* table = tables + (size_t)tid * tsize;
+    const uint32_t mask = tsize - 1u;
+    const int shift = 32 - (31 - __clz(tsize));
+    const uint32_t n = min(*queue_count, queue_cap);
+    for (uint32_t q = tid; q < n; q += nthreads) {
+        uint2 job = queue[q];
+        uint2* list = arena + job.x;
+        const int n_listed = (int)job.y;
+        int n_t = 0;
+        for (int f = 0; f < n_listed; ++f) {
+            uint32_t sel_peak = 0, sel_slot = 0, sel_entry = 0;
+            int sel_votes = 0;
+            bool sel_seen = false;
+            for (int i = 0; i < e; ++i) {
+                uint2 cd = list[(size_t)f * e + i];
+                if (!cd.x) continue;
+                uint32_t idx = (cd.y * 2654435761u) >> shift, ent;
+                while ((ent = table[idx]) != 0u && (ent >> 10) != cd.y) idx = (idx + 1u) & mask;
+                if (ent) {
+                    int v = (int)(ent & 1023u);
+                    if (v >= sel_votes) { sel_peak = cd.x; sel_votes = v; sel_seen = true; sel_slot = idx; sel_entry = ent; }
+                } else if (sel_peak == 0) { sel_peak = cd.x; sel_votes = 0; sel_seen = false; sel_slot = idx; sel_entry = cd.y << 10; }
+            }
+            table[sel_slot] = sel_entry + 1u;
+            if (!sel_seen) list[n_t++] = make_uint2(sel_slot, sel_peak);      // n_t <= f + 1: that entry has been consumed
+        }
+        int largest = 0, second = 0, strong = 0;
+        for (int t = 0; t < n_t; ++t) {
+            int v = (int)(table[list[t].x] & 1023u);
+            if (v < 6) continue;
+            ++strong;
+            if (v >= largest) { second = largest; largest = v; }
+            else if (v >= second) second = v;
+        }
+        for (int t = 0; t < n_t; ++t) {
+            uint2 rec = list[t];
+            int v = (int)(table[rec.x] & 1023u);
+            if (strong >= 2 && v >= 6 && (v == largest || v == second)) peak_filter[rec.y] = 1;   // only >= 1 is consumed (E:526)
+            table[rec.x] = 0u;
+        }
+    }
+}
+
+__global__ void contig_first_kernel(const Contig* __restrict__ contigs, uint32_t n_contigs, const uint32_t* __restrict__ tile_base,
+                                    uint32_t total, uint32_t* __restrict__ contig_first) {
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n_contigs) contig_first[c] = tile_base[contigs[c].tile0];
+    else if (c == n_contigs) contig_first[c] = total;
+}
+
+int launch_contig_first(const Contig* contigs, uint32_t n_contigs, const uint32_t* tile_base, uint32_t total, uint32_t* contig_first,
+                        cudaStream_t st) {
+    contig_first_kernel<<<(n_contigs + 1 + 255) / 256, 256, 0, st>>>(contigs, n_contigs, tile_base, total, contig_first);
+    return 1;
+}
+
+int s3_vote_threads() { return kSMs * 128; }
+
+int launch_s3_vote(const S3Scratch& sc, int e, uint32_t* tables, uint32_t tsize, uint8_t* peak_filter, cudaStream_t st) {
+    s3_vote_kernel<<<kSMs, 128, 0, st>>>(sc.arena, sc.queue, sc.queue_count, sc.queue_cap, e, tables, tsize, peak_filter);
+    return 1;
 }
 
 int launch_s3(const uint8_t* fq1, const uint64_t* s1, const uint64_t* e1, uint64_t nrec1, const uint8_t* fq2,
@@ -1848,6 +2142,49 @@ __global__ void sample_bits_kernel(const uint32_t* __restrict__ m, uint64_t n, u
 
 int launch_sample_bits(const uint32_t* m, uint64_t n, uint32_t m_star, uint32_t* bits, uint64_t words, cudaStream_t st) {
     sample_bits_kernel<<<kSMs * 8, 256, 0, st>>>(m, n, m_star, bits, words);
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// OUT: the kept peaks (peak_filter >= 1, E:526) in id order, compacted on the device so that only they cross PCIe
+// ------------------------------------------------------------------------------------------------
+constexpr int kKeepBlock = 1024;
+__global__ void __launch_bounds__(256) peaks_count_kernel(const uint8_t* __restrict__ filter, uint64_t n, uint32_t* __restrict__ block_cnt) {
+    __shared__ uint32_t sm[33];
+    uint64_t base = (uint64_t)blockIdx.x * kKeepBlock + threadIdx.x * 4;
+    uint32_t c = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) c += base + q < n && filter[base + q] != 0;
+    uint32_t total;
+    block_exclusive_scan(c, &total, sm);
+    if (threadIdx.x == 0) block_cnt[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(256) peaks_write_kernel(const uint8_t* __restrict__ filter, const int32_t* __restrict__ loci, uint64_t n,
+                                                          const uint32_t* __restrict__ block_base, int32_t* __restrict__ out) {
+    __shared__ uint32_t sm[33];
+    uint64_t base = (uint64_t)blockIdx.x * kKeepBlock + threadIdx.x * 4;
+    bool keep[4];
+    uint32_t c = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { keep[q] = base + q < n && filter[base + q] != 0; c += keep[q]; }
+    uint32_t total, at = block_exclusive_scan(c, &total, sm) + block_base[blockIdx.x];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (keep[q]) { out[2 * (size_t)at] = loci[2 * (base + q)]; out[2 * (size_t)at + 1] = loci[2 * (base + q) + 1]; ++at; }
+}
+
+uint64_t peaks_keep_blocks(uint64_t n) { return (n + kKeepBlock - 1) / kKeepBlock; }
+
+int launch_peaks_compact(const uint8_t* filter, const int32_t* loci, uint64_t n, uint32_t* block_cnt, uint32_t* block_base,
+                         uint32_t* scan_tmp, int32_t* out, int phase, cudaStream_t st) {
+    uint64_t blocks = peaks_keep_blocks(n);
+    if (!blocks) return 0;
+    if (phase == 0) {
+        peaks_count_kernel<<<(unsigned)blocks, 256, 0, st>>>(filter, n, block_cnt);
+        return 1 + launch_scan_exclusive(block_cnt, block_base, blocks, scan_tmp, st);
+    }
+    peaks_write_kernel<<<(unsigned)blocks, 256, 0, st>>>(filter, loci, n, block_base, out);
     return 1;
 }
 
@@ -1913,8 +2250,8 @@ int launch_count_merge(uint32_t* count, const uint32_t* other, uint64_t words, c
 // owns slice `rank` of every rank's table; it reads that slice from all `world` tables, combines the 2-bit fields with
 // min(3, sum) and stores the result back into all of them.  Ranks touch disjoint slices, so the only synchronisation
 // is a barrier before (every table final) and after (every slice written everywhere).
-__global__ void __launch_bounds__(256) count_exchange_kernel(PeerTables pt, int world, int rank, uint64_t slice_vec /* uint4s per slice */) {
-    const uint64_t lo = (uint64_t)rank * slice_vec;
+__global__ void __launch_bounds__(256) count_exchange_kernel(PeerTables pt, int world, uint64_t lo /* first uint4 of this rank's slice */,
+                                                             uint64_t slice_vec /* uint4s in it */) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < slice_vec; i += (uint64_t)gridDim.x * blockDim.x) {
         uint4 v[kMaxPeers];
 #pragma unroll
@@ -1933,10 +2270,13 @@ __global__ void __launch_bounds__(256) count_exchange_kernel(PeerTables pt, int 
     }
 }
 
+// slices are whole 16-byte vectors and differ by at most one vector when `world` does not divide the table
 int launch_count_exchange(const PeerTables& pt, int world, int rank, uint64_t table_words, cudaStream_t st) {
-    uint64_t slice_vec = table_words / 4 / (uint64_t)world;
-    if (slice_vec == 0) return 0;
-    count_exchange_kernel<<<kSMs * 8, 256, 0, st>>>(pt, world, rank, slice_vec);
+    uint64_t vecs = table_words / 4, base = vecs / (uint64_t)world, extra = vecs % (uint64_t)world;
+    uint64_t lo = (uint64_t)rank * base + ((uint64_t)rank < extra ? (uint64_t)rank : extra);
+    uint64_t n = base + ((uint64_t)rank < extra ? 1 : 0);
+    if (n == 0) return 0;
+    count_exchange_kernel<<<kSMs * 8, 256, 0, st>>>(pt, world, lo, n);
     return 1;
 }
 

@@ -87,8 +87,15 @@ struct S3Scratch {                     // per resident warp
     // direct-addressed vote table for pairs that touch many contigs (s3_vote_table): per warp [0] = epoch counter,
     // [1 + c] = epoch << 10 | votes of contig c, [1 + n_contigs + 1 + c] = first peak voted for contig c
     uint32_t* vote_table;              // nullptr: not available (too many contigs) -> linear search
-    size_t vote_stride;                // 2 * (n_contigs + 1) + 1
+    size_t vote_stride;                // 2 * (vote_contigs + 1) + 1
+    uint32_t vote_contigs;
+    // peak id -> contig: first peak id of every indexed contig, n_contigs + 1 entries (contig_of_peak)
+    const uint32_t* contig_first;
     uint32_t n_contigs;
+    // hand-over to s3_vote_kernel: candidate lists ({peak id, contig} per (listed position, hash)) bump-allocated in `arena`,
+    // one {offset, listed positions} job per pair in `queue`; arena = nullptr: every warp votes itself
+    uint2* arena; uint32_t arena_cap; uint32_t* arena_cursor;
+    uint2* queue; uint32_t queue_cap; uint32_t* queue_count;
 };
 
 // ---- launchers (all asynchronous on `st`; return the number of kernels launched) ----
@@ -128,20 +135,33 @@ int launch_s1_binned(const uint8_t* fq, const uint64_t* rec_start, const uint64_
 size_t s1_bin_smem_bytes(const BinP& bp);
 int s1_leaf_max_log2();              // largest table slice (log2 counters) s1_leaf_kernel holds in shared memory
 
+// S2.  gather: trio (exact) + hash-0 hits as the lower bound of single, for tiles [tile_begin, tile_end);
+// mark: hot tiles and the unordered list of tiles the remaining passes must visit (*n_need zeroed by the caller);
+// single: `single` made exact on the needed tiles of [tile_begin, tile_end); the rest run over the needed tiles only
+// (good / flagged / tile_new must be zero elsewhere: the caller clears them).
 int launch_s2_gather(const uint32_t* image, const Contig* contigs, const Tile* tiles, uint64_t tile_begin,
                      uint64_t tile_end, const HashP& hp, const uint32_t* count, uint32_t* single,
                      uint32_t* trio, cudaStream_t st);
-int launch_s2_good(const Contig* contigs, const Tile* tiles, uint64_t ntiles, const uint32_t* single,
+int launch_s2_mark(const Contig* contigs, const Tile* tiles, uint64_t ntiles, const uint32_t* trio, int three_min, uint8_t* hot,
+                   uint32_t* need_list, uint32_t* n_need, cudaStream_t st);
+int launch_s2_single(const uint32_t* image, const Contig* contigs, const Tile* tiles, const uint32_t* need_list, const uint32_t* n_need,
+                     uint64_t tile_begin, uint64_t tile_end, const HashP& hp, const uint32_t* count, uint32_t* single, cudaStream_t st);
+int launch_s2_good(const Contig* contigs, const Tile* tiles, const uint32_t* need_list, const uint32_t* n_need, const uint32_t* single,
                    const uint32_t* trio, int one_min, int three_min, uint32_t* good, cudaStream_t st);
-int launch_s2_flag(const Contig* contigs, const Tile* tiles, uint64_t ntiles, int k, const uint32_t* single,
-                   const uint32_t* good, uint32_t* flagged, cudaStream_t st);
-int launch_s2_count_new(const Contig* contigs, const Tile* tiles, uint64_t ntiles, const uint32_t* flagged,
+int launch_s2_flag(const Contig* contigs, const Tile* tiles, uint64_t ntiles, const uint32_t* need_list, const uint32_t* n_need, int k,
+                   const uint32_t* single, const uint32_t* good, uint32_t* flagged, cudaStream_t st);
+int launch_s2_count_new(const Tile* tiles, const uint32_t* need_list, const uint32_t* n_need, const uint32_t* flagged,
                         uint32_t* tile_new, unsigned long long* flagged_total, cudaStream_t st);
 // mode 0: write loci + scatter-max peak ids + pre-filter bits; mode 1: clear what mode 0 wrote
-int launch_s2_register(const uint32_t* image, const Contig* contigs, const Tile* tiles, uint64_t ntiles,
-                       const HashP& hp, const uint32_t* count, const uint32_t* flagged,
-                       const uint32_t* tile_base, int32_t* loci, uint32_t* peak_kmer, uint32_t* prefilter,
-                       int mode, cudaStream_t st);
+int launch_s2_register(const uint32_t* image, const Contig* contigs, const Tile* tiles, const uint32_t* need_list, const uint32_t* n_need,
+                       const HashP& hp, const uint32_t* count, const uint32_t* flagged, const uint32_t* tile_base, int32_t* loci,
+                       uint32_t loci_cap, uint32_t* peak_kmer, uint32_t* prefilter, int mode, cudaStream_t st);
+
+// kept peaks (filter != 0) in id order: phase 0 counts per 1024-peak block and scans (block_cnt / block_base: peaks_keep_blocks(n)
+// words, scan_tmp: scan_tmp_words of that), phase 1 writes (contig, position) pairs into `out`
+uint64_t peaks_keep_blocks(uint64_t n);
+int launch_peaks_compact(const uint8_t* filter, const int32_t* loci, uint64_t n, uint32_t* block_cnt, uint32_t* block_base,
+                         uint32_t* scan_tmp, int32_t* out, int phase, cudaStream_t st);
 
 int launch_s3(const uint8_t* fq1, const uint64_t* s1, const uint64_t* e1, uint64_t nrec1,
               const uint8_t* fq2, const uint64_t* s2, const uint64_t* e2, uint64_t nrec2,
@@ -150,6 +170,11 @@ int launch_s3(const uint8_t* fq1, const uint64_t* s1, const uint64_t* e1, uint64
               const uint32_t* prefilter, const uint32_t* peak_kmer, const int32_t* loci,
               uint8_t* peak_filter, S3Scratch scratch, int grid_blocks, unsigned long long* n_sampled,
               int* err, cudaStream_t st);
+int launch_contig_first(const Contig* contigs, uint32_t n_contigs, const uint32_t* tile_base, uint32_t total, uint32_t* contig_first,
+                        cudaStream_t st);
+// votes of the pairs queued by launch_s3: `tables` holds s3_vote_threads() * tsize zeroed words (left zeroed)
+int s3_vote_threads();
+int launch_s3_vote(const S3Scratch& sc, int e, uint32_t* tables, uint32_t tsize, uint8_t* peak_filter, cudaStream_t st);
 int s3_grid_blocks(int device);
 int s3_warps_per_block();
 

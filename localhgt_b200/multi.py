@@ -81,14 +81,22 @@ class GpuEngine:
 
 
 class Shard:
-    def __init__(self, scr, rank: int = 0, world: int = 1, dist=None, torch=None, engine=None):
+    """same_stream=True: the engine launches on torch's CURRENT stream (the caller did scr.set_stream(that stream)), so the
+    engine's kernels and the collectives are ordered by the stream itself and a step needs no host synchronisation
+    between them: a barrier is a one-element all-reduce in stream order.  Otherwise every hand-over is fenced on the host."""
+
+    def __init__(self, scr, rank: int = 0, world: int = 1, dist=None, torch=None, engine=None, same_stream: bool = False,
+                 force_nccl: bool = False):
         self.rank, self.world, self.dist, self.torch = rank, world, dist, torch
         self.eng = engine if engine is not None else GpuEngine(scr, torch)
-        self.last_stage_ms = np.zeros(11)
+        self.same_stream = same_stream and engine is None
+        self.last_stage_ms = np.zeros(13)
         self.last_peaks = 0
         self.last_counts = {}
         self.last_wall_ms = {}
-        self.p2p = self._open_peers()
+        self.p2p = False if force_nccl else self._open_peers()
+        self._tiny = None
+        self._spans = []
 
     def _open_peers(self) -> bool:
         """Maps every rank's count table into this process (CUDA IPC) so that the count exchange can run as one kernel
@@ -127,24 +135,53 @@ class Shard:
     def _fence(self, t) -> None:
         """The engine's kernels run on its own stream: make the host wait for the collective (which torch
         orders after the current stream) before the next engine call touches the buffer."""
+        if self.same_stream:
+            return
         if t is not None and t.is_cuda:
             self.torch.cuda.current_stream(t.device).synchronize()
+
+    def _engine_done(self) -> None:
+        if not self.same_stream:
+            self.eng.sync()
+
+    def _barrier(self) -> None:
+        if not self.same_stream:
+            self.dist.barrier()
+            return
+        if self._tiny is None:
+            self._tiny = self.torch.zeros(1, dtype=self.torch.int32, device=self._dev())
+        self.dist.all_reduce(self._tiny)                       # in stream order: completes once every rank has reached it
+
+    def _span(self, name):
+        """Device time of an exchange, from CUDA events on the shared stream (read at the end of the step)."""
+        if not self.same_stream:
+            return None
+        ev = (name, self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True))
+        ev[1].record()
+        self._spans.append(ev)
+        return ev
+
+    @staticmethod
+    def _end(ev):
+        if ev is not None:
+            ev[2].record()
 
     # ---- exchanges
     def exchange_counts(self) -> None:
         """count := min(3, sum over ranks), on every rank."""
         if self.p2p:                                           # one kernel per rank over peer memory, between two barriers
-            self.eng.sync()
-            self.dist.barrier()                                # every rank's S1 has finished: all tables are final
+            self._engine_done()
+            self._barrier()                                    # every rank's S1 has finished: all tables are final
             self.eng.count_exchange_p2p()
-            self.eng.sync()
-            self.dist.barrier()                                # every slice has been written into every table
+            self._engine_done()
+            self._barrier()                                    # every slice has been written into every table
             return
         tab = self.eng.table()
         n = tab.numel()
         w = self.world
         if n % 4:
             raise ValueError("count table is not a whole number of 32-bit words")
+        self._engine_done()
         # slice j (whole words; the slices differ by at most one word when w does not divide the table) belongs to rank j
         spans = [tuple(4 * x for x in split_range(n // 4, w, j)) for j in range(w)]
         sizes = [hi - lo for lo, hi in spans]
@@ -155,8 +192,8 @@ class Shard:
         for j in range(w):
             if j != self.rank and mine_n:
                 self.eng.merge_into(lo, recv[j * mine_n:(j + 1) * mine_n])
-        self.eng.sync()
-        if w & (w - 1) == 0 and len(set(sizes)) == 1:
+        self._engine_done()
+        if len(set(sizes)) == 1:
             mine = tab[lo:lo + mine_n].clone()
             self.dist.all_gather_into_tensor(tab, mine)
         else:                                                  # uneven slices: one broadcast per owner
@@ -165,14 +202,22 @@ class Shard:
                     self.dist.broadcast(tab[a:b], src=j)
         self._fence(tab)
 
-    def exchange_hit_bits(self, ntiles: int) -> None:
+    def tile_block(self, ntiles: int):
+        """Equal blocks of tiles per rank (the last ones may be short or empty): rank r owns [r * B, (r + 1) * B) cut at ntiles."""
+        B = -(-ntiles // self.world)
+        lo = min(ntiles, self.rank * B)
+        return B, lo, min(ntiles, lo + B)
+
+    def exchange_hit_bits(self, ntiles: int, which=(0, 1)) -> None:
+        """All-gather, in place, of the per-rank tile blocks of the hit-bit arrays (the arrays are padded to world * B tiles)."""
         tb = self.eng.tile_bytes()
-        for which in (0, 1):
-            bits = self.eng.hit_bits(which)
-            for r in range(self.world):
-                lo, hi = split_range(ntiles, self.world, r)
-                if hi > lo:
-                    self.dist.broadcast(bits[lo * tb:hi * tb], src=r)
+        B, _, _ = self.tile_block(ntiles)
+        self._engine_done()
+        for w_ in which:
+            bits = self.eng.hit_bits(w_)
+            if bits.numel() < self.world * B * tb:
+                raise ValueError("hit-bit array lacks the padding for equal tile blocks")
+            self.dist.all_gather_into_tensor(bits[: self.world * B * tb], bits[self.rank * B * tb:(self.rank + 1) * B * tb])
             self._fence(bits)
 
     # ---- the pass
@@ -183,9 +228,11 @@ class Shard:
         needed up front for the Q15 budget), before_s2() must make the index resident.  That is the stage order of the
         reference's main() (E:1426-1507), which lets host->device copies hide behind S1."""
         eng, w = self.eng, self.world
-        ms = np.zeros(11)
+        ms = np.zeros(13)
         wall = {}
         t0 = time.perf_counter()
+        self._spans = []
+        deferred = hasattr(eng, "set_deferred")
 
         def lap(name, since):
             now = time.perf_counter()
@@ -193,6 +240,8 @@ class Shard:
             return now
 
         eng.reset()
+        if deferred:
+            eng.set_deferred(True)
         nrec1 = eng.reads_records(0)
         t = lap("reset", t0)
         info = self._all_gather_ints([nrec1, eng.reads_seq_bases(0), size1, eng.reads_bytes(1) if size2 is None else size2])
@@ -215,43 +264,62 @@ class Shard:
             t = lap("s1", t)
             eng.set_sampling(ratio, seed, rand_skip)                   # fq2 may hold more records than fq1: cover them
         n2 = eng.s1_count(1, budget2) if budget2 >= 0 else 0
-        t = t1 = lap("s1", t)
+        t = lap("s1", t)
         if w > 1:
+            ev = self._span("exchange_counts")
             self.exchange_counts()
+            self._end(ev)
             t = lap("exchange_counts", t)
         if before_s2 is not None:
             before_s2()
             t = lap("index_upload", t)
         if w > 1 and eng.sharded_s2:
             nt = eng.s2_tiles()
-            lo, hi = split_range(nt, w, self.rank)
+            _, lo, hi = self.tile_block(nt)
             eng.s2_gather(lo, hi)
-            eng.sync()
             t = lap("s2_gather", t)
+            ev = self._span("exchange_hit_bits")
             self.exchange_hit_bits(nt)
+            self._end(ev)
+            t = lap("exchange_hit_bits", t)
+            eng.s2_mark(match)
+            eng.s2_complete(lo, hi)
+            t = lap("s2_complete", t)
+            ev = self._span("exchange_single")
+            self.exchange_hit_bits(nt, which=(0,))
+            self._end(ev)
             t = lap("exchange_hit_bits", t)
             n_peaks = eng.s2_finish(hit, match, max_peak)
             t = lap("s2_finish", t)
         else:
             n_peaks = eng.s2_peaks(hit, match, max_peak)
             t = lap("s2", t)
-        t2 = time.perf_counter()
         n3 = eng.s3_pairs()
         t = lap("s3", t)
         if w > 1 and n_peaks > 0:
-            eng.sync()
+            self._engine_done()
             filt = eng.peak_filter()
+            ev = self._span("reduce_filter")
             self.dist.all_reduce(filt, op=self.dist.ReduceOp.MAX)
+            self._end(ev)
             self._fence(filt)
             t = lap("reduce_filter", t)
         text = eng.intervals()
         t = lap("intervals", t)
+        if deferred:
+            n1, n2, n3 = eng.deferred_counts()
+            eng.set_deferred(False)
         self.last_wall_ms = wall
         st = eng.stage_ms()
         ms[:6] = st[:6]
         if len(st) >= 9:
             ms[8:11] = st[6:9]                                          # S1 in streams: hash, split, leaf-apply kernels
-        ms[6] = 1000 * (t2 - t1) - st[2] - st[3] if w > 1 else 0.0
+        if len(st) >= 12:
+            ms[11:13] = st[10:12]                                       # S2 peak registration, S3 vote
+        ms[6] = sum(a.elapsed_time(b) for _, a, b in self._spans) if self._spans else 0.0
+        self.last_exchange_ms = {}
+        for name, a, b in self._spans:
+            self.last_exchange_ms[name] = self.last_exchange_ms.get(name, 0.0) + a.elapsed_time(b)
         self.last_stage_ms = ms
         self.last_peaks = int(n_peaks)
         self.last_counts = {"s1": (int(n1), int(n2)), "s3": int(n3), "ratio": ratio, "ordinal_base": base}

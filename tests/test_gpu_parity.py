@@ -570,3 +570,114 @@ def test_ordinal_base_makes_shards_equal_the_whole_sample(workdir):
         _, f_ab = parts.peaks()                                  # the filter accumulates across s3 calls
         assert n3 == n3_whole
         assert np.array_equal(f_whole >= 1, f_ab >= 1) and not np.any((f_b >= 1) & ~(f_ab >= 1))
+
+
+# ------------------------------------------------------------------ S2 in its steps, count merge, S3 vote paths
+def _screened(case, workdir, **env):
+    """One GPU context with `case` loaded and S1 done; returns (screen, oracle with S1 + S2 done, ratio, skip, paths)."""
+    fa, fq1, fq2, o, s, idx, lenp, skip = _stage_run(case, workdir)
+    b1, b2 = _read(fq1), _read(fq2)
+    s.reads_upload(0, b1); s.reads_upload(1, b2)
+    ratio = s.sample_ratio(case.sample)
+    if ratio < 100:
+        o.fill_random(max(s.reads_records(0), s.reads_records(1)) + 8)
+    s.set_sampling(ratio, case.seed, skip)
+    o.s1_count(fq1, len(b1), ratio); o.s1_count(fq2, len(b1), ratio)
+    s.s1_count(0, len(b1)); s.s1_count(1, len(b1))
+    return s, o, ratio, (fq1, fq2, idx)
+
+
+@pytest.mark.parametrize("name", ["base_k24", "base_k20", "noisy", "shorts_bp", "base_k24_e4", "base_k31_e1"])
+def test_s2_in_steps_over_tile_ranges_equals_the_oracle(name, workdir):
+    """gather / complete on tile ranges (what each rank of the multi-GPU plan runs) + mark + finish == one s2_peaks ==
+    the oracle: the short-circuit trio gather, the hot/needed tile marking and the needed-tile passes drop nothing."""
+    case = fixtures.BY_NAME[name]
+    s, o, ratio, (fq1, fq2, idx) = _screened(case, workdir)
+    with s:
+        npo = o.s2_peaks(idx, case.hit, case.match, case.max_peak)
+        nt = s.s2_tiles()
+        cuts = sorted({0, nt // 3, nt // 3 + 1, (2 * nt) // 3, nt})
+        for a, b in zip(cuts, cuts[1:]):
+            s.s2_gather(a, b)
+        s.s2_mark(case.match)
+        for a, b in zip(reversed(cuts[:-1]), reversed(cuts[1:])):
+            s.s2_complete(a, b)
+        assert s.s2_finish(case.hit, case.match, case.max_peak) == npo
+        assert 0 <= s.s2_needed_tiles() <= nt
+        assert o.raw_positions() == s.flagged_positions()
+        loci, _ = s.peaks()
+        assert np.array_equal(o.peak_loci(), loci)
+        assert np.array_equal(o.peak_kmer(), s.peak_kmer())
+        so, sg = o.s3_pairs(fq1, fq2, ratio), s.s3_pairs()
+        assert so == sg
+        assert np.array_equal(o.peak_filter() >= 1, s.peaks()[1] >= 1)
+    o.close()
+
+
+def test_s2_marks_few_tiles_when_nothing_is_saturated(workdir):
+    """A sample that shares nothing with the reference: no hot tile, no needed tile, no peak -- and S2 says so without
+    visiting the windows."""
+    case = fixtures.BY_NAME["base_k24"]
+    fa, fq1, fq2 = fixtures.materialize(case.data, workdir)
+    rng = np.random.default_rng(5)
+    other = synth.Reference(["x"], [synth.random_genome(rng, 300000)])
+    with api.Screen(case.k, case.e) as s:
+        cc, _ = api.random_coder(case.seed, case.k, case.e)
+        s.set_coder(cc)
+        s.index_build(b">x\n" + other.seqs[0].tobytes() + b"\n")
+        b1, b2 = _read(fq1), _read(fq2)
+        s.reads_upload(0, b1); s.reads_upload(1, b2)
+        s.set_sampling(100.0, case.seed, 0)
+        s.s1_count(0, len(b1)); s.s1_count(1, len(b1))
+        assert s.s2_peaks(case.hit, case.match, case.max_peak) == 0
+        assert s.s2_needed_tiles() == 0 and s.flagged_positions() == 0
+        s.s3_pairs()
+        assert s.intervals() == b"1\t1\t1\n"
+
+
+@pytest.mark.parametrize("k", [16, 24])
+def test_count_merge_is_a_saturating_add(k, workdir):
+    """lhgt_count_merge on the packed 2-bit tables (the NCCL form of the multi-GPU count exchange) == min(3, a + b)."""
+    case = fixtures.BY_NAME["base_k24"]
+    fa, fq1, fq2 = fixtures.materialize(case.data, workdir)
+    b1, b2 = _read(fq1), _read(fq2)
+    cc, _ = api.random_coder(3, k, 3)
+    import torch
+    with api.Screen(k, 3) as a, api.Screen(k, 3) as b:
+        for s, buf in ((a, b1), (b, b2)):
+            s.set_coder(cc)
+            s.reads_upload(0, buf)
+            s.set_sampling(100.0, 1, 0)
+            s.s1_count(0, len(buf))
+            if s is b:
+                s.s1_count(0, len(buf))                    # twice: plenty of 2s and 3s on this side
+        ta, tb = a.count_table(), b.count_table()
+        assert ta.max() == 3 or tb.max() == 3
+        ptr, n = b.dev_count_table()
+        half = (n // 8) * 4                                # a word-aligned split: two merges of sub-ranges
+        a.count_merge(ptr, half, 0)
+        a.count_merge(ptr + half, n - half, half // 4)
+        a.sync()
+        assert np.array_equal(a.count_table(), np.minimum(3, ta.astype(np.int32) + tb).astype(np.uint8))
+
+
+@pytest.mark.parametrize("name", ["base_k20", "noisy"])
+def test_s3_vote_paths_agree(name, workdir, monkeypatch):
+    """S3's order-dependent vote runs in s3_vote_kernel (one thread per pair, candidates handed over through an arena);
+    a 1 MiB arena forces several batches and overflow into the in-warp vote, 0 disables the hand-over: same verdicts."""
+    case = fixtures.BY_NAME[name]
+    s, o, ratio, (fq1, fq2, idx) = _screened(case, workdir)
+    with s:
+        assert o.s2_peaks(idx, case.hit, case.match, case.max_peak) == s.s2_peaks(case.hit, case.match, case.max_peak)
+        o.s3_pairs(fq1, fq2, ratio)
+        want = o.peak_filter() >= 1
+        assert want.any()
+        for arena_mb in (None, "1", "0"):
+            if arena_mb is None:
+                monkeypatch.delenv("LHGT_S3_ARENA_MB", raising=False)
+            else:
+                monkeypatch.setenv("LHGT_S3_ARENA_MB", arena_mb)
+            s.s2_finish(case.hit, case.match, case.max_peak)      # clears the verdicts (same peaks)
+            s.s3_pairs()
+            assert np.array_equal(want, s.peaks()[1] >= 1), arena_mb
+    o.close()

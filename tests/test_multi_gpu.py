@@ -1,0 +1,53 @@
+"""GPU, world_size >= 2: the sharded plan of localhgt_b200/multi.py with the REAL engine -- count exchange as one kernel
+over NVLink peer memory (CUDA IPC) and in its NCCL form, tile-sharded S2 gather/complete with the in-place all-gather of
+the hit-bit arrays, verdict max-reduce -- against ONE run of the scalar oracle over the whole files (tests/multi_worker.py).
+Skipped on boxes with a single GPU (`gpurun --gpus 2` provides two)."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+N_GPUS = torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+def _port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _run(world, work, case, form, env=None):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(_port()), os.path.join(ROOT, "tests", "multi_worker.py"), work, case, form]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, **(env or {})))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert f"OK {case} {form} world={world}" in r.stdout
+
+
+@pytest.mark.skipif(N_GPUS < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("form", ["p2p", "nccl"])
+@pytest.mark.parametrize("case", ["base_k24", "fq2_longer", "half_build", "base_k20", "noisy"])
+def test_two_gpus_equal_the_oracle(case, form, tmp_path):
+    _run(2, str(tmp_path), case, form)
+
+
+@pytest.mark.skipif(N_GPUS < 2, reason="needs 2 GPUs")
+def test_two_gpus_stream_counting_path(tmp_path):
+    """S1 through hash streams (forced at k = 24 with 2^12-counter leaves) under the peer-memory exchange."""
+    _run(2, str(tmp_path), "base_k24", "p2p", env={"LHGT_LEAF_LOG2": "12", "LHGT_TEST_S1_MODE": "2"})
+
+
+@pytest.mark.skipif(N_GPUS < 3, reason="needs 3 GPUs")
+@pytest.mark.parametrize("form", ["p2p", "nccl"])
+def test_three_gpus_uneven_slices(form, tmp_path):
+    _run(3, str(tmp_path), "base_k24", form)
+
+
+@pytest.mark.skipif(N_GPUS < 4, reason="needs 4 GPUs")
+def test_four_gpus(tmp_path):
+    _run(4, str(tmp_path), "noisy", "p2p")
