@@ -120,9 +120,14 @@ int      lhgt_index_load_file(lhgt_ctx* c, const char* index_path);
 
 /* Copies one FASTQ file image (mate 0 = fq1, 1 = fq2) from host memory to HBM and locates its
  * records there (newline scan).  lhgt_reads_attach_device does the same for bytes that are already
- * resident on this device (no copy; the caller keeps them alive). */
+ * resident on this device (no copy; the caller keeps them alive).  The device buffer must be 16-byte aligned and extend
+ * to the next 16-byte boundary at or beyond n: reads are staged in whole 16-byte granules. */
 int      lhgt_reads_upload(lhgt_ctx* c, int mate, const uint8_t* fq, uint64_t n);
 int      lhgt_reads_attach_device(lhgt_ctx* c, int mate, const void* dev_fq, uint64_t n);
+/* The same from a file, streamed through a ring of three 64 MiB pinned staging buffers (disk read, host->device copy and
+ * whatever the GPU is computing overlap; pinned host memory stays bounded by the ring whatever the file size).
+ * lhgt_index_build_file and lhgt_index_load_file read their files the same way. */
+int      lhgt_reads_upload_file(lhgt_ctx* c, int mate, const char* path);
 long     lhgt_reads_records(const lhgt_ctx* c, int mate);
 uint64_t lhgt_reads_seq_bases(const lhgt_ctx* c, int mate);   /* sum of sequence-line lengths */
 uint64_t lhgt_reads_bytes(const lhgt_ctx* c, int mate);       /* size of the resident FASTQ image */

@@ -69,6 +69,7 @@ SYMBOLS = {
     "lhgt_index_load_file": (_i, [_vp, _s]),
     "lhgt_reads_upload": (_i, [_vp, _i, _vp, _u64]),
     "lhgt_reads_prefetch": (_i, [_vp, _i, _vp, _u64]),
+    "lhgt_reads_upload_file": (_i, [_vp, _i, _s]),
     "lhgt_index_prefetch": (_i, [_vp, _vp, _u64]),
     "lhgt_reads_attach_device": (_i, [_vp, _i, _vp, _u64]),
     "lhgt_reads_records": (_l, [_vp, _i]),
@@ -295,6 +296,9 @@ class Screen:
 
     def reads_upload_ptr(self, mate: int, host_ptr: int, n: int) -> None:
         _check(self._L.lhgt_reads_upload(self._h, mate, host_ptr, n))
+
+    def reads_upload_file(self, mate: int, path: str) -> None:
+        _check(self._L.lhgt_reads_upload_file(self._h, mate, path.encode()))
 
     def reads_attach_device(self, mate: int, dev_ptr: int, n: int) -> None:
         _check(self._L.lhgt_reads_attach_device(self._h, mate, dev_ptr, n))

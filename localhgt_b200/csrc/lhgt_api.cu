@@ -164,6 +164,7 @@ struct lhgt_ctx {
     uint32_t* d_cands = nullptr; int32_t* d_tally = nullptr; S3Scratch scratch{};
     uint32_t* d_vote_table = nullptr; uint32_t vote_contigs = 0;
 
+    uint8_t* ring[3] = {nullptr, nullptr, nullptr}; cudaEvent_t ring_free[3] = {nullptr, nullptr, nullptr};   // pinned staging ring of the file readers
     bool deferred = false;                   // stages leave their counters on the device (lhgt_set_deferred)
     int s1_mode = 0;                         // 0 auto, 1 direct probes, 2 binned streams (lhgt_set_s1_mode)
     uint32_t *d_bin_pool_a = nullptr, *d_bin_pool_b = nullptr, *d_bin_cursor = nullptr;   // hash streams, leaf streams, their cursors
@@ -177,6 +178,9 @@ struct lhgt_ctx {
     long launches = 0;
 };
 
+struct Reads;
+static int index_reads(lhgt_ctx* c, Reads& r, int last_byte, uint64_t tail_start);
+static uint64_t last_line_start(const uint8_t* p, uint64_t n);
 static int start_prefetch(lhgt_ctx* c, lhgt_ctx::Prefetch& p, void* dst, const void* host, uint64_t n);
 static bool adopt_prefetch(lhgt_ctx* c, lhgt_ctx::Prefetch& p, const void* host, uint64_t n);
 
@@ -373,6 +377,7 @@ extern "C" void lhgt_destroy(lhgt_ctx* c) {
     c->rand_m_buf.release(); delete c->rand_gen;
     dev_free(c->d_cands); dev_free(c->d_tally); dev_free(c->d_vote_table); dev_free(c->d_counter); dev_free(c->d_err); dev_free(c->d_misc);
     dev_free(c->d_bin_pool_a); dev_free(c->d_bin_pool_b); dev_free(c->d_bin_cursor);
+    for (int i = 0; i < 3; ++i) { if (c->ring[i]) cudaFreeHost(c->ring[i]); if (c->ring_free[i]) cudaEventDestroy(c->ring_free[i]); }
     c->fasta_buf.release();
     c->contig_first_buf.release(); c->s3_tables_buf.release(); c->s3_arena_buf.release(); c->s3_queue_buf.release();
     c->keep_cnt_buf.release(); c->keep_base_buf.release(); c->keep_tmp_buf.release(); c->keep_out_buf.release();
@@ -792,13 +797,87 @@ static int spill(const char* path, const void* p, size_t n) {
     return 0;
 }
 
+// Reads a file into device memory through a ring of three pinned staging buffers: the disk read of one chunk overlaps the
+// host->device copies of the previous ones (copy stream), and the pinned host memory is the ring (3 x 64 MiB) whatever the file
+// size -- the reference walks its inputs with getline in bounded memory (E:1020-1034, 356-409, 761-831); so do we.  `tail`
+// (nullable) receives the last <= 64 KiB of the file (lhgt_reads_upload needs the last line).  The compute stream is made to
+// wait for the last copy.
+static const size_t kRingChunk = (size_t)64 << 20;
+
+static size_t ring_chunk() {
+    const char* g = getenv("LHGT_RING_KB");                       // test knob: small chunks exercise the ring on small files
+    size_t kb = g ? (size_t)atol(g) : 0;
+    return kb ? std::min(kRingChunk, std::max<size_t>(kb << 10, 4096)) : kRingChunk;
+}
+
+static int ring_ready(lhgt_ctx* c) {
+    for (int i = 0; i < 3; ++i) {
+        if (!c->ring[i] && cudaHostAlloc((void**)&c->ring[i], kRingChunk, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(LHGT_E_NOMEM, "cannot allocate the pinned staging ring (3 x %zu MiB)", kRingChunk >> 20);
+        }
+        if (!c->ring_free[i]) CU(cudaEventCreateWithFlags(&c->ring_free[i], cudaEventDisableTiming));
+    }
+    return 0;
+}
+
+static int file_size_of(const char* path, size_t* n) {
+    struct stat st;
+    if (stat(path, &st) != 0) return fail(LHGT_E_IO, "cannot stat %s", path);
+    *n = (size_t)st.st_size;
+    return 0;
+}
+
+static int stream_file_to_device(lhgt_ctx* c, const char* path, uint8_t* d_dst, size_t n, std::vector<uint8_t>* tail) {
+    int rc = ring_ready(c);
+    if (rc) return rc;
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return fail(LHGT_E_IO, "cannot open %s", path);
+    const size_t chunk = ring_chunk();
+    cudaEvent_t after = nullptr;
+    if (cudaEventCreateWithFlags(&after, cudaEventDisableTiming) != cudaSuccess) { close(fd); return fail(LHGT_E_CUDA, "event create failed"); }
+    cudaEventRecord(after, c->st);                                  // whatever still reads the destination on the compute stream
+    cudaStreamWaitEvent(c->copy_st, after, 0);
+    if (tail) tail->clear();
+    size_t done = 0;
+    int slot = 0;
+    rc = 0;
+    while (done < n) {
+        size_t m = std::min(chunk, n - done);
+        if (cudaEventSynchronize(c->ring_free[slot]) != cudaSuccess) { rc = fail(LHGT_E_CUDA, "staging ring failed"); break; }   // its previous copy has left
+        size_t got = 0;
+        while (got < m) {
+            ssize_t r = pread(fd, c->ring[slot] + got, m - got, (off_t)(done + got));
+            if (r <= 0) break;
+            got += (size_t)r;
+        }
+        if (got != m) { rc = fail(LHGT_E_IO, "short read on %s", path); break; }
+        const size_t from = n > 65536 ? n - 65536 : 0;
+        if (tail && done + m > from) {                              // this chunk reaches into the last 64 KiB
+            size_t a = std::max(from, done) - done;
+            tail->insert(tail->end(), c->ring[slot] + a, c->ring[slot] + m);
+        }
+        if (cudaMemcpyAsync(d_dst + done, c->ring[slot], m, cudaMemcpyHostToDevice, c->copy_st) != cudaSuccess ||
+            cudaEventRecord(c->ring_free[slot], c->copy_st) != cudaSuccess) { rc = fail(LHGT_E_CUDA, "host->device copy failed"); break; }
+        done += m;
+        slot = (slot + 1) % 3;
+    }
+    close(fd);
+    if (!rc) { cudaEventRecord(after, c->copy_st); cudaStreamWaitEvent(c->st, after, 0); }
+    cudaEventDestroy(after);
+    return rc;
+}
+
 extern "C" int lhgt_index_build_file(lhgt_ctx* c, const char* fasta_path, const char* index_path, const char* len_path) {
     if (!c || !fasta_path || !index_path || !len_path) return fail(LHGT_E_ARG, "null pointer");
-    HostFile fa;
-    int rc = slurp(fasta_path, fa, false);
+    CU(cudaSetDevice(c->device));
+    size_t n = 0;
+    int rc = file_size_of(fasta_path, &n);
     if (rc) return rc;
-    if ((rc = lhgt_index_build(c, fa.p, fa.n))) return rc;
-    fa.release();
+    if ((rc = c->fasta_buf.reserve(n + 64)) || (n && (rc = stream_file_to_device(c, fasta_path, c->fasta_buf.p, n, nullptr)))) return rc;
+    rc = index_build_from_device(c, c->fasta_buf.p, n);
+    if (!c->keep_fasta_buf) c->fasta_buf.release();
+    if (rc) return rc;
     // stream the image out through two pinned staging buffers
     FILE* f = fopen(index_path, "wb");
     if (!f) return fail(LHGT_E_IO, "cannot create %s", index_path);
@@ -837,10 +916,59 @@ extern "C" int lhgt_index_build_file(lhgt_ctx* c, const char* fasta_path, const 
 
 extern "C" int lhgt_index_load_file(lhgt_ctx* c, const char* index_path) {
     if (!c || !index_path) return fail(LHGT_E_ARG, "null pointer");
-    HostFile f;
-    int rc = slurp(index_path, f, true);
+    CU(cudaSetDevice(c->device));
+    size_t n = 0;
+    int rc = file_size_of(index_path, &n);
     if (rc) return rc;
-    return lhgt_index_upload(c, f.p, f.n);
+    if (n % 4) return fail(LHGT_E_FORMAT, "index image size is not a multiple of 4");
+    drop_index(c);
+    // header + the record structure (E:921-972): one 4-byte length per contig, read at its offset
+    int fd = open(index_path, O_RDONLY);
+    if (fd < 0) return fail(LHGT_E_IO, "cannot open %s", index_path);
+    uint32_t header[LHGT_CODER_SLOTS];
+    uint64_t nwords = n / 4;
+    if (nwords < LHGT_CODER_SLOTS || pread(fd, header, sizeof header, 0) != (ssize_t)sizeof header) { close(fd); return fail(LHGT_E_FORMAT, "index image shorter than its 1200-byte header"); }
+    int16_t cc[LHGT_CODER_SLOTS];
+    lhgt_header_to_coder(header, cc);
+    if (!coder_ok(cc, c->k, c->e)) { close(fd); return fail(LHGT_E_FORMAT, "index header does not describe k=%d e=%d", c->k, c->e); }
+    memcpy(c->cc, cc, sizeof cc);
+    make_hashp(c);
+    c->contigs.clear();
+    for (uint64_t at = LHGT_CODER_SLOTS; at < nwords;) {
+        uint32_t len = 0;
+        if (pread(fd, &len, 4, (off_t)(at * 4)) != 4) { close(fd); return fail(LHGT_E_IO, "short read on %s", index_path); }
+        if (len <= (uint32_t)c->k || len > 178000000u) { close(fd); return fail(LHGT_E_FORMAT, "bad contig length %u at word %llu", len, (unsigned long long)at); }
+        uint64_t span = (uint64_t)(len - c->k + 1) * c->e;
+        if (at + 1 + span > nwords) { close(fd); return fail(LHGT_E_FORMAT, "index image truncated inside a contig record"); }
+        Contig g{};
+        g.hash_word = at + 1; g.seq_off = 0; g.len = len;
+        c->contigs.push_back(g);
+        at += 1 + span;
+    }
+    close(fd);
+    if ((rc = alloc_image(c, nwords)) || (rc = stream_file_to_device(c, index_path, (uint8_t*)c->d_image, n, nullptr))) return rc;
+    return finish_index_tables(c);
+}
+
+extern "C" int lhgt_reads_upload_file(lhgt_ctx* c, int mate, const char* path) {
+    if (!c || mate < 0 || mate > 1 || !path) return fail(LHGT_E_ARG, "lhgt_reads_upload_file: bad argument");
+    CU(cudaSetDevice(c->device));
+    size_t n = 0;
+    int rc = file_size_of(path, &n);
+    if (rc) return rc;
+    Reads& r = c->reads[mate];
+    drop_reads(r);
+    if ((rc = r.fq_buf.reserve(n + 64))) return rc;
+    r.d_fq = r.fq_buf.p; r.owned = true; r.n = n;
+    std::vector<uint8_t> tail;
+    if (n && (rc = stream_file_to_device(c, path, r.fq_buf.p, n, &tail))) return rc;
+    uint64_t tail_start = 0;
+    int last = '\n';
+    if (n) {
+        last = tail.back();
+        if (last != '\n') tail_start = (n - tail.size()) + last_line_start(tail.data(), tail.size());
+    }
+    return index_reads(c, r, last, tail_start);
 }
 
 // ------------------------------------------------------------------------------------------------ reads
@@ -1621,6 +1749,38 @@ extern "C" long lhgt_launch_count(const lhgt_ctx* c) { return c ? c->launches : 
 // ------------------------------------------------------------------------------------------------ the program
 static bool file_exists(const char* p) { struct stat st; return stat(p, &st) == 0; }
 
+// First line of a text file (without its newline).
+static bool first_line(const char* path, std::string* out) {
+    FILE* f = fopen(path, "rb");
+    if (!f) return false;
+    out->clear();
+    int ch;
+    while ((ch = fgetc(f)) != EOF && ch != '\n') out->push_back((char)ch);
+    fclose(f);
+    return true;
+}
+
+// E:368-399 at -t 1: when the first read ids of fq1 and fq2 differ, the reference re-reads fq2 from byte 1 line by line until
+// a line carries fq1's first id and pairs fq1's lines with fq2's from there on.  Returns the index of that line, -1 if none.
+static long find_line_with_id(const char* path, const std::string& id) {
+    FILE* f = fopen(path, "rb");
+    if (!f) return -1;
+    std::string line;
+    long idx = 0;
+    int ch = fgetc(f);                                             // seekg(1): the first line is read without its first byte
+    bool more = ch != EOF;
+    while (more) {
+        line.clear();
+        while ((ch = fgetc(f)) != EOF && ch != '\n') line.push_back((char)ch);
+        more = ch != EOF;
+        if (!more && line.empty()) break;
+        if (std::string(line.data(), read_id_len((const uint8_t*)line.data(), line.size())) == id) { fclose(f); return idx; }
+        ++idx;
+    }
+    fclose(f);
+    return -1;
+}
+
 extern "C" int lhgt_extract_ref(const lhgt_args* a, lhgt_stats* stats) {
     if (!a || !a->fq1 || !a->fq2 || !a->fasta || !a->interval) return fail(LHGT_E_ARG, "lhgt_extract_ref: null argument");
     lhgt_stats st;
@@ -1631,18 +1791,30 @@ extern "C" int lhgt_extract_ref(const lhgt_args* a, lhgt_stats* stats) {
         printf("kmer length is %d\nseed is %u\nnum of hash functions is %d\n", a->k, a->seed, a->e);
         if (a->threads != 1) printf("note: -t %d accepted; results follow the reference's single-thread semantics\n", a->threads);
     }
+    // pairing of the two files, before any work (E:368-399)
+    long fq2_record_shift = 0;
+    {
+        std::string l1, l2;
+        if (!first_line(a->fq1, &l1)) return fail(LHGT_E_IO, "cannot open %s", a->fq1);
+        if (!first_line(a->fq2, &l2)) return fail(LHGT_E_IO, "cannot open %s", a->fq2);
+        std::string id1(l1.data(), read_id_len((const uint8_t*)l1.data(), l1.size())), id2(l2.data(), read_id_len((const uint8_t*)l2.data(), l2.size()));
+        if (!l1.empty() && !l2.empty() && id1 != id2) {
+            long line = find_line_with_id(a->fq2, id1);
+            if (line < 0 || line % 4 != 0)
+                return fail(LHGT_E_UNPAIRED, "first records of fq1 and fq2 carry different read ids and fq2 holds no record named like fq1's first");
+            fq2_record_shift = line / 4;
+            if (say) printf("%s\t<=>\t%s (fq2 record %ld)\n", id1.c_str(), id1.c_str(), fq2_record_shift);
+        }
+    }
     lhgt_ctx* c = nullptr;
     int rc = lhgt_create(&c, a->device, a->k, a->e);
     if (rc) return rc;
     struct Guard { lhgt_ctx* c; ~Guard() { lhgt_destroy(c); } } guard{c};
+    lhgt_set_deferred(c, 1);                                              // the host streams the next input while a stage computes
 
-    // inputs: both FASTQ images cross PCIe once and stay in HBM for S1 and S3.  The copies run on the copy stream:
-    // fq1's while fq2 is still being read from disk, fq2's and the index image's behind S1 of fq1.
+    // inputs cross PCIe once, streamed through the pinned ring, and stay in HBM for S1 and S3
     t = now_s();
-    HostFile f1, f2, fidx;
-    if ((rc = slurp(a->fq1, f1, true)) || (rc = lhgt_reads_prefetch(c, 0, f1.p, f1.n))) return rc;
-    if ((rc = slurp(a->fq2, f2, true)) || (rc = lhgt_reads_prefetch(c, 1, f2.p, f2.n))) return rc;
-    if ((rc = lhgt_reads_upload(c, 0, f1.p, f1.n))) return rc;
+    if ((rc = lhgt_reads_upload_file(c, 0, a->fq1))) return rc;
     st.seconds[1] = now_s() - t;
     uint64_t size1 = c->reads[0].n;                                       // E:1419
 
@@ -1671,7 +1843,14 @@ extern "C" int lhgt_extract_ref(const lhgt_args* a, lhgt_stats* stats) {
         st.index_built = 1;
     } else {
         if (say) printf("Reference index is detected.\n");
-        if ((rc = slurp(index_path.c_str(), fidx, true)) || (rc = lhgt_index_prefetch(c, fidx.p, fidx.n))) return rc;
+        // the header's coder governs S1 as well (E:1417 re-reads it before read_fastq); the image itself follows behind S1
+        uint32_t header[LHGT_CODER_SLOTS];
+        int fd = open(index_path.c_str(), O_RDONLY);
+        if (fd < 0 || pread(fd, header, sizeof header, 0) != (ssize_t)sizeof header) { if (fd >= 0) close(fd); return fail(LHGT_E_FORMAT, "index image shorter than its 1200-byte header"); }
+        close(fd);
+        int16_t cc[LHGT_CODER_SLOTS];
+        lhgt_header_to_coder(header, cc);
+        if ((rc = lhgt_set_coder(c, cc))) return rc;
         index_pending = true;
     }
     st.seconds[2] = now_s() - t;
@@ -1681,20 +1860,15 @@ extern "C" int lhgt_extract_ref(const lhgt_args* a, lhgt_stats* stats) {
 
     t = now_s();
     long n;
-    if ((n = lhgt_s1_count(c, 0, size1)) < 0) return (int)n;
-    st.reads_s1[0] = n;
-    if ((rc = lhgt_reads_upload(c, 1, f2.p, f2.n))) return rc;
+    if ((n = lhgt_s1_count(c, 0, size1)) < 0) return (int)n;               // enqueued; fq2 streams in meanwhile
+    if ((rc = lhgt_reads_upload_file(c, 1, a->fq2))) return rc;
     if ((rc = lhgt_set_sampling(c, ratio, a->seed, rand_skip))) return rc;   // fq2 may hold more records than fq1
     if ((n = lhgt_s1_count(c, 1, size1)) < 0) return (int)n;               // Q15: fq1's size bounds fq2 too
-    st.reads_s1[1] = n;
-    f1.release(); f2.release();
     st.seconds[3] = now_s() - t;
-    if (say) printf("K-mer counting is finished.\nconsidered read pair num in kmer counting:%ld\n", (st.reads_s1[0] + st.reads_s1[1]) / 2);
 
     if (index_pending) {
         double t2 = now_s();
-        if ((rc = lhgt_index_upload(c, fidx.p, fidx.n))) return rc;
-        fidx.release();
+        if ((rc = lhgt_index_load_file(c, index_path.c_str()))) return rc;
         st.seconds[2] += now_s() - t2;
     }
 
@@ -1702,25 +1876,15 @@ extern "C" int lhgt_extract_ref(const lhgt_args* a, lhgt_stats* stats) {
     if ((n = lhgt_s2_peaks(c, (float)a->hit_ratio, (float)a->match_ratio, a->max_peak)) < 0) return (int)n;
     st.peaks = n; st.flagged_positions = c->n_flagged;
     st.seconds[4] = now_s() - t;
-    if (say) printf("Slided ref len: %llu bp\tNo. of raw BKPs: %ld\nraw breakpoint screening is done.\n", (unsigned long long)c->index_bases, st.peaks);
 
-    // first records must carry the same read id (E:368-399); we refuse instead of re-seeking fq2
     t = now_s();
-    if (c->reads[0].nrec && c->reads[1].n) {
-        uint8_t h1[512], h2[512];
-        size_t n1 = std::min<uint64_t>(c->reads[0].n, sizeof h1), n2 = std::min<uint64_t>(c->reads[1].n, sizeof h2);
-        CU(cudaMemcpy(h1, c->reads[0].d_fq, n1, cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(h2, c->reads[1].d_fq, n2, cudaMemcpyDeviceToHost));
-        const uint8_t* e1 = (const uint8_t*)memchr(h1, '\n', n1);
-        const uint8_t* e2 = (const uint8_t*)memchr(h2, '\n', n2);
-        size_t l1 = read_id_len(h1, e1 ? (size_t)(e1 - h1) : n1), l2 = read_id_len(h2, e2 ? (size_t)(e2 - h2) : n2);
-        if (l1 != l2 || memcmp(h1, h2, l1) != 0)
-            return fail(LHGT_E_UNPAIRED, "first records of fq1 and fq2 carry different read ids");
+    if (fq2_record_shift) {                                                // fq1 record r pairs with fq2 record r + shift
+        Reads& b = c->reads[1];
+        uint64_t sh = std::min<uint64_t>((uint64_t)fq2_record_shift, b.nrec);
+        b.d_start += sh; b.d_end += sh; b.nrec -= sh;
     }
     if ((n = lhgt_s3_pairs(c, 0, -1)) < 0) return (int)n;
-    st.pairs_s3 = n;
     st.seconds[5] = now_s() - t;
-    if (say) printf("candidate HGT breakpoint screening is done.\nconsidered read pair num in finding candidate HGT breakpoint:%ld\n", st.pairs_s3);
 
     t = now_s();
     size_t need = 0;
@@ -1729,9 +1893,17 @@ extern "C" int lhgt_extract_ref(const lhgt_args* a, lhgt_stats* stats) {
     if ((rc = lhgt_intervals(c, &text[0], text.size(), &need))) return rc;
     if ((rc = spill(a->interval, text.data(), text.size()))) return rc;
     st.kept_peaks = c->kept_peaks;
+    long counts[3] = {0, 0, 0};
+    if ((rc = lhgt_deferred_counts(c, counts))) return rc;
+    st.reads_s1[0] = counts[0]; st.reads_s1[1] = counts[1]; st.pairs_s3 = counts[2];
     st.seconds[6] = now_s() - t;
     st.seconds[0] = now_s() - t0;
-    if (say) printf("Finish with time:\t%.3f\n", st.seconds[0]);
+    if (say) {
+        printf("K-mer counting is finished.\nconsidered read pair num in kmer counting:%ld\n", (st.reads_s1[0] + st.reads_s1[1]) / 2);
+        printf("Slided ref len: %llu bp\tNo. of raw BKPs: %ld\nraw breakpoint screening is done.\n", (unsigned long long)c->index_bases, st.peaks);
+        printf("candidate HGT breakpoint screening is done.\nconsidered read pair num in finding candidate HGT breakpoint:%ld\n", st.pairs_s3);
+        printf("Finish with time:\t%.3f\n", st.seconds[0]);
+    }
     if (stats) *stats = st;
     return 0;
 }
@@ -1916,7 +2088,8 @@ extern "C" int lhgt_main(int argc, char** argv) {
     memset(&a, 0, sizeof a);
     a.fq1 = argv[1]; a.fq2 = argv[2]; a.fasta = argv[3]; a.interval = argv[4];
     a.hit_ratio = (double)(float)v[0]; a.match_ratio = (double)(float)v[1];   // float hit_ratio = stod(...) (E:1368-1369)
-    a.threads = (int)v[2]; a.k = (int)v[3]; a.max_peak = (long)(int)v[4]; a.e = (int)v[5];
+    a.threads = (int)v[2]; a.k = (int)v[3]; a.max_peak = (long)v[4]; a.e = (int)v[5];   // the reference's int max_peak overflows beyond 2^31; we keep the value
+   
     a.seed = (unsigned)v[6]; a.sample = v[7];
     const char* dev = getenv("LHGT_DEVICE");
     a.device = dev ? atoi(dev) : 0;

@@ -681,3 +681,53 @@ def test_s3_vote_paths_agree(name, workdir, monkeypatch):
             s.s3_pairs()
             assert np.array_equal(want, s.peaks()[1] >= 1), arena_mb
     o.close()
+
+
+# ------------------------------------------------------------------ streamed ingest, fq2 re-synchronisation
+def test_streamed_ingest_through_a_small_ring(manifest, workdir, monkeypatch):
+    """Files are read through the pinned staging ring; 8 KiB chunks make every file wrap the ring many times, with the
+    chunk edges falling inside lines and records."""
+    case = fixtures.BY_NAME["fq2_longer"]                      # also the case whose last line has no newline
+    gold = manifest[case.name]
+    fa, fq1, fq2 = fixtures.materialize(case.data, workdir)
+    fixtures.clean_outputs(fa)
+    monkeypatch.setenv("LHGT_RING_KB", "8")
+    out = os.path.join(workdir, "ring.interval.txt")
+    try:
+        for _ in range(2):                                     # builds the index, then loads the file it wrote
+            api.extract_ref(fq1, fq2, fa, out, hit_ratio=case.hit, match_ratio=case.match, k=case.k, max_peak=case.max_peak, e=case.e,
+                            seed=case.seed, sample=case.sample)
+            assert _read(out).decode() == gold["interval_text"]
+        assert fixtures.sha256(fixtures.index_path(fa, case.k, case.e)) == gold["index_sha256"]
+    finally:
+        fixtures.clean_outputs(fa)
+
+
+def test_fq2_with_leading_records_is_resynchronised_like_the_reference(workdir):
+    """E:368-399: when the first read ids differ the reference scans fq2 for fq1's first id and pairs from there.  Three
+    stray records in front of fq2: same intervals as the unmodified reference binary (run here, k = 20)."""
+    if not os.path.exists(orc.REF_BIN_Z):
+        pytest.skip("oracle/_ref not built")
+    case = fixtures.BY_NAME["base_k20"]
+    fa, fq1, fq2 = fixtures.materialize(case.data, workdir)
+    stray = b"".join(b"@stray%d/2\n" % i + b"ACGT" * 30 + b"\n+\n" + b"I" * 120 + b"\n" for i in range(3))
+    fq2s = os.path.join(workdir, "stray.2.fq")
+    open(fq2s, "wb").write(stray + _read(fq2))
+    d = os.path.join(workdir, "stray_ref"); os.makedirs(d, exist_ok=True)
+    fa_ref = os.path.join(d, "ref.fa"); shutil.copy(fa, fa_ref)
+    out_ref, out_gpu = os.path.join(d, "ref.txt"), os.path.join(d, "gpu.txt")
+    orc.run_reference(fq1, fq2s, fa_ref, out_ref, hit=case.hit, match=case.match, k=case.k, max_peak=case.max_peak, e=case.e, seed=case.seed,
+                      sample=case.sample, timeout=600)
+    fixtures.clean_outputs(fa)
+    try:
+        api.extract_ref(fq1, fq2s, fa, out_gpu, hit_ratio=case.hit, match_ratio=case.match, k=case.k, max_peak=case.max_peak, e=case.e,
+                        seed=case.seed, sample=case.sample)
+        assert _read(out_gpu) == _read(out_ref)
+        assert len(_read(out_gpu).splitlines()) > 1
+        with pytest.raises(api.LhgtError) as ei:               # no record of fq2 is named like fq1's first
+            other = os.path.join(workdir, "other.2.fq")
+            open(other, "wb").write(_read(fq2).replace(b"@r", b"@q"))
+            api.extract_ref(fq1, other, fa, out_gpu, k=case.k, e=case.e, max_peak=case.max_peak)
+        assert ei.value.code == -7
+    finally:
+        fixtures.clean_outputs(fa)
