@@ -126,6 +126,7 @@ struct lhgt_ctx {
     cudaStream_t copy_st = nullptr;              // host->device prefetches run here, beside the kernels on `st`
     struct Prefetch { const void* host = nullptr; uint64_t n = 0; cudaEvent_t done = nullptr; bool active = false; };
     Prefetch pf_reads[2], pf_index, pf_fasta;
+    DevBuf<ByteSpan> fa_spans_buf; DevBuf<uint64_t> fa_words_buf; DevBuf<uint8_t> fa_text_buf, fa_seq_buf;   // FASTA ingest scratch
     DevBuf<uint8_t> fasta_buf; bool keep_fasta_buf = false;   // raw FASTA bytes of lhgt_index_build (kept when prefetched: a context that re-builds per sample)
 
     uint32_t* d_count = nullptr; uint64_t count_words = 0;
@@ -378,7 +379,7 @@ extern "C" void lhgt_destroy(lhgt_ctx* c) {
     dev_free(c->d_cands); dev_free(c->d_tally); dev_free(c->d_vote_table); dev_free(c->d_counter); dev_free(c->d_err); dev_free(c->d_misc);
     dev_free(c->d_bin_pool_a); dev_free(c->d_bin_pool_b); dev_free(c->d_bin_cursor);
     for (int i = 0; i < 3; ++i) { if (c->ring[i]) cudaFreeHost(c->ring[i]); if (c->ring_free[i]) cudaEventDestroy(c->ring_free[i]); }
-    c->fasta_buf.release();
+    c->fasta_buf.release(); c->fa_spans_buf.release(); c->fa_words_buf.release(); c->fa_text_buf.release(); c->fa_seq_buf.release();
     c->contig_first_buf.release(); c->s3_tables_buf.release(); c->s3_arena_buf.release(); c->s3_queue_buf.release();
     c->keep_cnt_buf.release(); c->keep_base_buf.release(); c->keep_tmp_buf.release(); c->keep_out_buf.release();
     peers_close(c);
@@ -477,54 +478,51 @@ static int alloc_image(lhgt_ctx* c, uint64_t words) {
 static int ingest_fasta_device(lhgt_ctx* c, const uint8_t* d_fa, size_t n, ParsedFasta& pf, uint8_t** d_seq) {
     *d_seq = nullptr;
     uint64_t tiles = fastq_index_tiles(n);
-    ByteSpan* d_spans = nullptr; uint64_t *d_off = nullptr, *d_before = nullptr, *d_cnt = nullptr, *d_base = nullptr, *d_tmp = nullptr;
-    uint8_t* d_text = nullptr;
-    unsigned long long* d_count = nullptr;
-    auto cleanup = [&]() { dev_free(d_spans); dev_free(d_off); dev_free(d_before); dev_free(d_cnt); dev_free(d_base); dev_free(d_tmp); dev_free(d_text); dev_free(d_count); };
     int rc = 0;
     std::vector<ByteSpan> spans;
-    if ((rc = dev_alloc(&d_count, 1))) return rc;
-    for (uint32_t cap = 1u << 16;;) {                                             // header spans, unordered
-        if ((rc = dev_alloc(&d_spans, cap))) { cleanup(); return rc; }
+    unsigned long long* d_count = c->d_counter + CNT_MAIN;
+    // the scratch lives in the context (grow-only): cudaMalloc / cudaFree synchronise the device, and a context that
+    // re-builds its index for every sample would pay for them every time
+    for (size_t cap = std::max<size_t>(c->fa_spans_buf.cap, (size_t)1 << 16);;) {  // header spans, unordered
+        if ((rc = c->fa_spans_buf.reserve(cap))) return rc;
         unsigned long long found = 0;
         cudaMemsetAsync(d_count, 0, sizeof found, c->st);
-        c->launches += launch_fasta_headers(d_fa, n, d_spans, cap, d_count, c->st);
+        c->launches += launch_fasta_headers(d_fa, n, c->fa_spans_buf.p, (uint32_t)std::min<size_t>(c->fa_spans_buf.cap, 0xffffffffu), d_count, c->st);
         cudaMemcpyAsync(&found, d_count, sizeof found, cudaMemcpyDeviceToHost, c->st);
         cudaError_t e0 = cudaStreamSynchronize(c->st);
-        if (e0 != cudaSuccess) { cleanup(); return fail(LHGT_E_CUDA, "FASTA header scan failed: %s", cudaGetErrorString(e0)); }
-        if (found > 0xfffffff0ull) { cleanup(); return fail(LHGT_E_FORMAT, "FASTA holds more than 2^32 header lines"); }
-        if (found <= cap) {
+        if (e0 != cudaSuccess) return fail(LHGT_E_CUDA, "FASTA header scan failed: %s", cudaGetErrorString(e0));
+        if (found > 0xfffffff0ull) return fail(LHGT_E_FORMAT, "FASTA holds more than 2^32 header lines");
+        if (found <= c->fa_spans_buf.cap) {
             spans.resize((size_t)found);
-            if (found && cudaMemcpy(spans.data(), d_spans, (size_t)found * sizeof(ByteSpan), cudaMemcpyDeviceToHost) != cudaSuccess) {
-                cleanup();
+            if (found && cudaMemcpy(spans.data(), c->fa_spans_buf.p, (size_t)found * sizeof(ByteSpan), cudaMemcpyDeviceToHost) != cudaSuccess)
                 return fail(LHGT_E_CUDA, "FASTA header download failed");
-            }
             break;
         }
-        dev_free(d_spans);
-        cap = (uint32_t)found;
+        cap = (size_t)found;
     }
     std::sort(spans.begin(), spans.end(), [](const ByteSpan& x, const ByteSpan& y) { return x.lo < y.lo; });
     const uint32_t ns = (uint32_t)spans.size();
     std::vector<uint64_t> off(ns + 1, 0), before(ns + 1, 0);
     for (uint32_t i = 0; i < ns; ++i) off[i + 1] = off[i] + (spans[i].hi - spans[i].lo + 1);   // the newline (or last byte) travels too; trimmed below
     std::vector<uint8_t> text((size_t)off[ns] + 1);
-    if ((rc = dev_alloc(&d_off, (size_t)ns + 1)) || (rc = dev_alloc(&d_before, (size_t)ns + 1)) || (rc = dev_alloc(&d_cnt, tiles + 1)) ||
-        (rc = dev_alloc(&d_base, tiles + 1)) || (rc = dev_alloc(&d_tmp, scan_tmp_words(tiles))) || (rc = dev_alloc(&d_text, (size_t)off[ns] + 1)) ||
-        (rc = dev_alloc(d_seq, n + 64))) {
-        cleanup(); dev_free(*d_seq);
+    // one 8-byte scratch buffer: header-text offsets | sequence bytes before each header | tile counts | tile bases | scan temporaries
+    size_t w_off = 0, w_before = w_off + ns + 1, w_cnt = w_before + ns + 1, w_base = w_cnt + tiles + 1, w_tmp = w_base + tiles + 1;
+    if ((rc = c->fa_words_buf.reserve(w_tmp + scan_tmp_words(tiles))) || (rc = c->fa_text_buf.reserve((size_t)off[ns] + 1)) ||
+        (rc = c->fa_seq_buf.reserve(n + 64)))
         return rc;
-    }
+    uint64_t *d_off = c->fa_words_buf.p + w_off, *d_before = c->fa_words_buf.p + w_before, *d_cnt = c->fa_words_buf.p + w_cnt,
+             *d_base = c->fa_words_buf.p + w_base, *d_tmp = c->fa_words_buf.p + w_tmp;
+    ByteSpan* d_spans = c->fa_spans_buf.p;
+    *d_seq = c->fa_seq_buf.p;
     if (ns) cudaMemcpyAsync(d_spans, spans.data(), ns * sizeof(ByteSpan), cudaMemcpyHostToDevice, c->st);   // now in file order
     cudaMemcpyAsync(d_off, off.data(), (ns + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->st);
-    c->launches += launch_fasta_header_text(d_fa, d_spans, ns, d_off, d_text, c->st);
+    c->launches += launch_fasta_header_text(d_fa, d_spans, ns, d_off, c->fa_text_buf.p, c->st);
     c->launches += launch_fasta_compact(d_fa, n, d_spans, ns, d_cnt, d_base, d_tmp, *d_seq, d_before, 0, c->st);
     c->launches += launch_fasta_compact(d_fa, n, d_spans, ns, d_cnt, d_base, d_tmp, *d_seq, d_before, 1, c->st);
-    if (off[ns]) cudaMemcpyAsync(text.data(), d_text, (size_t)off[ns], cudaMemcpyDeviceToHost, c->st);
+    if (off[ns]) cudaMemcpyAsync(text.data(), c->fa_text_buf.p, (size_t)off[ns], cudaMemcpyDeviceToHost, c->st);
     cudaMemcpyAsync(before.data(), d_before, (ns + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->st);
     cudaError_t e1 = cudaStreamSynchronize(c->st);
-    cleanup();
-    if (e1 != cudaSuccess) { dev_free(*d_seq); return fail(LHGT_E_CUDA, "FASTA compaction failed: %s", cudaGetErrorString(e1)); }
+    if (e1 != cudaSuccess) return fail(LHGT_E_CUDA, "FASTA compaction failed: %s", cudaGetErrorString(e1));
     // contig 0 is what precedes the first header (name "start", E:747); contig i >= 1 follows header i
     uint64_t word = LHGT_CODER_SLOTS;
     long cumulative = 0;
@@ -546,7 +544,7 @@ static int ingest_fasta_device(lhgt_ctx* c, const uint8_t* d_fa, size_t n, Parse
             pf.len_text += name; pf.len_text += buf;
             Contig g{};
             g.hash_word = word + 1; g.seq_off = lo; g.len = (uint32_t)len; g.tile0 = 0;
-            if (len > 178000000u) { dev_free(*d_seq); return fail(LHGT_E_FORMAT, "contig longer than the reference's int buffers allow (E:925)"); }
+            if (len > 178000000u) return fail(LHGT_E_FORMAT, "contig longer than the reference's int buffers allow (E:925)");
             pf.contigs.push_back(g);
             word += 1 + (uint64_t)(len - c->k + 1) * c->e;
         }
@@ -565,7 +563,7 @@ static int index_build_from_device(lhgt_ctx* c, const uint8_t* d_fa, size_t n) {
     c->len_text = pf.len_text;
     uint64_t words = LHGT_CODER_SLOTS;
     for (auto& g : c->contigs) words += 1 + (uint64_t)(g.len - c->k + 1) * c->e;
-    if ((rc = alloc_image(c, words)) || (rc = finish_index_tables(c))) { cudaStreamSynchronize(c->st); cudaFree(d_seq); return rc; }
+    if ((rc = alloc_image(c, words)) || (rc = finish_index_tables(c))) return rc;
     uint32_t header[LHGT_CODER_SLOTS];
     lhgt_coder_to_header(c->cc, header);
     CU(cudaMemcpyAsync(c->d_image, header, sizeof header, cudaMemcpyHostToDevice, c->st));
@@ -574,7 +572,7 @@ static int index_build_from_device(lhgt_ctx* c, const uint8_t* d_fa, size_t n) {
         c->launches += launch_index_build(d_seq, c->d_contigs, c->d_tiles, c->tiles.size(), c->hp, c->d_image, nullptr, c->st);
     }
     cudaError_t e1 = cudaStreamSynchronize(c->st);
-    cudaFree(d_seq);
+    if (!c->keep_fasta_buf) { c->fa_seq_buf.release(); c->fa_words_buf.release(); }   // one-off builds give the big scratch back
     if (e1 != cudaSuccess) return fail(LHGT_E_CUDA, "index build kernel failed: %s", cudaGetErrorString(e1));
     return 0;
 }

@@ -677,6 +677,7 @@ __global__ void __launch_bounds__(256) index_build_kernel(const uint8_t* __restr
                                                           const Tile* __restrict__ tiles, HashP hp,
                                                           uint32_t* __restrict__ image, uint8_t* __restrict__ valid_out) {
     __shared__ uint32_t planes[4 * kIbPlane];
+    __shared__ __align__(16) uint32_t outw[E ? kTile * E + 4 : 1];   // the tile's hashes, position-major, as the file holds them
     const int e = E ? E : hp.e;
     Tile t = tiles[blockIdx.x];
     Contig c = contigs[t.contig];
@@ -699,18 +700,36 @@ __global__ void __launch_bounds__(256) index_build_kernel(const uint8_t* __restr
     }
     __syncthreads();
     if (j0 == 0 && threadIdx.x == 0) image[c.hash_word - 1] = c.len;
+    uint32_t* dst = image + c.hash_word + (size_t)j0 * e;
+    const int n_here = (int)min((long)kTile, np - j0);           // positions of this tile that hold a k-mer
+    // With E known the hashes are staged in shared memory and leave as 16-byte vectors: a thread's own e words sit 4e
+    // bytes from its neighbour's, so direct stores would touch every sector of the run three times over.
+    const int mis = E ? (int)(((uintptr_t)dst >> 2) & 3u) : 0;    // words by which dst trails a 16-byte boundary
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         int jl = r * 256 + threadIdx.x;
-        long j = j0 + jl;
-        if (j < np) {
+        if (jl < n_here) {
             KmerWin kw = make_win<kIbPlane>(planes, jl, hp);
-            uint32_t* dst = image + c.hash_word + (size_t)j * e;
 #pragma unroll
             for (int i = 0; i < (E ? E : kMaxE); ++i)
-                if (i < e) dst[i] = kw.valid ? hash_of(kw, hp, i) : 0u;
-            if (valid_out) valid_out[j] = kw.valid;
+                if (i < e) {
+                    uint32_t hv = kw.valid ? hash_of(kw, hp, i) : 0u;
+                    if (E) outw[mis + jl * E + i] = hv; else dst[(size_t)jl * e + i] = hv;
+                }
+            if (valid_out) valid_out[j0 + jl] = kw.valid;
         }
+    }
+    if (E) {
+        __syncthreads();
+        const int total = n_here * E;                            // words; word x of the run sits at outw[mis + x] and goes to dst[x]
+        const int head = min(total, (4 - mis) & 3);              // words before the first 16-byte boundary of dst
+        const int nvec = (total - head) >> 2;
+        if ((int)threadIdx.x < head) dst[threadIdx.x] = outw[mis + threadIdx.x];
+        uint4* dst4 = reinterpret_cast<uint4*>(dst + head);
+        const uint4* src4 = reinterpret_cast<const uint4*>(outw + mis + head);    // (mis + head) % 4 == 0
+        for (int v = threadIdx.x; v < nvec; v += 256) dst4[v] = src4[v];
+        int tail0 = head + (nvec << 2);
+        if ((int)threadIdx.x < total - tail0) dst[tail0 + threadIdx.x] = outw[mis + tail0 + threadIdx.x];
     }
 }
 
@@ -2035,15 +2054,23 @@ __global__ void __launch_bounds__(kS3Warps * 32, LHGT_S3_CTAS) s3_pairs_kernel(
 
 // The vote of the queued pairs (judge_base + check_split, E:118-202), one thread per pair.  The tally is an open-addressed
 // table of `tsize` 32-bit slots per thread (contig << 10 | votes; 0 = empty; tsize a power of two >= twice the longest
-// list) in global memory sized to stay L2-resident; it is left clean: the slots a pair fills are remembered, together
-// with the first peak voted for that contig, in the arena space of candidates already consumed, and zeroed at the end.
+// list).  SMEM = true keeps the tables in shared memory, slot s of thread t at tab[s * blockDim.x + t] (conflict-free
+// whatever the slots); otherwise they live in global memory, sized to stay L2-resident.  A table is left clean: the slots a
+// pair fills are remembered, together with the first peak voted for that contig, in the arena space of candidates
+// already consumed, and zeroed at the end.  The e candidates of a position are looked up side by side (their first
+// probes are independent loads); only the update is serial.
+template <bool SMEM, int E>
 __global__ void __launch_bounds__(128) s3_vote_kernel(uint2* __restrict__ arena, const uint2* __restrict__ queue,
-                                                      const uint32_t* __restrict__ queue_count, uint32_t queue_cap, int e,
+                                                      const uint32_t* __restrict__ queue_count, uint32_t queue_cap, int e_rt,
                                                       uint32_t* __restrict__ tables, uint32_t tsize, uint8_t* __restrict__ peak_filter) {
+    extern __shared__ uint32_t tab_s[];
+    const int e = E ? E : e_rt;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
-    uint32_t* table = tables + (size_t)tid * tsize;
+    uint32_t* table = SMEM ? tab_s + threadIdx.x : tables + (size_t)tid * tsize;
+    const uint32_t stride = SMEM ? blockDim.x : 1u;
     const uint32_t mask = tsize - 1u;
     const int shift = 32 - (31 - __clz(tsize));
+    if (SMEM) for (uint32_t x = 0; x < tsize; ++x) table[x * stride] = 0u;
     const uint32_t n = min(*queue_count, queue_cap);
     for (uint32_t q = tid; q < n; q += nthreads) {
         uint2 job = queue[q];
@@ -2051,25 +2078,36 @@ __global__ void __launch_bounds__(128) s3_vote_kernel(uint2* __restrict__ arena,
         const int n_listed = (int)job.y;
         int n_t = 0;
         for (int f = 0; f < n_listed; ++f) {
+            uint2 cd[E ? E : kMaxE];
+            uint32_t idx[E ? E : kMaxE], ent[E ? E : kMaxE];
+#pragma unroll
+            for (int i = 0; i < (E ? E : kMaxE); ++i)
+                if (i < e) {
+                    cd[i] = list[(size_t)f * e + i];
+                    idx[i] = (cd[i].y * 2654435761u) >> shift;
+                }
+#pragma unroll
+            for (int i = 0; i < (E ? E : kMaxE); ++i)
+                if (i < e) ent[i] = cd[i].x ? table[idx[i] * stride] : 0u;
             uint32_t sel_peak = 0, sel_slot = 0, sel_entry = 0;
             int sel_votes = 0;
             bool sel_seen = false;
-            for (int i = 0; i < e; ++i) {
-                uint2 cd = list[(size_t)f * e + i];
-                if (!cd.x) continue;
-                uint32_t idx = (cd.y * 2654435761u) >> shift, ent;
-                while ((ent = table[idx]) != 0u && (ent >> 10) != cd.y) idx = (idx + 1u) & mask;
-                if (ent) {
-                    int v = (int)(ent & 1023u);
-                    if (v >= sel_votes) { sel_peak = cd.x; sel_votes = v; sel_seen = true; sel_slot = idx; sel_entry = ent; }
-                } else if (sel_peak == 0) { sel_peak = cd.x; sel_votes = 0; sel_seen = false; sel_slot = idx; sel_entry = cd.y << 10; }
+#pragma unroll
+            for (int i = 0; i < (E ? E : kMaxE); ++i) {
+                if (i >= e || !cd[i].x) continue;
+                uint32_t en = ent[i], ix = idx[i];
+                while (en != 0u && (en >> 10) != cd[i].y) { ix = (ix + 1u) & mask; en = table[ix * stride]; }
+                if (en) {
+                    int v = (int)(en & 1023u);
+                    if (v >= sel_votes) { sel_peak = cd[i].x; sel_votes = v; sel_seen = true; sel_slot = ix; sel_entry = en; }
+                } else if (sel_peak == 0) { sel_peak = cd[i].x; sel_votes = 0; sel_seen = false; sel_slot = ix; sel_entry = cd[i].y << 10; }
             }
-            table[sel_slot] = sel_entry + 1u;
+            table[sel_slot * stride] = sel_entry + 1u;
             if (!sel_seen) list[n_t++] = make_uint2(sel_slot, sel_peak);      // n_t <= f + 1: that entry has been consumed
         }
         int largest = 0, second = 0, strong = 0;
         for (int t = 0; t < n_t; ++t) {
-            int v = (int)(table[list[t].x] & 1023u);
+            int v = (int)(table[list[t].x * stride] & 1023u);
             if (v < 6) continue;
             ++strong;
             if (v >= largest) { second = largest; largest = v; }
@@ -2077,9 +2115,9 @@ __global__ void __launch_bounds__(128) s3_vote_kernel(uint2* __restrict__ arena,
         }
         for (int t = 0; t < n_t; ++t) {
             uint2 rec = list[t];
-            int v = (int)(table[rec.x] & 1023u);
+            int v = (int)(table[rec.x * stride] & 1023u);
             if (strong >= 2 && v >= 6 && (v == largest || v == second)) peak_filter[rec.y] = 1;   // only >= 1 is consumed (E:526)
-            table[rec.x] = 0u;
+            table[rec.x * stride] = 0u;
         }
     }
 }
@@ -2099,8 +2137,21 @@ int launch_contig_first(const Contig* contigs, uint32_t n_contigs, const uint32_
 
 int s3_vote_threads() { return kSMs * 128; }
 
+// tables in shared memory when `tsize` slots per thread leave room for at least one warp per CTA
 int launch_s3_vote(const S3Scratch& sc, int e, uint32_t* tables, uint32_t tsize, uint8_t* peak_filter, cudaStream_t st) {
-    s3_vote_kernel<<<kSMs, 128, 0, st>>>(sc.arena, sc.queue, sc.queue_count, sc.queue_cap, e, tables, tsize, peak_filter);
+    const size_t budget = 192 << 10;
+    int warps = (int)(budget / ((size_t)tsize * 4 * 32));
+    if (warps >= 1) {
+        warps = warps > 4 ? 4 : warps;
+        size_t smem = (size_t)warps * 32 * tsize * 4;
+        auto kern = e == 3 ? s3_vote_kernel<true, 3> : s3_vote_kernel<true, 0>;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        int ctas = (int)((220u << 10) / smem);
+        kern<<<kSMs * (ctas < 1 ? 1 : ctas), warps * 32, smem, st>>>(sc.arena, sc.queue, sc.queue_count, sc.queue_cap, e, tables, tsize, peak_filter);
+        return 1;
+    }
+    if (e == 3) s3_vote_kernel<false, 3><<<kSMs, 128, 0, st>>>(sc.arena, sc.queue, sc.queue_count, sc.queue_cap, e, tables, tsize, peak_filter);
+    else s3_vote_kernel<false, 0><<<kSMs, 128, 0, st>>>(sc.arena, sc.queue, sc.queue_count, sc.queue_cap, e, tables, tsize, peak_filter);
     return 1;
 }
 
