@@ -147,6 +147,8 @@ struct lhgt_ctx {
     uint32_t *d_tile_new = nullptr, *d_tile_base = nullptr, *d_scan_tmp = nullptr;
     bool gathered = false, marked = false; float mark_match = 0.f; uint32_t n_needed_tiles = 0;
     DevBuf<uint8_t> hot_buf; DevBuf<uint32_t> need_buf; uint32_t* d_misc = nullptr;
+    DevBuf<uint2> gs_pool_buf; DevBuf<uint32_t> gs_cursor_buf, sat_buf; bool single_exact = false;   // S2 gather through table slices
+    DevBuf<uint2> reg_pool_buf; DevBuf<uint32_t> reg_cursor_buf; bool filter_on = true;   // S2 registration through buckets
     DevBuf<uint32_t> contig_first_buf, s3_tables_buf; DevBuf<uint2> s3_arena_buf, s3_queue_buf;   // S3: peak -> contig search, vote hand-over
     DevBuf<uint32_t> keep_cnt_buf, keep_base_buf, keep_tmp_buf; DevBuf<int32_t> keep_out_buf;   // OUT: kept-peak compaction
     std::string intervals_text; bool intervals_valid = false; long kept_peaks = 0;
@@ -380,6 +382,7 @@ extern "C" void lhgt_destroy(lhgt_ctx* c) {
     dev_free(c->d_bin_pool_a); dev_free(c->d_bin_pool_b); dev_free(c->d_bin_cursor);
     for (int i = 0; i < 3; ++i) { if (c->ring[i]) cudaFreeHost(c->ring[i]); if (c->ring_free[i]) cudaEventDestroy(c->ring_free[i]); }
     c->fasta_buf.release(); c->fa_spans_buf.release(); c->fa_words_buf.release(); c->fa_text_buf.release(); c->fa_seq_buf.release();
+    c->reg_pool_buf.release(); c->reg_cursor_buf.release(); c->gs_pool_buf.release(); c->gs_cursor_buf.release(); c->sat_buf.release();
     c->contig_first_buf.release(); c->s3_tables_buf.release(); c->s3_arena_buf.release(); c->s3_queue_buf.release();
     c->keep_cnt_buf.release(); c->keep_base_buf.release(); c->keep_tmp_buf.release(); c->keep_out_buf.release();
     peers_close(c);
@@ -1270,8 +1273,41 @@ extern "C" int lhgt_s2_gather(lhgt_ctx* c, long tile_begin, long tile_end) {
     if (tile_begin < 0 || tile_begin > tile_end) return fail(LHGT_E_ARG, "bad tile range");
     CU(cudaSetDevice(c->device));
     Span sp(c, 2);
-    c->launches += launch_s2_gather(c->d_image, c->d_contigs, c->d_tiles, (uint64_t)tile_begin, (uint64_t)tile_end, c->hp,
-                                    c->d_count, c->d_single, c->d_trio, c->st);
+    // Tables far beyond L2 are gathered slice by slice (records bucketed by table slice, answered while the slice is
+    // L2-resident: both single and trio exact); smaller ones are probed directly with the short-circuit AND.
+    const char* force = getenv("LHGT_S2_SLICED");                     // test knob: 1 forces the sliced form (k >= 8), 0 the direct one
+    bool sliced = c->e <= 4 && c->k >= 8 && (force ? atoi(force) != 0 : c->count_words * 4 > ((uint64_t)128 << 20));
+    if (sliced && tile_end > tile_begin) {
+        const char* kb = getenv("LHGT_S2_POOL_KB");                     // test knob: small record regions force several chunks and overflow
+        uint2* pool = nullptr; uint64_t pool_records = 0;
+        if (!kb && c->d_bin_pool_a && c->bin_pool_a_entries / 2 >= ((uint64_t)16 << 20)) { pool = (uint2*)c->d_bin_pool_a; pool_records = c->bin_pool_a_entries / 2; }
+        else {
+            uint64_t want = kb ? std::max<uint64_t>(((uint64_t)atol(kb) << 10) / 8, (uint64_t)s2_gs_buckets() * 64)
+                               : std::min<uint64_t>((uint64_t)(tile_end - tile_begin) * kTile * c->e * 9 / 8 + 4096, (uint64_t)32 << 20);
+            int rc = c->gs_pool_buf.reserve(want);
+            if (rc) return rc;
+            pool = c->gs_pool_buf.p; pool_records = want;
+        }
+        size_t plane_words = ((size_t)nt + kMaxPeers) * kTileWords;
+        int rc = c->sat_buf.reserve(plane_words * c->e);
+        if (!rc) rc = c->gs_cursor_buf.reserve((size_t)s2_gs_cursor_words());
+        if (rc) return rc;
+        for (int i = 0; i < c->e; ++i)
+            CU(cudaMemsetAsync(c->sat_buf.p + (size_t)i * plane_words + (size_t)tile_begin * kTileWords, 0, (size_t)(tile_end - tile_begin) * kTileWords * 4, c->st));
+        uint32_t cap = (uint32_t)std::min<uint64_t>(pool_records / (uint64_t)s2_gs_buckets(), 0xfffffff0u);
+        uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)1 << 18, (uint64_t)(0.9 * (double)cap * s2_gs_buckets() / ((double)kTile * c->e))));
+        for (uint64_t lo = (uint64_t)tile_begin; lo < (uint64_t)tile_end; lo += chunk) {
+            CU(cudaMemsetAsync(c->gs_cursor_buf.p, 0, (size_t)s2_gs_cursor_words() * 4, c->st));
+            c->launches += launch_s2_gather_sliced(c->d_image, c->d_contigs, c->d_tiles, lo, std::min<uint64_t>((uint64_t)tile_end, lo + chunk), c->hp, c->d_count,
+                                                   c->sat_buf.p, plane_words, pool, c->gs_cursor_buf.p, cap, c->st);
+        }
+        c->launches += launch_s2_gather_combine(c->sat_buf.p, plane_words, c->e, (uint64_t)tile_begin, (uint64_t)tile_end, c->d_single, c->d_trio, c->st);
+        c->single_exact = true;
+    } else {
+        c->launches += launch_s2_gather(c->d_image, c->d_contigs, c->d_tiles, (uint64_t)tile_begin, (uint64_t)tile_end, c->hp,
+                                        c->d_count, c->d_single, c->d_trio, c->st);
+        c->single_exact = false;
+    }
     c->gathered = true;
     c->marked = false;
     return 0;
@@ -1301,6 +1337,7 @@ extern "C" int lhgt_s2_complete(lhgt_ctx* c, long tile_begin, long tile_end) {
     if (tile_end < 0 || tile_end > nt) tile_end = nt;
     if (tile_begin < 0 || tile_begin > tile_end) return fail(LHGT_E_ARG, "bad tile range");
     CU(cudaSetDevice(c->device));
+    if (c->single_exact) return 0;                                   // the sliced gather answered every hash
     Span sp(c, 2);
     c->launches += launch_s2_single(c->d_image, c->d_contigs, c->d_tiles, c->need_buf.p, c->d_misc + MISC_NEED, (uint64_t)tile_begin,
                                     (uint64_t)tile_end, c->hp, c->d_count, c->d_single, c->st);
@@ -1375,11 +1412,45 @@ extern "C" int lhgt_s2_finish(lhgt_ctx* c, float hit_ratio, float match_ratio, l
         if (rc) return rc;
         c->launches += launch_contig_first(c->d_contigs, (uint32_t)c->contigs.size(), c->d_tile_base, (uint32_t)total, c->contig_first_buf.p, c->st);
     }
+    // the S3 pre-filter only pays while it is sparse (2^28 bits against the registered k-mers): a dense result skips it
+    c->filter_on = (double)c->n_flagged * c->e < 0.7 * (double)(1u << kFilterLog2);
     if (total > 0) {
         CU(cudaMemsetAsync(c->d_filter, 0, (size_t)total, c->st));
         Span sp(c, 10);
-        c->launches += launch_s2_register(c->d_image, c->d_contigs, c->d_tiles, need, n_need, c->hp, c->d_count, c->d_flagged, c->d_tile_base,
-                                          c->d_loci, (uint32_t)std::min<long>(c->peaks_cap, 0xffffffffL), c->d_peak_kmer, c->d_prefilter, 0, c->st);
+        uint32_t loci_cap = (uint32_t)std::min<long>(c->peaks_cap, 0xffffffffL);
+        uint32_t* prefilter = c->filter_on ? c->d_prefilter : nullptr;
+        const char* force = getenv("LHGT_REG_BUCKETED");               // test knob: 1 forces the bucketed form, 0 the direct one
+        double records = (double)c->n_flagged * c->e;
+        bool bucketed = force ? atoi(force) != 0 : records >= 8e6;      // below that the direct atomics finish in well under a millisecond
+        if (bucketed && c->n_needed_tiles > 0) {
+            // record regions: the S1 leaf-stream pool when there is one (idle now), else a buffer of our own
+            const char* kb = getenv("LHGT_REG_POOL_KB");                 // test knob: small regions force chunks and overflow
+            uint2* pool = nullptr; uint64_t pool_records = 0;
+            if (!kb && c->d_bin_pool_b && c->bin_pool_b_entries / 2 >= ((uint64_t)32 << 20)) { pool = (uint2*)c->d_bin_pool_b; pool_records = c->bin_pool_b_entries / 2; }
+            else {
+                uint64_t want = kb ? std::max<uint64_t>(((uint64_t)atol(kb) << 10) / 8, (uint64_t)s2_reg_buckets() * 4)
+                                   : std::min<uint64_t>((uint64_t)(records * 1.25) + (uint64_t)s2_reg_buckets() * 1024, (uint64_t)64 << 20);
+                int rc = c->reg_pool_buf.reserve(want);
+                if (rc) return rc;
+                pool = c->reg_pool_buf.p; pool_records = want;
+            }
+            int rc = c->reg_cursor_buf.reserve((size_t)s2_reg_cursor_words());
+            if (rc) return rc;
+            uint32_t cap = (uint32_t)std::min<uint64_t>(pool_records / (uint64_t)s2_reg_buckets(), 0xfffffff0u);
+            double per_tile = std::max(1.0, records / (double)c->n_needed_tiles);
+            uint32_t chunk = (uint32_t)std::max(1.0, std::min((double)c->n_needed_tiles, 0.85 * (double)cap * s2_reg_buckets() / per_tile));
+            for (uint32_t lo = 0; lo < c->n_needed_tiles; lo += chunk) {
+                CU(cudaMemsetAsync(c->reg_cursor_buf.p, 0, (size_t)s2_reg_cursor_words() * 4, c->st));
+                int nl = launch_s2_register_bucketed(c->d_image, c->d_contigs, c->d_tiles, need, n_need, lo, std::min(c->n_needed_tiles, lo + chunk), c->hp,
+                                                     c->d_count, c->d_flagged, c->d_tile_base, c->d_loci, loci_cap, c->d_peak_kmer, prefilter,
+                                                     pool, c->reg_cursor_buf.p, cap, c->st);
+                if (nl < 0) return fail(LHGT_E_CUDA, "registration kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                c->launches += nl;
+            }
+        } else {
+            c->launches += launch_s2_register(c->d_image, c->d_contigs, c->d_tiles, need, n_need, c->hp, c->d_count, c->d_flagged, c->d_tile_base,
+                                              c->d_loci, loci_cap, c->d_peak_kmer, prefilter, 0, c->st);
+        }
         c->peak_tables_dirty = true;
     }
     c->n_peaks = total;
@@ -1482,8 +1553,7 @@ extern "C" long lhgt_s3_pairs(lhgt_ctx* c, long first, long count) {
                 CU(cudaMemsetAsync(c->s3_tables_buf.p, 0, tw * 4, c->st));          // s3_vote_kernel leaves them zeroed
             }
         }
-        // the pre-filter only pays while it is sparse: 2^28 bits against the registered k-mers
-        bool use_filter = (double)c->n_flagged * c->e < 0.7 * (double)(1u << kFilterLog2);
+        bool use_filter = c->filter_on;                                 // decided at registration (lhgt_s2_finish)
         S3Scratch sc = c->scratch;
         sc.arena = arena; sc.arena_cap = (uint32_t)arena_cap; sc.arena_cursor = c->d_misc + MISC_ARENA;
         sc.queue = c->s3_queue_buf.p; sc.queue_cap = (uint32_t)std::min<uint64_t>(batch, 0xffffffffu); sc.queue_count = c->d_misc + MISC_QUEUE;

@@ -1648,7 +1648,7 @@ __global__ void __launch_bounds__(256) s2_register_kernel(const uint32_t* __rest
                     uint32_t slot = prefilter_slot(h);
                     if (mode == 0) {
                         atomicMax(peak_kmer + h, id);
-                        atomicOr(prefilter + (slot >> 5), 1u << (slot & 31));
+                        if (prefilter) atomicOr(prefilter + (slot >> 5), 1u << (slot & 31));
                     } else {
                         peak_kmer[h] = 0u;
                         prefilter[slot >> 5] = 0u;
@@ -1657,6 +1657,278 @@ __global__ void __launch_bounds__(256) s2_register_kernel(const uint32_t* __rest
             }
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// S2 gather through table slices (DESIGN.md 4.5a').  A direct probe of a count table far larger than L2 is a 128-byte DRAM
+// fill for 2 useful bits.  Here the stored hashes of a chunk of the reference are turned into (position, table index)
+// records, appended to 16 buckets = 16 contiguous slices of the table (64 MiB each at k = 32), and answered bucket by bucket
+// while that slice sits in L2; a saturated counter sets the position's bit in the hash's own plane (records keep their
+// position order inside a bucket, so those atomics stay in L2 too).  Everything that touches DRAM is then a stream: the
+// image once, the records once out and once in, the table once per chunk.
+// ------------------------------------------------------------------------------------------------
+constexpr int kGsBuckets = 16, kGsStage = 256, kGsCursorStride = 32;
+
+struct GsSink { uint2* pool; uint32_t* cursor; uint32_t cap; };   // bucket b: pool[b * cap .. +cap), cursor[b * kGsCursorStride]
+
+__device__ __forceinline__ void gs_answer(uint2 r, uint32_t bucket, int slice_shift, uint64_t chunk_bit0, size_t plane_words,
+                                          const uint32_t* __restrict__ count, uint32_t* __restrict__ sat) {
+    uint32_t g = (bucket << slice_shift) | (r.x & 0x0fffffffu), i = r.x >> 28;
+    if (((ld_table(count + (g >> 4)) >> ((g & 15u) * 2)) & 3u) != 3u) return;
+    uint64_t bit = chunk_bit0 + r.y;
+    atomicOr(sat + (size_t)i * plane_words + (bit >> 5), 1u << (bit & 31));
+}
+
+template <int E>
+__global__ void __launch_bounds__(256) s2_gsemit_kernel(const uint32_t* __restrict__ image, const Contig* __restrict__ contigs,
+                                                        const Tile* __restrict__ tiles, uint64_t tile_begin, uint64_t chunk_tile0, HashP hp,
+                                                        int slice_shift, size_t plane_words, const uint32_t* __restrict__ count,
+                                                        uint32_t* __restrict__ sat, GsSink sink) {
+    __shared__ uint2 stage[kGsBuckets][kGsStage];
+    __shared__ uint32_t cnt[kGsBuckets];
+    const int e = E ? E : hp.e;
+    uint64_t tix = tile_begin + blockIdx.x;
+    Tile t = tiles[tix];
+    Contig c = contigs[t.contig];
+    long np = (long)c.len - hp.k + 1;
+    const uint32_t* hashes = image + c.hash_word;
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < kGsBuckets) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t chunk_bit0 = chunk_tile0 * kTile;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        int xl = r * 256 + threadIdx.x;
+        long j = (long)t.j0 + xl;
+        if (j >= np) continue;
+        uint32_t pos = (uint32_t)((tix - chunk_tile0) * kTile + xl);        // < 2^28: the caller bounds the chunk
+#pragma unroll
+        for (int i = 0; i < (E ? E : 4); ++i) {
+            if (i >= e) break;
+            uint32_t h = ld_stream(hashes + (size_t)j * e + i);
+            if (!h) continue;                                                 // stored 0 = no hit (Q4, E:936-941)
+            uint32_t g = tbl_index(h, hp), b = g >> slice_shift;
+            uint2 rec = make_uint2((g & ((1u << slice_shift) - 1u)) | ((uint32_t)i << 28), pos);
+            uint32_t slot = atomicAdd(&cnt[b], 1u);
+            if (slot < (uint32_t)kGsStage) stage[b][slot] = rec;
+            else {                                                            // stage full (a skewed tile): straight to the region
+                uint32_t gq = atomicAdd(sink.cursor + b * kGsCursorStride, 1u);
+                if (gq < sink.cap) sink.pool[(size_t)b * sink.cap + gq] = rec;
+                else gs_answer(rec, b, slice_shift, chunk_bit0, plane_words, count, sat);
+            }
+        }
+    }
+    __syncthreads();
+    for (int b = warp; b < kGsBuckets; b += 8) {                              // a warp hands each of its buckets over as one coalesced run
+        uint32_t n = min(cnt[b], (uint32_t)kGsStage), g0 = 0;
+        if (lane == 0 && n) g0 = atomicAdd(sink.cursor + b * kGsCursorStride, n);
+        g0 = __shfl_sync(kFull, g0, 0);
+        for (uint32_t q = lane; q < n; q += 32) {
+            if (g0 + q < sink.cap) sink.pool[(size_t)b * sink.cap + g0 + q] = stage[b][q];
+            else gs_answer(stage[b][q], b, slice_shift, chunk_bit0, plane_words, count, sat);
+        }
+    }
+}
+
+// grid (parts, kGsBuckets), dispatched in index order: the resident CTAs share one or two slices of the table
+__global__ void __launch_bounds__(256, 4) s2_gsapply_kernel(GsSink sink, int slice_shift, uint64_t chunk_bit0, size_t plane_words,
+                                                            const uint32_t* __restrict__ count, uint32_t* __restrict__ sat) {
+    const uint32_t b = blockIdx.y;
+    const uint32_t n = min(sink.cursor[b * kGsCursorStride], sink.cap);
+    const uint2* __restrict__ in = sink.pool + (size_t)b * sink.cap;
+    for (uint32_t x = blockIdx.x * 256 + threadIdx.x; x < n; x += gridDim.x * 256) {
+        uint2 r;
+        asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(in + x));
+        gs_answer(r, b, slice_shift, chunk_bit0, plane_words, count, sat);
+    }
+}
+
+// single = some plane set, trio = all e planes set, word by word over tiles [tile_begin, tile_end)
+__global__ void s2_gscombine_kernel(const uint32_t* __restrict__ sat, size_t plane_words, int e, size_t w_lo, size_t w_hi,
+                                    uint32_t* __restrict__ single, uint32_t* __restrict__ trio) {
+    for (size_t w = w_lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < w_hi; w += (size_t)gridDim.x * blockDim.x) {
+        uint32_t any = 0u, all = 0xffffffffu;
+        for (int i = 0; i < e; ++i) { uint32_t v = sat[(size_t)i * plane_words + w]; any |= v; all &= v; }
+        single[w] = any; trio[w] = all;
+    }
+}
+
+int s2_gs_buckets() { return kGsBuckets; }
+int s2_gs_cursor_words() { return kGsBuckets * kGsCursorStride; }
+
+// one chunk of tiles [tile_begin, tile_end) (at most 2^18 tiles: positions inside a chunk fit 28 bits); cursor zeroed by the caller
+int launch_s2_gather_sliced(const uint32_t* image, const Contig* contigs, const Tile* tiles, uint64_t tile_begin, uint64_t tile_end,
+                            const HashP& hp, const uint32_t* count, uint32_t* sat, size_t plane_words, uint2* pool, uint32_t* cursor,
+                            uint32_t cap, cudaStream_t st) {
+    if (tile_end <= tile_begin) return 0;
+    GsSink sink{pool, cursor, cap};
+    int slice_shift = hp.k - 4;
+    unsigned grid = (unsigned)(tile_end - tile_begin);
+    uint64_t bit0 = tile_begin * kTile;
+    switch (hp.e) {
+        case 1: s2_gsemit_kernel<1><<<grid, 256, 0, st>>>(image, contigs, tiles, tile_begin, tile_begin, hp, slice_shift, plane_words, count, sat, sink); break;
+        case 2: s2_gsemit_kernel<2><<<grid, 256, 0, st>>>(image, contigs, tiles, tile_begin, tile_begin, hp, slice_shift, plane_words, count, sat, sink); break;
+        case 3: s2_gsemit_kernel<3><<<grid, 256, 0, st>>>(image, contigs, tiles, tile_begin, tile_begin, hp, slice_shift, plane_words, count, sat, sink); break;
+        default: s2_gsemit_kernel<4><<<grid, 256, 0, st>>>(image, contigs, tiles, tile_begin, tile_begin, hp, slice_shift, plane_words, count, sat, sink); break;
+    }
+    s2_gsapply_kernel<<<dim3(kSMs * 2, kGsBuckets), 256, 0, st>>>(sink, slice_shift, bit0, plane_words, count, sat);
+    return 2;
+}
+
+int launch_s2_gather_combine(const uint32_t* sat, size_t plane_words, int e, uint64_t tile_begin, uint64_t tile_end, uint32_t* single,
+                             uint32_t* trio, cudaStream_t st) {
+    if (tile_end <= tile_begin) return 0;
+    s2_gscombine_kernel<<<kSMs * 8, 256, 0, st>>>(sat, plane_words, e, (size_t)tile_begin * kTileWords, (size_t)tile_end * kTileWords, single, trio);
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Peak registration through buckets.  Every flagged position stamps its peak id on up to e entries of the
+// 2^k-entry peak table: as direct atomics that is one random 128-byte DRAM read-modify-write per k-mer (cfg4: ~6 G of
+// them, 466 ms).  Instead the (hash, id) records are appended to 512 buckets chosen by the hash's bits [9, 18) -- uniform
+// middle bits, DESIGN.md 3 -- through per-CTA shared-memory stages flushed in runs, and applied bucket by bucket: the
+// peak-table entries of one bucket are 32 MiB (2^14 runs of 2 KiB) and its count-table entries 2 MiB, so while a bucket is
+// being applied the scatter-max and the count > 0 test (E:250,265) run against L2, not DRAM.
+// ------------------------------------------------------------------------------------------------
+constexpr int kRegBuckets = 512, kRegStage = 24, kRegFlushMin = 8;
+constexpr int kRegCursorStride = 32;                           // words between bucket cursors (own 128-byte line each)
+__host__ __device__ inline uint32_t reg_bucket(uint32_t h) { return (h >> 9) & (kRegBuckets - 1); }
+
+struct RegSink {
+    uint2* pool; uint32_t* cursor; uint32_t cap;               // bucket b occupies pool[b * cap .. +cap); cursor[b * kRegCursorStride]
+};
+
+__device__ __forceinline__ void reg_apply_one(uint32_t h, uint32_t id, const HashP& hp, const uint32_t* __restrict__ count,
+                                              uint32_t* __restrict__ peak_kmer, uint32_t* __restrict__ prefilter) {
+    uint32_t g = tbl_index(h, hp);
+    if (((ld_table(count + (g >> 4)) >> ((g & 15u) * 2)) & 3u) == 0u) return;   // E:250,265: hit > 0
+    atomicMax(peak_kmer + h, id);
+    if (prefilter) { uint32_t slot = prefilter_slot(h); atomicOr(prefilter + (slot >> 5), 1u << (slot & 31)); }
+}
+
+template <int E>
+__global__ void __launch_bounds__(256, 2) s2_regemit_kernel(const uint32_t* __restrict__ image, const Contig* __restrict__ contigs,
+                                                            const Tile* __restrict__ tiles, const uint32_t* __restrict__ need_list,
+                                                            const uint32_t* __restrict__ n_need, uint32_t it_lo, uint32_t it_hi, HashP hp,
+                                                            const uint32_t* __restrict__ count, const uint32_t* __restrict__ flagged,
+                                                            const uint32_t* __restrict__ tile_base, int32_t* __restrict__ loci, uint32_t loci_cap,
+                                                            uint32_t* __restrict__ peak_kmer, uint32_t* __restrict__ prefilter, RegSink sink) {
+    extern __shared__ __align__(16) uint32_t dyn[];
+    uint2* stage = reinterpret_cast<uint2*>(dyn);               // [kRegBuckets][kRegStage]
+    uint32_t* cnt = dyn + 2 * kRegBuckets * kRegStage;          // [kRegBuckets]
+    __shared__ uint32_t opener[kTileWords];
+    __shared__ int cum[kTileWords + 1];
+    const int e = E ? E : hp.e;
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int b = threadIdx.x; b < kRegBuckets; b += 256) cnt[b] = 0;
+    const uint32_t hi = min(it_hi, *n_need);
+    auto direct = [&](uint32_t b, uint2 r) {                     // past a stage or a bucket region: rare, exact either way
+        uint32_t g = atomicAdd(sink.cursor + b * kRegCursorStride, 1u);
+        if (g < sink.cap) sink.pool[(size_t)b * sink.cap + g] = r;
+        else reg_apply_one(r.x, r.y, hp, count, peak_kmer, prefilter);
+    };
+    auto flush = [&](bool final) {
+        for (int b = threadIdx.x; b < kRegBuckets; b += 256) {
+            uint32_t n = min(cnt[b], (uint32_t)kRegStage);
+            if (n >= (uint32_t)kRegFlushMin || (final && n)) {
+                uint32_t g = atomicAdd(sink.cursor + b * kRegCursorStride, n);
+                const uint2* from = stage + b * kRegStage;
+                for (uint32_t q = 0; q < n; ++q) {
+                    if (g + q < sink.cap) sink.pool[(size_t)b * sink.cap + g + q] = from[q];
+                    else reg_apply_one(from[q].x, from[q].y, hp, count, peak_kmer, prefilter);
+                }
+                n = 0;
+            }
+            cnt[b] = n;
+        }
+    };
+    for (uint32_t it = it_lo + blockIdx.x; it < hi; it += gridDim.x) {
+        const uint64_t tix = need_list[it];
+        Tile t = tiles[tix];
+        Contig c = contigs[t.contig];
+        bool fl[4], op[4];
+        bool any = false;
+        __syncthreads();                                        // previous round: stage writers and opener/cum readers are done
+        flush(false);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            int xl = r * 256 + threadIdx.x;
+            uint32_t w = flagged[(size_t)tix * kTileWords + (xl >> 5)];
+            fl[r] = (w >> (xl & 31)) & 1u;
+            op[r] = fl[r] && opens_peak(flagged, tix, t.j0, (long)t.j0 + xl);
+            uint32_t wo = __ballot_sync(kFull, op[r]);
+            if (lane == 0) opener[r * 8 + warp] = wo;
+            any |= fl[r];
+        }
+        if (!__syncthreads_or(any)) continue;                   // (also orders the flush before this round's stage writes)
+        prefix_words(opener, cum, kTileWords);
+        __syncthreads();
+        long np = (long)c.len - hp.k + 1;
+        uint32_t base = tile_base[tix];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if (!fl[r]) continue;
+            int xl = r * 256 + threadIdx.x;
+            long j = (long)t.j0 + xl;
+            uint32_t id = base + (uint32_t)bits_upto(opener, cum, xl) - 1u;
+            if (op[r] && id < loci_cap) { loci[2 * (size_t)id] = (int32_t)t.contig + 1; loci[2 * (size_t)id + 1] = (int32_t)j; }
+            if (j < np && id != 0u) {                                         // j = len-k+1 reads the zero tail (Q6); id 0 never registers (Q10)
+                const uint32_t* hashes = image + c.hash_word + (size_t)j * e;
+#pragma unroll
+                for (int i = 0; i < (E ? E : kMaxE); ++i) {
+                    if (i >= e) break;
+                    uint32_t h = ld_stream(hashes + i);
+                    if (!h) continue;
+                    uint32_t b = reg_bucket(h);
+                    uint32_t slot = atomicAdd(&cnt[b], 1u);
+                    if (slot < (uint32_t)kRegStage) stage[b * kRegStage + slot] = make_uint2(h, id);
+                    else direct(b, make_uint2(h, id));
+                }
+            }
+        }
+    }
+    __syncthreads();
+    flush(true);
+}
+
+// grid (parts, kRegBuckets): blocks are dispatched in index order, so at any time the resident CTAs work on one or two
+// adjacent buckets and those buckets' table entries stay in L2
+__global__ void __launch_bounds__(256, 4) s2_regapply_kernel(RegSink sink, HashP hp, const uint32_t* __restrict__ count,
+                                                             uint32_t* __restrict__ peak_kmer, uint32_t* __restrict__ prefilter) {
+    const uint32_t b = blockIdx.y;
+    const uint32_t n = min(sink.cursor[b * kRegCursorStride], sink.cap);
+    const uint2* __restrict__ in = sink.pool + (size_t)b * sink.cap;
+    for (uint32_t x = blockIdx.x * 256 + threadIdx.x; x < n; x += gridDim.x * 256) {
+        uint2 r;
+        asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(in + x));
+        reg_apply_one(r.x, r.y, hp, count, peak_kmer, prefilter);
+    }
+}
+
+size_t s2_regemit_smem() { return (size_t)kRegBuckets * kRegStage * 8 + (size_t)kRegBuckets * 4; }
+int s2_reg_buckets() { return kRegBuckets; }
+int s2_reg_cursor_words() { return kRegBuckets * kRegCursorStride; }
+
+// one chunk of the needed-tile list [it_lo, it_hi): emit, then apply (cursor zeroed by the caller)
+int launch_s2_register_bucketed(const uint32_t* image, const Contig* contigs, const Tile* tiles, const uint32_t* need_list,
+                                const uint32_t* n_need, uint32_t it_lo, uint32_t it_hi, const HashP& hp, const uint32_t* count,
+                                const uint32_t* flagged, const uint32_t* tile_base, int32_t* loci, uint32_t loci_cap, uint32_t* peak_kmer,
+                                uint32_t* prefilter, uint2* pool, uint32_t* cursor, uint32_t cap, cudaStream_t st) {
+    if (it_hi <= it_lo) return 0;
+    RegSink sink{pool, cursor, cap};
+    size_t smem = s2_regemit_smem();
+    unsigned grid = it_hi - it_lo < (uint32_t)kSMs * 2 ? it_hi - it_lo : (uint32_t)kSMs * 2;
+#define LHGT_REGEMIT(EE)                                                                                                        \
+    do {                                                                                                                        \
+        if (cudaFuncSetAttribute(s2_regemit_kernel<EE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) \
+            return -1;                                                                                                          \
+        s2_regemit_kernel<EE><<<grid, 256, smem, st>>>(image, contigs, tiles, need_list, n_need, it_lo, it_hi, hp, count, flagged, \
+                                                      tile_base, loci, loci_cap, peak_kmer, prefilter, sink);                  \
+    } while (0)
+    if (hp.e == 3) LHGT_REGEMIT(3); else LHGT_REGEMIT(0);
+#undef LHGT_REGEMIT
+    s2_regapply_kernel<<<dim3(kSMs * 2, kRegBuckets), 256, 0, st>>>(sink, hp, count, peak_kmer, prefilter);
+    return 2;
 }
 
 constexpr int kS2Grid = kSMs * 8;                              // persistent grids over the needed-tile list
@@ -2077,33 +2349,51 @@ __global__ void __launch_bounds__(128) s3_vote_kernel(uint2* __restrict__ arena,
         uint2* list = arena + job.x;
         const int n_listed = (int)job.y;
         int n_t = 0;
-        for (int f = 0; f < n_listed; ++f) {
-            uint2 cd[E ? E : kMaxE];
-            uint32_t idx[E ? E : kMaxE], ent[E ? E : kMaxE];
+        // candidates are fetched a block of kAhead positions ahead of the vote: a thread walks its own list, so every load is
+        // its own sector and would otherwise put an L2 (or DRAM) round trip into each step of the serial chain
+        constexpr int kAhead = 4, EE = E ? E : kMaxE;
+        uint2 nxt[kAhead][EE];
+        auto fetch = [&](int f0) {
 #pragma unroll
-            for (int i = 0; i < (E ? E : kMaxE); ++i)
-                if (i < e) {
-                    cd[i] = list[(size_t)f * e + i];
-                    idx[i] = (cd[i].y * 2654435761u) >> shift;
+            for (int a = 0; a < kAhead; ++a)
+#pragma unroll
+                for (int i = 0; i < EE; ++i)
+                    nxt[a][i] = (i < e && f0 + a < n_listed) ? list[(size_t)(f0 + a) * e + i] : make_uint2(0u, 0u);
+        };
+        fetch(0);
+        for (int f0 = 0; f0 < n_listed; f0 += kAhead) {
+            uint2 cur[kAhead][EE];
+#pragma unroll
+            for (int a = 0; a < kAhead; ++a)
+#pragma unroll
+                for (int i = 0; i < EE; ++i) cur[a][i] = nxt[a][i];
+            fetch(f0 + kAhead);
+#pragma unroll
+            for (int a = 0; a < kAhead; ++a) {
+                if (f0 + a >= n_listed) break;
+                uint32_t idx[EE], ent[EE];
+#pragma unroll
+                for (int i = 0; i < EE; ++i)
+                    if (i < e) idx[i] = (cur[a][i].y * 2654435761u) >> shift;
+#pragma unroll
+                for (int i = 0; i < EE; ++i)
+                    if (i < e) ent[i] = cur[a][i].x ? table[idx[i] * stride] : 0u;
+                uint32_t sel_peak = 0, sel_slot = 0, sel_entry = 0;
+                int sel_votes = 0;
+                bool sel_seen = false;
+#pragma unroll
+                for (int i = 0; i < EE; ++i) {
+                    if (i >= e || !cur[a][i].x) continue;
+                    uint32_t en = ent[i], ix = idx[i];
+                    while (en != 0u && (en >> 10) != cur[a][i].y) { ix = (ix + 1u) & mask; en = table[ix * stride]; }
+                    if (en) {
+                        int v = (int)(en & 1023u);
+                        if (v >= sel_votes) { sel_peak = cur[a][i].x; sel_votes = v; sel_seen = true; sel_slot = ix; sel_entry = en; }
+                    } else if (sel_peak == 0) { sel_peak = cur[a][i].x; sel_votes = 0; sel_seen = false; sel_slot = ix; sel_entry = cur[a][i].y << 10; }
                 }
-#pragma unroll
-            for (int i = 0; i < (E ? E : kMaxE); ++i)
-                if (i < e) ent[i] = cd[i].x ? table[idx[i] * stride] : 0u;
-            uint32_t sel_peak = 0, sel_slot = 0, sel_entry = 0;
-            int sel_votes = 0;
-            bool sel_seen = false;
-#pragma unroll
-            for (int i = 0; i < (E ? E : kMaxE); ++i) {
-                if (i >= e || !cd[i].x) continue;
-                uint32_t en = ent[i], ix = idx[i];
-                while (en != 0u && (en >> 10) != cd[i].y) { ix = (ix + 1u) & mask; en = table[ix * stride]; }
-                if (en) {
-                    int v = (int)(en & 1023u);
-                    if (v >= sel_votes) { sel_peak = cd[i].x; sel_votes = v; sel_seen = true; sel_slot = ix; sel_entry = en; }
-                } else if (sel_peak == 0) { sel_peak = cd[i].x; sel_votes = 0; sel_seen = false; sel_slot = ix; sel_entry = cd[i].y << 10; }
+                table[sel_slot * stride] = sel_entry + 1u;
+                if (!sel_seen) list[n_t++] = make_uint2(sel_slot, sel_peak);  // n_t <= f + 1: that entry has been consumed (fetched) already
             }
-            table[sel_slot * stride] = sel_entry + 1u;
-            if (!sel_seen) list[n_t++] = make_uint2(sel_slot, sel_peak);      // n_t <= f + 1: that entry has been consumed
         }
         int largest = 0, second = 0, strong = 0;
         for (int t = 0; t < n_t; ++t) {

@@ -157,6 +157,28 @@ int launch_s2_register(const uint32_t* image, const Contig* contigs, const Tile*
                        const HashP& hp, const uint32_t* count, const uint32_t* flagged, const uint32_t* tile_base, int32_t* loci,
                        uint32_t loci_cap, uint32_t* peak_kmer, uint32_t* prefilter, int mode, cudaStream_t st);
 
+// S2 gather through table slices (tables > 128 MiB, e <= 4): one chunk of at most 2^18 tiles per call -- records into
+// s2_gs_buckets() regions of `cap` in `pool` (cursor: s2_gs_cursor_words() zeroed words), answered slice by slice into the e
+// bit planes `sat` (plane_words apart, zeroed by the caller); then launch_s2_gather_combine derives single and trio (both exact).
+int s2_gs_buckets();
+int s2_gs_cursor_words();
+int launch_s2_gather_sliced(const uint32_t* image, const Contig* contigs, const Tile* tiles, uint64_t tile_begin, uint64_t tile_end,
+                            const HashP& hp, const uint32_t* count, uint32_t* sat, size_t plane_words, uint2* pool, uint32_t* cursor,
+                            uint32_t cap, cudaStream_t st);
+int launch_s2_gather_combine(const uint32_t* sat, size_t plane_words, int e, uint64_t tile_begin, uint64_t tile_end, uint32_t* single,
+                             uint32_t* trio, cudaStream_t st);
+
+// Registration through buckets, one chunk [it_lo, it_hi) of the needed-tile list: (hash, id) records are appended to
+// s2_reg_buckets() regions of `cap` records each in `pool` (cursor: s2_reg_cursor_words() zeroed words) and applied bucket by
+// bucket against L2-resident slices of the tables.  Whatever does not fit is applied directly: exact either way.
+size_t s2_regemit_smem();
+int s2_reg_buckets();
+int s2_reg_cursor_words();
+int launch_s2_register_bucketed(const uint32_t* image, const Contig* contigs, const Tile* tiles, const uint32_t* need_list,
+                                const uint32_t* n_need, uint32_t it_lo, uint32_t it_hi, const HashP& hp, const uint32_t* count,
+                                const uint32_t* flagged, const uint32_t* tile_base, int32_t* loci, uint32_t loci_cap, uint32_t* peak_kmer,
+                                uint32_t* prefilter, uint2* pool, uint32_t* cursor, uint32_t cap, cudaStream_t st);
+
 // kept peaks (filter != 0) in id order: phase 0 counts per 1024-peak block and scans (block_cnt / block_base: peaks_keep_blocks(n)
 // words, scan_tmp: scan_tmp_words of that), phase 1 writes (contig, position) pairs into `out`
 uint64_t peaks_keep_blocks(uint64_t n);

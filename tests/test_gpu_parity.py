@@ -587,11 +587,20 @@ def _screened(case, workdir, **env):
     return s, o, ratio, (fq1, fq2, idx)
 
 
+@pytest.mark.parametrize("sliced", [None, "big", "64"], ids=["direct", "sliced", "sliced_small_regions"])
 @pytest.mark.parametrize("name", ["base_k24", "base_k20", "noisy", "shorts_bp", "base_k24_e4", "base_k31_e1"])
-def test_s2_in_steps_over_tile_ranges_equals_the_oracle(name, workdir):
+def test_s2_in_steps_over_tile_ranges_equals_the_oracle(name, sliced, workdir, monkeypatch):
     """gather / complete on tile ranges (what each rank of the multi-GPU plan runs) + mark + finish == one s2_peaks ==
-    the oracle: the short-circuit trio gather, the hot/needed tile marking and the needed-tile passes drop nothing."""
+    the oracle: the short-circuit trio gather, the hot/needed tile marking and the needed-tile passes drop nothing.
+    `sliced` runs the gather through table slices instead (records bucketed by slice, answered from L2; forced here at
+    small k), once with record regions so small that every call takes several chunks and overflows."""
     case = fixtures.BY_NAME[name]
+    if sliced:
+        monkeypatch.setenv("LHGT_S2_SLICED", "1")
+        if sliced != "big":
+            monkeypatch.setenv("LHGT_S2_POOL_KB", sliced)
+    else:
+        monkeypatch.setenv("LHGT_S2_SLICED", "0")
     s, o, ratio, (fq1, fq2, idx) = _screened(case, workdir)
     with s:
         npo = o.s2_peaks(idx, case.hit, case.match, case.max_peak)
@@ -731,3 +740,29 @@ def test_fq2_with_leading_records_is_resynchronised_like_the_reference(workdir):
         assert ei.value.code == -7
     finally:
         fixtures.clean_outputs(fa)
+
+
+@pytest.mark.parametrize("name,pool_kb", [("base_k20", None), ("base_k20", "64"), ("noisy", "16"), ("base_k24_e4", None)])
+def test_bucketed_registration_equals_direct(name, pool_kb, workdir, monkeypatch):
+    """Peak registration through hash buckets (records staged in shared memory, appended in runs, applied bucket by bucket
+    against L2-resident table slices) == the direct scatter-max == the oracle's peak_kmer; small record regions force
+    several chunks and the overflow path."""
+    case = fixtures.BY_NAME[name]
+    s, o, ratio, (fq1, fq2, idx) = _screened(case, workdir)
+    with s:
+        npo = o.s2_peaks(idx, case.hit, case.match, case.max_peak)
+        want = o.peak_kmer().copy()
+        monkeypatch.setenv("LHGT_REG_BUCKETED", "1")
+        if pool_kb:
+            monkeypatch.setenv("LHGT_REG_POOL_KB", pool_kb)
+        assert s.s2_peaks(case.hit, case.match, case.max_peak) == npo
+        assert np.array_equal(want, s.peak_kmer())
+        assert np.array_equal(o.peak_loci(), s.peaks()[0])
+        monkeypatch.setenv("LHGT_REG_BUCKETED", "0")
+        assert s.s2_peaks(case.hit, case.match, case.max_peak) == npo      # un-writes / clears, registers again directly
+        assert np.array_equal(want, s.peak_kmer())
+        monkeypatch.setenv("LHGT_REG_BUCKETED", "1")
+        assert s.s2_peaks(case.hit, case.match, case.max_peak) == npo
+        so, sg = o.s3_pairs(fq1, fq2, ratio), s.s3_pairs()
+        assert so == sg and np.array_equal(o.peak_filter() >= 1, s.peaks()[1] >= 1)
+    o.close()
