@@ -1711,8 +1711,19 @@ extern "C" long lhgt_flagged_positions(const lhgt_ctx* c) { return c ? c->n_flag
 extern "C" int lhgt_peak_kmer_copy(lhgt_ctx* c, uint32_t* dst) {
     if (!c || !dst) return fail(LHGT_E_ARG, "null pointer");
     CU(cudaSetDevice(c->device));
-    CU(cudaMemcpyAsync(dst, c->d_peak_kmer, (1ull << c->k) * 4, cudaMemcpyDeviceToHost, c->st));
-    CU(cudaStreamSynchronize(c->st));
+    // the table is stored leaf-major like the count table; hand it out in hash order, 2^26 entries at a time
+    const uint64_t entries = 1ull << c->k, step = std::min<uint64_t>(entries, 1ull << 26);
+    uint32_t* d = nullptr;
+    int rc = dev_alloc(&d, step);
+    if (rc) return rc;
+    cudaError_t e1 = cudaSuccess;
+    for (uint64_t h0 = 0; h0 < entries && e1 == cudaSuccess; h0 += step) {
+        c->launches += launch_peak_unpack(c->d_peak_kmer, h0, step, c->hp, d, c->st);
+        e1 = cudaMemcpyAsync(dst + h0, d, step * 4, cudaMemcpyDeviceToHost, c->st);
+        if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(c->st);
+    }
+    cudaFree(d);
+    if (e1 != cudaSuccess) return fail(LHGT_E_CUDA, "peak table copy failed: %s", cudaGetErrorString(e1));
     return 0;
 }
 

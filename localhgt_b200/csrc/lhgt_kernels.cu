@@ -677,7 +677,6 @@ __global__ void __launch_bounds__(256) index_build_kernel(const uint8_t* __restr
                                                           const Tile* __restrict__ tiles, HashP hp,
                                                           uint32_t* __restrict__ image, uint8_t* __restrict__ valid_out) {
     __shared__ uint32_t planes[4 * kIbPlane];
-    __shared__ __align__(16) uint32_t outw[E ? kTile * E + 4 : 1];   // the tile's hashes, position-major, as the file holds them
     const int e = E ? E : hp.e;
     Tile t = tiles[blockIdx.x];
     Contig c = contigs[t.contig];
@@ -700,36 +699,19 @@ __global__ void __launch_bounds__(256) index_build_kernel(const uint8_t* __restr
     }
     __syncthreads();
     if (j0 == 0 && threadIdx.x == 0) image[c.hash_word - 1] = c.len;
-    uint32_t* dst = image + c.hash_word + (size_t)j0 * e;
-    const int n_here = (int)min((long)kTile, np - j0);           // positions of this tile that hold a k-mer
-    // With E known the hashes are staged in shared memory and leave as 16-byte vectors: a thread's own e words sit 4e
-    // bytes from its neighbour's, so direct stores would touch every sector of the run three times over.
-    const int mis = E ? (int)(((uintptr_t)dst >> 2) & 3u) : 0;    // words by which dst trails a 16-byte boundary
+    // (staging the tile's hashes in shared memory and storing 16-byte vectors was measured: 142 against 164 Gbp/s)
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         int jl = r * 256 + threadIdx.x;
-        if (jl < n_here) {
+        long j = j0 + jl;
+        if (j < np) {
             KmerWin kw = make_win<kIbPlane>(planes, jl, hp);
+            uint32_t* dst = image + c.hash_word + (size_t)j * e;
 #pragma unroll
             for (int i = 0; i < (E ? E : kMaxE); ++i)
-                if (i < e) {
-                    uint32_t hv = kw.valid ? hash_of(kw, hp, i) : 0u;
-                    if (E) outw[mis + jl * E + i] = hv; else dst[(size_t)jl * e + i] = hv;
-                }
-            if (valid_out) valid_out[j0 + jl] = kw.valid;
+                if (i < e) dst[i] = kw.valid ? hash_of(kw, hp, i) : 0u;
+            if (valid_out) valid_out[j] = kw.valid;
         }
-    }
-    if (E) {
-        __syncthreads();
-        const int total = n_here * E;                            // words; word x of the run sits at outw[mis + x] and goes to dst[x]
-        const int head = min(total, (4 - mis) & 3);              // words before the first 16-byte boundary of dst
-        const int nvec = (total - head) >> 2;
-        if ((int)threadIdx.x < head) dst[threadIdx.x] = outw[mis + threadIdx.x];
-        uint4* dst4 = reinterpret_cast<uint4*>(dst + head);
-        const uint4* src4 = reinterpret_cast<const uint4*>(outw + mis + head);    // (mis + head) % 4 == 0
-        for (int v = threadIdx.x; v < nvec; v += 256) dst4[v] = src4[v];
-        int tail0 = head + (nvec << 2);
-        if ((int)threadIdx.x < total - tail0) dst[tail0 + threadIdx.x] = outw[mis + tail0 + threadIdx.x];
     }
 }
 
@@ -1645,12 +1627,12 @@ __global__ void __launch_bounds__(256) s2_register_kernel(const uint32_t* __rest
                     uint32_t g = tbl_index(h, hp);
                     uint32_t cnt = (count[g >> 4] >> ((g & 15u) * 2)) & 3u;
                     if (!cnt) continue;                                        // E:250,265: hit > 0
-                    uint32_t slot = prefilter_slot(h);
+                    uint32_t slot = prefilter_slot(g);
                     if (mode == 0) {
-                        atomicMax(peak_kmer + h, id);
+                        atomicMax(peak_kmer + g, id);                           // the peak table is laid out like the count table (tbl_index)
                         if (prefilter) atomicOr(prefilter + (slot >> 5), 1u << (slot & 31));
                     } else {
-                        peak_kmer[h] = 0u;
+                        peak_kmer[g] = 0u;
                         prefilter[slot >> 5] = 0u;
                     }
                 }
@@ -1662,12 +1644,12 @@ __global__ void __launch_bounds__(256) s2_register_kernel(const uint32_t* __rest
 // ------------------------------------------------------------------------------------------------
 // S2 gather through table slices (DESIGN.md 4.5a').  A direct probe of a count table far larger than L2 is a 128-byte DRAM
 // fill for 2 useful bits.  Here the stored hashes of a chunk of the reference are turned into (position, table index)
-// records, appended to 16 buckets = 16 contiguous slices of the table (64 MiB each at k = 32), and answered bucket by bucket
-// while that slice sits in L2; a saturated counter sets the position's bit in the hash's own plane (records keep their
+// records, appended to 128 buckets = 128 contiguous slices of the table (8 MiB each at k = 32: the two or three slices in
+// flight, the record stream and the planes share L2 comfortably), and answered bucket by bucket while that slice sits in L2; a saturated counter sets the position's bit in the hash's own plane (records keep their
 // position order inside a bucket, so those atomics stay in L2 too).  Everything that touches DRAM is then a stream: the
 // image once, the records once out and once in, the table once per chunk.
 // ------------------------------------------------------------------------------------------------
-constexpr int kGsBuckets = 16, kGsStage = 256, kGsCursorStride = 32;
+constexpr int kGsBuckets = 128, kGsLog2 = 7, kGsStage = 40, kGsCursorStride = 32;
 
 struct GsSink { uint2* pool; uint32_t* cursor; uint32_t cap; };   // bucket b: pool[b * cap .. +cap), cursor[b * kGsCursorStride]
 
@@ -1762,7 +1744,7 @@ int launch_s2_gather_sliced(const uint32_t* image, const Contig* contigs, const 
                             uint32_t cap, cudaStream_t st) {
     if (tile_end <= tile_begin) return 0;
     GsSink sink{pool, cursor, cap};
-    int slice_shift = hp.k - 4;
+    int slice_shift = hp.k - kGsLog2;
     unsigned grid = (unsigned)(tile_end - tile_begin);
     uint64_t bit0 = tile_begin * kTile;
     switch (hp.e) {
@@ -1785,25 +1767,26 @@ int launch_s2_gather_combine(const uint32_t* sat, size_t plane_words, int e, uin
 // ------------------------------------------------------------------------------------------------
 // Peak registration through buckets.  Every flagged position stamps its peak id on up to e entries of the
 // 2^k-entry peak table: as direct atomics that is one random 128-byte DRAM read-modify-write per k-mer (cfg4: ~6 G of
-// them, 466 ms).  Instead the (hash, id) records are appended to 512 buckets chosen by the hash's bits [9, 18) -- uniform
-// middle bits, DESIGN.md 3 -- through per-CTA shared-memory stages flushed in runs, and applied bucket by bucket: the
-// peak-table entries of one bucket are 32 MiB (2^14 runs of 2 KiB) and its count-table entries 2 MiB, so while a bucket is
-// being applied the scatter-max and the count > 0 test (E:250,265) run against L2, not DRAM.
+// them, 466 ms).  Instead (table index, id) records are appended to 512 buckets = the top 9 bits of the table index -- the
+// peak table shares the count table's leaf-major layout, whose top bits are the uniform middle bits of the
+// hash -- through per-CTA shared-memory stages flushed in runs, and applied bucket by bucket: a bucket is one contiguous
+// 1/512 of both tables (32 MiB and 2 MiB at k = 32), so while it is being applied the scatter-max and the count > 0 test
+// (E:250,265) run against L2, not DRAM.
 // ------------------------------------------------------------------------------------------------
 constexpr int kRegBuckets = 512, kRegStage = 24, kRegFlushMin = 8;
 constexpr int kRegCursorStride = 32;                           // words between bucket cursors (own 128-byte line each)
-__host__ __device__ inline uint32_t reg_bucket(uint32_t h) { return (h >> 9) & (kRegBuckets - 1); }
 
 struct RegSink {
     uint2* pool; uint32_t* cursor; uint32_t cap;               // bucket b occupies pool[b * cap .. +cap); cursor[b * kRegCursorStride]
+    int shift;                                                 // bucket of table index g = g >> shift (its top 9 bits)
 };
 
-__device__ __forceinline__ void reg_apply_one(uint32_t h, uint32_t id, const HashP& hp, const uint32_t* __restrict__ count,
+// record = (table index g, peak id)
+__device__ __forceinline__ void reg_apply_one(uint32_t g, uint32_t id, const uint32_t* __restrict__ count,
                                               uint32_t* __restrict__ peak_kmer, uint32_t* __restrict__ prefilter) {
-    uint32_t g = tbl_index(h, hp);
     if (((ld_table(count + (g >> 4)) >> ((g & 15u) * 2)) & 3u) == 0u) return;   // E:250,265: hit > 0
-    atomicMax(peak_kmer + h, id);
-    if (prefilter) { uint32_t slot = prefilter_slot(h); atomicOr(prefilter + (slot >> 5), 1u << (slot & 31)); }
+    atomicMax(peak_kmer + g, id);
+    if (prefilter) { uint32_t slot = prefilter_slot(g); atomicOr(prefilter + (slot >> 5), 1u << (slot & 31)); }
 }
 
 template <int E>
@@ -1825,23 +1808,33 @@ __global__ void __launch_bounds__(256, 2) s2_regemit_kernel(const uint32_t* __re
     auto direct = [&](uint32_t b, uint2 r) {                     // past a stage or a bucket region: rare, exact either way
         uint32_t g = atomicAdd(sink.cursor + b * kRegCursorStride, 1u);
         if (g < sink.cap) sink.pool[(size_t)b * sink.cap + g] = r;
-        else reg_apply_one(r.x, r.y, hp, count, peak_kmer, prefilter);
+        else reg_apply_one(r.x, r.y, count, peak_kmer, prefilter);
     };
+    // A warp hands over its share of the buckets, 32 at a time: lane l looks at bucket base + l, the reservations are one
+    // atomic per flushing bucket, and every run leaves as one coalesced store per 32 records (a lane writing its own
+    // bucket's run would make each store instruction touch 32 different sectors).
     auto flush = [&](bool final) {
-        for (int b = threadIdx.x; b < kRegBuckets; b += 256) {
+        for (int base = warp * 32; base < kRegBuckets; base += 256) {
+            int b = base + lane;
             uint32_t n = min(cnt[b], (uint32_t)kRegStage);
-            if (n >= (uint32_t)kRegFlushMin || (final && n)) {
-                uint32_t g = atomicAdd(sink.cursor + b * kRegCursorStride, n);
-                const uint2* from = stage + b * kRegStage;
-                for (uint32_t q = 0; q < n; ++q) {
-                    if (g + q < sink.cap) sink.pool[(size_t)b * sink.cap + g + q] = from[q];
-                    else reg_apply_one(from[q].x, from[q].y, hp, count, peak_kmer, prefilter);
+            bool go = n >= (uint32_t)kRegFlushMin || (final && n);
+            uint32_t g = go ? atomicAdd(sink.cursor + b * kRegCursorStride, n) : 0u;
+            if (go) cnt[b] = 0; else cnt[b] = n;
+            uint32_t m = __ballot_sync(kFull, go);
+            while (m) {
+                int src = __ffs(m) - 1;
+                m &= m - 1;
+                uint32_t nb = __shfl_sync(kFull, n, src), gb = __shfl_sync(kFull, g, src);
+                int bb = base + src;
+                if ((uint32_t)lane < nb) {
+                    uint2 r = stage[bb * kRegStage + lane];
+                    if (gb + lane < sink.cap) sink.pool[(size_t)bb * sink.cap + gb + lane] = r;
+                    else reg_apply_one(r.x, r.y, count, peak_kmer, prefilter);
                 }
-                n = 0;
             }
-            cnt[b] = n;
         }
     };
+    static_assert(kRegStage <= 32, "a run is written by one warp instruction");
     for (uint32_t it = it_lo + blockIdx.x; it < hi; it += gridDim.x) {
         const uint64_t tix = need_list[it];
         Tile t = tiles[tix];
@@ -1879,10 +1872,10 @@ __global__ void __launch_bounds__(256, 2) s2_regemit_kernel(const uint32_t* __re
                     if (i >= e) break;
                     uint32_t h = ld_stream(hashes + i);
                     if (!h) continue;
-                    uint32_t b = reg_bucket(h);
+                    uint32_t g = tbl_index(h, hp), b = g >> sink.shift;
                     uint32_t slot = atomicAdd(&cnt[b], 1u);
-                    if (slot < (uint32_t)kRegStage) stage[b * kRegStage + slot] = make_uint2(h, id);
-                    else direct(b, make_uint2(h, id));
+                    if (slot < (uint32_t)kRegStage) stage[b * kRegStage + slot] = make_uint2(g, id);
+                    else direct(b, make_uint2(g, id));
                 }
             }
         }
@@ -1892,8 +1885,8 @@ __global__ void __launch_bounds__(256, 2) s2_regemit_kernel(const uint32_t* __re
 }
 
 // grid (parts, kRegBuckets): blocks are dispatched in index order, so at any time the resident CTAs work on one or two
-// adjacent buckets and those buckets' table entries stay in L2
-__global__ void __launch_bounds__(256, 4) s2_regapply_kernel(RegSink sink, HashP hp, const uint32_t* __restrict__ count,
+// adjacent buckets; a bucket is a contiguous 1/512 of both tables (peak table: 32 MiB, count table: 2 MiB at k = 32)
+__global__ void __launch_bounds__(256, 4) s2_regapply_kernel(RegSink sink, const uint32_t* __restrict__ count,
                                                              uint32_t* __restrict__ peak_kmer, uint32_t* __restrict__ prefilter) {
     const uint32_t b = blockIdx.y;
     const uint32_t n = min(sink.cursor[b * kRegCursorStride], sink.cap);
@@ -1901,7 +1894,7 @@ __global__ void __launch_bounds__(256, 4) s2_regapply_kernel(RegSink sink, HashP
     for (uint32_t x = blockIdx.x * 256 + threadIdx.x; x < n; x += gridDim.x * 256) {
         uint2 r;
         asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(in + x));
-        reg_apply_one(r.x, r.y, hp, count, peak_kmer, prefilter);
+        reg_apply_one(r.x, r.y, count, peak_kmer, prefilter);
     }
 }
 
@@ -1915,7 +1908,7 @@ int launch_s2_register_bucketed(const uint32_t* image, const Contig* contigs, co
                                 const uint32_t* flagged, const uint32_t* tile_base, int32_t* loci, uint32_t loci_cap, uint32_t* peak_kmer,
                                 uint32_t* prefilter, uint2* pool, uint32_t* cursor, uint32_t cap, cudaStream_t st) {
     if (it_hi <= it_lo) return 0;
-    RegSink sink{pool, cursor, cap};
+    RegSink sink{pool, cursor, cap, hp.k > 9 ? hp.k - 9 : 0};
     size_t smem = s2_regemit_smem();
     unsigned grid = it_hi - it_lo < (uint32_t)kSMs * 2 ? it_hi - it_lo : (uint32_t)kSMs * 2;
 #define LHGT_REGEMIT(EE)                                                                                                        \
@@ -1927,7 +1920,7 @@ int launch_s2_register_bucketed(const uint32_t* image, const Contig* contigs, co
     } while (0)
     if (hp.e == 3) LHGT_REGEMIT(3); else LHGT_REGEMIT(0);
 #undef LHGT_REGEMIT
-    s2_regapply_kernel<<<dim3(kSMs * 2, kRegBuckets), 256, 0, st>>>(sink, hp, count, peak_kmer, prefilter);
+    s2_regapply_kernel<<<dim3(kSMs * 2, kRegBuckets), 256, 0, st>>>(sink, count, peak_kmer, prefilter);
     return 2;
 }
 
@@ -2045,7 +2038,7 @@ __device__ __forceinline__ int s3_scan_mate(const uint8_t* src, int len, const u
 #pragma unroll
         for (int i = 0; i < (E ? E : kMaxE); ++i)
             if (i < e) {
-                h[i] = le_hash(kw, hp, i);
+                h[i] = tbl_index(le_hash(kw, hp, i), hp);                 // table index from here on (count and peak tables share the layout)
                 uint32_t slot = prefilter_slot(h[i]);
                 fw[i] = !kw.valid ? 0u : prefilter ? ld_table(prefilter + (slot >> 5)) >> (slot & 31) : 1u;   // no filter: it is saturated
             }
@@ -2537,6 +2530,17 @@ __global__ void count_unpack_kernel(const uint32_t* __restrict__ count, uint64_t
         uint32_t g = tbl_index((uint32_t)h, hp);
         out[h] = (count[g >> 4] >> ((g & 15u) * 2)) & 3u;
     }
+}
+
+// out[h - h0] = peak_kmer[tbl_index(h)] for h in [h0, h0 + n): the peak table in hash order (test hook)
+__global__ void peak_unpack_kernel(const uint32_t* __restrict__ peak_kmer, uint64_t h0, uint64_t n, HashP hp, uint32_t* __restrict__ out) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        out[i] = peak_kmer[tbl_index((uint32_t)(h0 + i), hp)];
+}
+
+int launch_peak_unpack(const uint32_t* peak_kmer, uint64_t h0, uint64_t n, const HashP& hp, uint32_t* out, cudaStream_t st) {
+    peak_unpack_kernel<<<kSMs * 8, 256, 0, st>>>(peak_kmer, h0, n, hp, out);
+    return 1;
 }
 
 int launch_count_unpack(const uint32_t* count, uint64_t entries, const HashP& hp, uint8_t* out, cudaStream_t st) {

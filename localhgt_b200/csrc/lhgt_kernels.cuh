@@ -202,6 +202,7 @@ int s3_warps_per_block();
 
 // bit o of `bits` := o < n && m[o] < m_star (the sampling decision of ordinal o); the other bits of the 50 M-bit array := 0
 int launch_sample_bits(const uint32_t* m, uint64_t n, uint32_t m_star, uint32_t* bits, uint64_t words, cudaStream_t st);
+int launch_peak_unpack(const uint32_t* peak_kmer, uint64_t h0, uint64_t n, const HashP& hp, uint32_t* out, cudaStream_t st);
 int launch_count_unpack(const uint32_t* count, uint64_t entries, const HashP& hp, uint8_t* out, cudaStream_t st);
 int launch_count_merge(uint32_t* count, const uint32_t* other, uint64_t words, cudaStream_t st);
 // out4[1..3] += number of counters equal to 1, 2, 3 (out4 zeroed by the caller; [0] follows from the table size)
@@ -212,8 +213,8 @@ struct PeerTables { uint32_t* table[kMaxPeers]; };   // every rank's count table
 // table_words must divide by 4 * world; slice `rank` of every table := min(3, sum over ranks)
 int launch_count_exchange(const PeerTables& pt, int world, int rank, uint64_t table_words, cudaStream_t st);
 
-__host__ __device__ inline uint32_t prefilter_slot(uint32_t h) {
-    // any function of h is exact here (the filter only gates the exact lookup); fold the high bits in
+__host__ __device__ inline uint32_t prefilter_slot(uint32_t h) {   // h: the TABLE INDEX of the hash (tbl_index), like the peak table's
+    // any function of it is exact here (the filter only gates the exact lookup); fold the high bits in
     return (h ^ (h >> kFilterLog2)) & ((1u << kFilterLog2) - 1u);
 }
 
