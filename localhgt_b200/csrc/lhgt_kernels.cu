@@ -1701,13 +1701,21 @@ __global__ void __launch_bounds__(256) s2_gsemit_kernel(const uint32_t* __restri
         }
     }
     __syncthreads();
-    for (int b = warp; b < kGsBuckets; b += 8) {                              // a warp hands each of its buckets over as one coalesced run
-        uint32_t n = min(cnt[b], (uint32_t)kGsStage), g0 = 0;
-        if (lane == 0 && n) g0 = atomicAdd(sink.cursor + b * kGsCursorStride, n);
-        g0 = __shfl_sync(kFull, g0, 0);
-        for (uint32_t q = lane; q < n; q += 32) {
-            if (g0 + q < sink.cap) sink.pool[(size_t)b * sink.cap + g0 + q] = stage[b][q];
-            else gs_answer(stage[b][q], b, slice_shift, chunk_bit0, plane_words, count, sat);
+    // a warp hands its 16 buckets over: all reservations first (one atomic per lane, in flight together), then one coalesced
+    // run per bucket
+    static_assert(kGsBuckets == 128 && kGsStage <= 64, "flush layout");
+    {
+        const int b_mine = warp * 16 + (lane & 15);
+        uint32_t n_mine = min(cnt[b_mine], (uint32_t)kGsStage), g_mine = 0;
+        if (lane < 16 && n_mine) g_mine = atomicAdd(sink.cursor + b_mine * kGsCursorStride, n_mine);
+#pragma unroll 1
+        for (int u = 0; u < 16; ++u) {
+            const int b = warp * 16 + u;
+            uint32_t n = __shfl_sync(kFull, n_mine, u), g0 = __shfl_sync(kFull, g_mine, u);
+            for (uint32_t q = lane; q < n; q += 32) {
+                if (g0 + q < sink.cap) sink.pool[(size_t)b * sink.cap + g0 + q] = stage[b][q];
+                else gs_answer(stage[b][q], b, slice_shift, chunk_bit0, plane_words, count, sat);
+            }
         }
     }
 }
@@ -1720,7 +1728,7 @@ __global__ void __launch_bounds__(256, 4) s2_gsapply_kernel(GsSink sink, int sli
     const uint2* __restrict__ in = sink.pool + (size_t)b * sink.cap;
     for (uint32_t x = blockIdx.x * 256 + threadIdx.x; x < n; x += gridDim.x * 256) {
         uint2 r;
-        asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(in + x));
+        asm volatile("ld.global.cs.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(in + x));   // evict-first: the table slice is what L2 is for
         gs_answer(r, b, slice_shift, chunk_bit0, plane_words, count, sat);
     }
 }
@@ -1753,7 +1761,7 @@ int launch_s2_gather_sliced(const uint32_t* image, const Contig* contigs, const 
         case 3: s2_gsemit_kernel<3><<<grid, 256, 0, st>>>(image, contigs, tiles, tile_begin, tile_begin, hp, slice_shift, plane_words, count, sat, sink); break;
         default: s2_gsemit_kernel<4><<<grid, 256, 0, st>>>(image, contigs, tiles, tile_begin, tile_begin, hp, slice_shift, plane_words, count, sat, sink); break;
     }
-    s2_gsapply_kernel<<<dim3(kSMs * 2, kGsBuckets), 256, 0, st>>>(sink, slice_shift, bit0, plane_words, count, sat);
+    s2_gsapply_kernel<<<dim3(kSMs * 4, kGsBuckets), 256, 0, st>>>(sink, slice_shift, bit0, plane_words, count, sat);
     return 2;
 }
 
@@ -1858,25 +1866,28 @@ __global__ void __launch_bounds__(256, 2) s2_regemit_kernel(const uint32_t* __re
         __syncthreads();
         long np = (long)c.len - hp.k + 1;
         uint32_t base = tile_base[tix];
+        uint32_t ids[4], hv[4][E ? E : kMaxE];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            if (!fl[r]) continue;
+        for (int r = 0; r < 4; ++r) {                                          // every hash load of this thread goes out before any is used
             int xl = r * 256 + threadIdx.x;
             long j = (long)t.j0 + xl;
-            uint32_t id = base + (uint32_t)bits_upto(opener, cum, xl) - 1u;
-            if (op[r] && id < loci_cap) { loci[2 * (size_t)id] = (int32_t)t.contig + 1; loci[2 * (size_t)id + 1] = (int32_t)j; }
-            if (j < np && id != 0u) {                                         // j = len-k+1 reads the zero tail (Q6); id 0 never registers (Q10)
-                const uint32_t* hashes = image + c.hash_word + (size_t)j * e;
+            ids[r] = fl[r] ? base + (uint32_t)bits_upto(opener, cum, xl) - 1u : 0u;
+            if (fl[r] && op[r] && ids[r] < loci_cap) { loci[2 * (size_t)ids[r]] = (int32_t)t.contig + 1; loci[2 * (size_t)ids[r] + 1] = (int32_t)j; }
+            bool reg = fl[r] && j < np && ids[r] != 0u;                        // j = len-k+1 reads the zero tail (Q6); id 0 never registers (Q10)
+            const uint32_t* hashes = image + c.hash_word + (size_t)j * e;
 #pragma unroll
-                for (int i = 0; i < (E ? E : kMaxE); ++i) {
-                    if (i >= e) break;
-                    uint32_t h = ld_stream(hashes + i);
-                    if (!h) continue;
-                    uint32_t g = tbl_index(h, hp), b = g >> sink.shift;
-                    uint32_t slot = atomicAdd(&cnt[b], 1u);
-                    if (slot < (uint32_t)kRegStage) stage[b * kRegStage + slot] = make_uint2(g, id);
-                    else direct(b, make_uint2(g, id));
-                }
+            for (int i = 0; i < (E ? E : kMaxE); ++i) hv[r][i] = (reg && i < e) ? ld_stream(hashes + i) : 0u;
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int i = 0; i < (E ? E : kMaxE); ++i) {
+                uint32_t h = hv[r][i];
+                if (!h) continue;
+                uint32_t g = tbl_index(h, hp), b = g >> sink.shift;
+                uint32_t slot = atomicAdd(&cnt[b], 1u);
+                if (slot < (uint32_t)kRegStage) stage[b * kRegStage + slot] = make_uint2(g, ids[r]);
+                else direct(b, make_uint2(g, ids[r]));
             }
         }
     }
@@ -1893,7 +1904,7 @@ __global__ void __launch_bounds__(256, 4) s2_regapply_kernel(RegSink sink, const
     const uint2* __restrict__ in = sink.pool + (size_t)b * sink.cap;
     for (uint32_t x = blockIdx.x * 256 + threadIdx.x; x < n; x += gridDim.x * 256) {
         uint2 r;
-        asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(in + x));
+        asm volatile("ld.global.cs.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(in + x));   // evict-first: the table slices are what L2 is for
         reg_apply_one(r.x, r.y, count, peak_kmer, prefilter);
     }
 }
@@ -1920,7 +1931,7 @@ int launch_s2_register_bucketed(const uint32_t* image, const Contig* contigs, co
     } while (0)
     if (hp.e == 3) LHGT_REGEMIT(3); else LHGT_REGEMIT(0);
 #undef LHGT_REGEMIT
-    s2_regapply_kernel<<<dim3(kSMs * 2, kRegBuckets), 256, 0, st>>>(sink, count, peak_kmer, prefilter);
+    s2_regapply_kernel<<<dim3(kSMs * 4, kRegBuckets), 256, 0, st>>>(sink, count, peak_kmer, prefilter);
     return 2;
 }
 
