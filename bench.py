@@ -64,7 +64,7 @@ WORKLOADS = {
 }
 FILE_WORKLOADS = ("cfg2", "small")
 # sha256 of the interval text the UNMODIFIED reference (oracle/_ref/extract_ref_z, -t 1) wrote for the workload's files
-KNOWN_ANSWERS = {}
+KNOWN_ANSWERS = {"cfg2": "1bd924af26dce59c383adc813ab9d123533b64d487ed010d33e17578d3efa8dd"}   # tests/golden/cfg2_reference.md
 
 
 def _rank_env():

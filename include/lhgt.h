@@ -190,6 +190,20 @@ int      lhgt_s2_mark(lhgt_ctx* c, float match_ratio);
 int      lhgt_s2_complete(lhgt_ctx* c, long tile_begin, long tile_end);
 int      lhgt_s2_finish(lhgt_ctx* c, float hit_ratio, float match_ratio, long max_peak, long* n_peaks);
 long     lhgt_s2_needed_tiles(const lhgt_ctx* c);        /* marked tiles of the last finish */
+/* finish = windows + ids + register, each of which the multi-GPU plan runs by tile block:
+ *   windows  [tile_begin, tile_end): good windows, flagged positions, new peaks per tile (slide_window E:597-712, the opening
+ *            rule of add_peak E:288-301); halos are re-evaluated locally, nothing is needed from the neighbours
+ *   ids      exclusive scan of the per-tile new-peak counts over ALL tiles (all-gather lhgt_dev_tile_new first), buffers;
+ *            flagged_total = flagged positions over all ranks (lhgt_s2_flagged_in_range summed), or < 0 for this context's
+ *   register [tile_begin, tile_end): peak_loci + peak_kmer[hash] = max id (E:246-270) for the flagged positions of the range.
+ *            With lhgt_s2_dense() the ranks then combine their peak tables and loci with an element-wise MAX (ids grow
+ *            with position, so the maximum is the last writer of the sequential loop); otherwise they all-gather the
+ *            flagged bits and every rank registers everything. */
+int      lhgt_s2_windows(lhgt_ctx* c, float hit_ratio, float match_ratio, long tile_begin, long tile_end);
+long     lhgt_s2_flagged_in_range(lhgt_ctx* c);
+int      lhgt_s2_ids(lhgt_ctx* c, long max_peak, long flagged_total, long* n_peaks);
+int      lhgt_s2_register(lhgt_ctx* c, long tile_begin, long tile_end);
+int      lhgt_s2_dense(const lhgt_ctx* c);
 /* Occupancy of the count table (the diagnostic of src/count_diff_kmer.cpp:26-50): out4[v] = number of the
  * 2^k counters holding v.  Its "empty" figure is out4[0] / 2^k, its "weak" figure (out4[0] + out4[1] + out4[2]) / 2^k. */
 int      lhgt_count_table_histogram(lhgt_ctx* c, uint64_t* out4);
@@ -199,6 +213,10 @@ void*    lhgt_dev_count_table(lhgt_ctx* c, uint64_t* bytes);      /* packed 2-bi
  * tiles so that equal per-rank tile blocks can be all-gathered in place. */
 void*    lhgt_dev_hit_bits(lhgt_ctx* c, int which /*0 single, 1 trio*/, uint64_t* bytes);
 void*    lhgt_dev_peak_filter(lhgt_ctx* c, uint64_t* bytes);
+void*    lhgt_dev_tile_new(lhgt_ctx* c, uint64_t* bytes);         /* u32 per tile (+ 8 of padding), new peaks opened in it */
+void*    lhgt_dev_flagged(lhgt_ctx* c, uint64_t* bytes);          /* flagged-position bits, laid out like the hit bits */
+void*    lhgt_dev_peak_table(lhgt_ctx* c, uint64_t* bytes);       /* 2^k u32 peak ids, in the count table's entry order */
+void*    lhgt_dev_loci(lhgt_ctx* c, uint64_t* bytes);             /* 2 x i32 per peak */
 /* count := min(3, count + other) field-wise on packed tables (other: device pointer, same size). */
 int      lhgt_count_merge(lhgt_ctx* c, const void* dev_other, uint64_t bytes, uint64_t word_offset);
 

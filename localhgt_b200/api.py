@@ -91,6 +91,15 @@ SYMBOLS = {
     "lhgt_s2_tiles": (_l, [_vp]),
     "lhgt_s2_gather": (_i, [_vp, _l, _l]),
     "lhgt_s2_finish": (_i, [_vp, _f, _f, _l, C.POINTER(_l)]),
+    "lhgt_s2_windows": (_i, [_vp, _f, _f, _l, _l]),
+    "lhgt_s2_flagged_in_range": (_l, [_vp]),
+    "lhgt_s2_ids": (_i, [_vp, _l, _l, C.POINTER(_l)]),
+    "lhgt_s2_register": (_i, [_vp, _l, _l]),
+    "lhgt_s2_dense": (_i, [_vp]),
+    "lhgt_dev_tile_new": (_vp, [_vp, C.POINTER(_u64)]),
+    "lhgt_dev_flagged": (_vp, [_vp, C.POINTER(_u64)]),
+    "lhgt_dev_peak_table": (_vp, [_vp, C.POINTER(_u64)]),
+    "lhgt_dev_loci": (_vp, [_vp, C.POINTER(_u64)]),
     "lhgt_s2_mark": (_i, [_vp, _f]),
     "lhgt_s2_complete": (_i, [_vp, _l, _l]),
     "lhgt_s2_needed_tiles": (_l, [_vp]),
@@ -342,6 +351,32 @@ class Screen:
         _check(self._L.lhgt_s2_complete(self._h, tile_begin, tile_end))
 
     def s2_needed_tiles(self) -> int: return int(self._L.lhgt_s2_needed_tiles(self._h))
+
+    def s2_windows(self, hit_ratio: float, match_ratio: float, tile_begin: int = 0, tile_end: int = -1) -> None:
+        _check(self._L.lhgt_s2_windows(self._h, hit_ratio, match_ratio, tile_begin, tile_end))
+
+    def s2_flagged_in_range(self) -> int:
+        return _check(self._L.lhgt_s2_flagged_in_range(self._h))
+
+    def s2_ids(self, max_peak: int = 300000000, flagged_total: int = -1) -> int:
+        n = _l(0)
+        _check(self._L.lhgt_s2_ids(self._h, max_peak, flagged_total, C.byref(n)))
+        return n.value
+
+    def s2_register(self, tile_begin: int = 0, tile_end: int = -1) -> None:
+        _check(self._L.lhgt_s2_register(self._h, tile_begin, tile_end))
+
+    def s2_dense(self) -> bool: return bool(self._L.lhgt_s2_dense(self._h))
+
+    def _dev(self, fn):
+        n = _u64(0)
+        p = fn(self._h, C.byref(n))
+        return int(p or 0), int(n.value)
+
+    def dev_tile_new(self): return self._dev(self._L.lhgt_dev_tile_new)
+    def dev_flagged(self): return self._dev(self._L.lhgt_dev_flagged)
+    def dev_peak_table(self): return self._dev(self._L.lhgt_dev_peak_table)
+    def dev_loci(self): return self._dev(self._L.lhgt_dev_loci)
 
     def s2_finish(self, hit_ratio: float = 0.1, match_ratio: float = 0.08, max_peak: int = 300000000) -> int:
         n = _l(0)

@@ -145,7 +145,7 @@ struct lhgt_ctx {
 
     uint32_t *d_single = nullptr, *d_trio = nullptr, *d_good = nullptr, *d_flagged = nullptr;
     uint32_t *d_tile_new = nullptr, *d_tile_base = nullptr, *d_scan_tmp = nullptr;
-    bool gathered = false, marked = false; float mark_match = 0.f; uint32_t n_needed_tiles = 0;
+    bool gathered = false, marked = false, windows_done = false; float mark_match = 0.f; uint32_t n_needed_tiles = 0;
     DevBuf<uint8_t> hot_buf; DevBuf<uint32_t> need_buf; uint32_t* d_misc = nullptr;
     DevBuf<uint2> gs_pool_buf; DevBuf<uint32_t> gs_cursor_buf, sat_buf; bool single_exact = false;   // S2 gather through table slices
     DevBuf<uint2> reg_pool_buf; DevBuf<uint32_t> reg_cursor_buf; bool filter_on = true;   // S2 registration through buckets
@@ -437,7 +437,7 @@ static int finish_index_tables(lhgt_ctx* c) {
     size_t bw = (nt + kMaxPeers) * kTileWords;                 // padding: per-rank tile blocks of equal size cover the arrays (multi-GPU all-gather)
     if ((rc = c->contigs_buf.reserve(c->contigs.size())) || (rc = c->tiles_buf.reserve(nt)) || (rc = c->single_buf.reserve(bw)) ||
         (rc = c->trio_buf.reserve(bw)) || (rc = c->good_buf.reserve(bw)) || (rc = c->flagged_buf.reserve(bw)) ||
-        (rc = c->tile_new_buf.reserve(nt)) || (rc = c->tile_base_buf.reserve(nt)) || (rc = c->scan_tmp_buf.reserve(scan_tmp_words(nt))) ||
+        (rc = c->tile_new_buf.reserve(nt + kMaxPeers)) || (rc = c->tile_base_buf.reserve(nt + kMaxPeers)) || (rc = c->scan_tmp_buf.reserve(scan_tmp_words(nt))) ||
         (rc = c->hot_buf.reserve(nt)) || (rc = c->need_buf.reserve(nt)))
         return rc;
     c->d_contigs = c->contigs_buf.p; c->d_tiles = c->tiles_buf.p;
@@ -1309,7 +1309,7 @@ extern "C" int lhgt_s2_gather(lhgt_ctx* c, long tile_begin, long tile_end) {
         c->single_exact = false;
     }
     c->gathered = true;
-    c->marked = false;
+    c->marked = false; c->windows_done = false;
     return 0;
 }
 
@@ -1352,7 +1352,7 @@ static int clear_peak_tables(lhgt_ctx* c) {
         double unwrite_s = (double)c->n_flagged * c->e * 50e-12;
         double clear_s = ((double)(1ull << c->k) * 4 + (double)kFilterWords * 4) / 5e12;
         if (unwrite_s <= clear_s) {
-            c->launches += launch_s2_register(c->d_image, c->d_contigs, c->d_tiles, c->need_buf.p, c->d_misc + MISC_NEED, c->hp, c->d_count,
+            c->launches += launch_s2_register(c->d_image, c->d_contigs, c->d_tiles, c->need_buf.p, c->d_misc + MISC_NEED, 0, c->tiles.size(), c->hp, c->d_count,
                                               c->d_flagged, c->d_tile_base, c->d_loci, 0u, c->d_peak_kmer, c->d_prefilter, 1, c->st);
         } else {
             CU(cudaMemsetAsync(c->d_peak_kmer, 0, (size_t)(1ull << c->k) * 4, c->st));
@@ -1363,7 +1363,13 @@ static int clear_peak_tables(lhgt_ctx* c) {
     return 0;
 }
 
-extern "C" int lhgt_s2_finish(lhgt_ctx* c, float hit_ratio, float match_ratio, long max_peak, long* n_peaks) {
+// ---- S2 finish in its steps (multi-GPU: windows and register run on each rank's block of tiles, ids replicated)
+
+// good windows, flagged positions and new-peak counts of the needed tiles in [tile_begin, tile_end).  The passes reach into
+// their neighbours (a window 499 positions back, an interval 1000 positions either side, a peak bucket 49 positions back):
+// good is evaluated on two tiles before and one after the range and flagged on one tile before it, so a rank needs nothing
+// from its neighbours but the (already exchanged) hit bits.
+extern "C" int lhgt_s2_windows(lhgt_ctx* c, float hit_ratio, float match_ratio, long tile_begin, long tile_end) {
     if (!c) return fail(LHGT_E_ARG, "null ctx");
     if (!c->index_ready || !c->gathered) return fail(LHGT_E_STATE, "gather the table first");
     CU(cudaSetDevice(c->device));
@@ -1373,31 +1379,59 @@ extern "C" int lhgt_s2_finish(lhgt_ctx* c, float hit_ratio, float match_ratio, l
         if (!rc) rc = lhgt_s2_complete(c, 0, -1);
         if (rc) return rc;
     }
+    long nt = (long)c->tiles.size();
+    if (tile_end < 0 || tile_end > nt) tile_end = nt;
+    if (tile_begin < 0 || tile_begin > tile_end) return fail(LHGT_E_ARG, "bad tile range");
     int one_min = (int)(500 * hit_ratio), three_min = (int)(500 * match_ratio);    // E:559-560 (int * float, fp32)
-    uint64_t nt = c->tiles.size();
-    c->n_peaks = 0; c->n_flagged = 0; c->intervals_valid = false;
-    if (nt == 0) { if (n_peaks) *n_peaks = 0; return 0; }
-    unsigned long long flagged_total = 0; uint32_t last_new = 0, last_base = 0;
+    c->n_peaks = -1; c->n_flagged = 0; c->intervals_valid = false;
+    c->windows_done = true;
+    if (nt == 0) return 0;
     const uint32_t* need = c->need_buf.p; const uint32_t* n_need = c->d_misc + MISC_NEED;
+    uint64_t lo = (uint64_t)tile_begin, hi = (uint64_t)tile_end;
+    Span sp(c, 3);
+    // good / flagged / tile_new are only written on the needed tiles: everything else must read as zero
+    CU(cudaMemsetAsync(c->d_good, 0, (size_t)nt * kTileWords * 4, c->st));
+    CU(cudaMemsetAsync(c->d_flagged, 0, (size_t)nt * kTileWords * 4, c->st));
+    CU(cudaMemsetAsync(c->d_tile_new, 0, ((size_t)nt + kMaxPeers) * 4, c->st));
+    CU(cudaMemsetAsync(c->d_counter + CNT_FLAGGED, 0, sizeof(unsigned long long), c->st));
+    c->launches += launch_s2_good(c->d_contigs, c->d_tiles, need, n_need, lo >= 2 ? lo - 2 : 0, std::min<uint64_t>((uint64_t)nt, hi + 1), c->d_single, c->d_trio,
+                                  one_min, three_min, c->d_good, c->st);
+    c->launches += launch_s2_flag(c->d_contigs, c->d_tiles, (uint64_t)nt, need, n_need, lo >= 1 ? lo - 1 : 0, hi, c->k, c->d_single, c->d_good, c->d_flagged, c->st);
+    c->launches += launch_s2_count_new(c->d_tiles, need, n_need, lo, hi, c->d_flagged, c->d_tile_new, c->d_counter + CNT_FLAGGED, c->st);
+    return 0;
+}
+
+// flagged positions counted by the last lhgt_s2_windows call (its tile range); synchronises
+extern "C" long lhgt_s2_flagged_in_range(lhgt_ctx* c) {
+    if (!c) return fail(LHGT_E_ARG, "null ctx");
+    CU(cudaSetDevice(c->device));
+    unsigned long long v = 0;
+    CU(cudaMemcpyAsync(&v, c->d_counter + CNT_FLAGGED, sizeof v, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    return (long)v;
+}
+
+// peak ids: exclusive scan of the per-tile new-peak counts (all tiles: multi-GPU callers all-gather lhgt_dev_tile_new first),
+// loci / verdict buffers, first id per contig.  flagged_total < 0: use this context's own count.
+extern "C" int lhgt_s2_ids(lhgt_ctx* c, long max_peak, long flagged_total, long* n_peaks) {
+    if (!c) return fail(LHGT_E_ARG, "null ctx");
+    if (!c->index_ready || !c->windows_done) return fail(LHGT_E_STATE, "run lhgt_s2_windows first");
+    CU(cudaSetDevice(c->device));
+    uint64_t nt = c->tiles.size();
+    c->n_peaks = 0; c->n_flagged = 0;
+    if (nt == 0) { if (n_peaks) *n_peaks = 0; return 0; }
+    unsigned long long flagged_local = 0; uint32_t last_new = 0, last_base = 0;
     {
         Span sp(c, 3);
-        // good / flagged / tile_new are only written on the needed tiles: everything else must read as zero
-        CU(cudaMemsetAsync(c->d_good, 0, nt * kTileWords * 4, c->st));
-        CU(cudaMemsetAsync(c->d_flagged, 0, nt * kTileWords * 4, c->st));
-        CU(cudaMemsetAsync(c->d_tile_new, 0, nt * 4, c->st));
-        CU(cudaMemsetAsync(c->d_counter + CNT_FLAGGED, 0, sizeof(unsigned long long), c->st));
-        c->launches += launch_s2_good(c->d_contigs, c->d_tiles, need, n_need, c->d_single, c->d_trio, one_min, three_min, c->d_good, c->st);
-        c->launches += launch_s2_flag(c->d_contigs, c->d_tiles, nt, need, n_need, c->k, c->d_single, c->d_good, c->d_flagged, c->st);
-        c->launches += launch_s2_count_new(c->d_tiles, need, n_need, c->d_flagged, c->d_tile_new, c->d_counter + CNT_FLAGGED, c->st);
         c->launches += launch_scan_exclusive(c->d_tile_new, c->d_tile_base, nt, c->d_scan_tmp, c->st);
     }
-    CU(cudaMemcpyAsync(&flagged_total, c->d_counter + CNT_FLAGGED, sizeof flagged_total, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(&flagged_local, c->d_counter + CNT_FLAGGED, sizeof flagged_local, cudaMemcpyDeviceToHost, c->st));
     CU(cudaMemcpyAsync(&last_new, c->d_tile_new + nt - 1, 4, cudaMemcpyDeviceToHost, c->st));
     CU(cudaMemcpyAsync(&last_base, c->d_tile_base + nt - 1, 4, cudaMemcpyDeviceToHost, c->st));
     CU(cudaMemcpyAsync(&c->n_needed_tiles, c->d_misc + MISC_NEED, 4, cudaMemcpyDeviceToHost, c->st));
     CU(cudaStreamSynchronize(c->st));
     long total = (long)last_new + (long)last_base;
-    c->n_flagged = (long)flagged_total;
+    c->n_flagged = flagged_total >= 0 ? flagged_total : (long)flagged_local;
     if (total > max_peak) return fail(LHGT_E_TOO_MANY_PEAKS, "%ld peaks exceed max_peak=%ld (E:272-274)", total, max_peak);
     if (total > c->peaks_cap) {
         dev_free(c->d_loci); dev_free(c->d_filter);
@@ -1412,51 +1446,83 @@ extern "C" int lhgt_s2_finish(lhgt_ctx* c, float hit_ratio, float match_ratio, l
         if (rc) return rc;
         c->launches += launch_contig_first(c->d_contigs, (uint32_t)c->contigs.size(), c->d_tile_base, (uint32_t)total, c->contig_first_buf.p, c->st);
     }
-    // the S3 pre-filter only pays while it is sparse (2^28 bits against the registered k-mers): a dense result skips it
-    c->filter_on = (double)c->n_flagged * c->e < 0.7 * (double)(1u << kFilterLog2);
     if (total > 0) {
         CU(cudaMemsetAsync(c->d_filter, 0, (size_t)total, c->st));
-        Span sp(c, 10);
-        uint32_t loci_cap = (uint32_t)std::min<long>(c->peaks_cap, 0xffffffffL);
-        uint32_t* prefilter = c->filter_on ? c->d_prefilter : nullptr;
-        const char* force = getenv("LHGT_REG_BUCKETED");               // test knob: 1 forces the bucketed form, 0 the direct one
-        double records = (double)c->n_flagged * c->e;
-        bool bucketed = force ? atoi(force) != 0 : records >= 8e6;      // below that the direct atomics finish in well under a millisecond
-        if (bucketed && c->n_needed_tiles > 0) {
-            // record regions: the S1 leaf-stream pool when there is one (idle now), else a buffer of our own
-            const char* kb = getenv("LHGT_REG_POOL_KB");                 // test knob: small regions force chunks and overflow
-            uint2* pool = nullptr; uint64_t pool_records = 0;
-            if (!kb && c->d_bin_pool_b && c->bin_pool_b_entries / 2 >= ((uint64_t)32 << 20)) { pool = (uint2*)c->d_bin_pool_b; pool_records = c->bin_pool_b_entries / 2; }
-            else {
-                uint64_t want = kb ? std::max<uint64_t>(((uint64_t)atol(kb) << 10) / 8, (uint64_t)s2_reg_buckets() * 4)
-                                   : std::min<uint64_t>((uint64_t)(records * 1.25) + (uint64_t)s2_reg_buckets() * 1024, (uint64_t)64 << 20);
-                int rc = c->reg_pool_buf.reserve(want);
-                if (rc) return rc;
-                pool = c->reg_pool_buf.p; pool_records = want;
-            }
-            int rc = c->reg_cursor_buf.reserve((size_t)s2_reg_cursor_words());
-            if (rc) return rc;
-            uint32_t cap = (uint32_t)std::min<uint64_t>(pool_records / (uint64_t)s2_reg_buckets(), 0xfffffff0u);
-            double per_tile = std::max(1.0, records / (double)c->n_needed_tiles);
-            uint32_t chunk = (uint32_t)std::max(1.0, std::min((double)c->n_needed_tiles, 0.85 * (double)cap * s2_reg_buckets() / per_tile));
-            for (uint32_t lo = 0; lo < c->n_needed_tiles; lo += chunk) {
-                CU(cudaMemsetAsync(c->reg_cursor_buf.p, 0, (size_t)s2_reg_cursor_words() * 4, c->st));
-                int nl = launch_s2_register_bucketed(c->d_image, c->d_contigs, c->d_tiles, need, n_need, lo, std::min(c->n_needed_tiles, lo + chunk), c->hp,
-                                                     c->d_count, c->d_flagged, c->d_tile_base, c->d_loci, loci_cap, c->d_peak_kmer, prefilter,
-                                                     pool, c->reg_cursor_buf.p, cap, c->st);
-                if (nl < 0) return fail(LHGT_E_CUDA, "registration kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-                c->launches += nl;
-            }
-        } else {
-            c->launches += launch_s2_register(c->d_image, c->d_contigs, c->d_tiles, need, n_need, c->hp, c->d_count, c->d_flagged, c->d_tile_base,
-                                              c->d_loci, loci_cap, c->d_peak_kmer, prefilter, 0, c->st);
-        }
-        c->peak_tables_dirty = true;
+        CU(cudaMemsetAsync(c->d_loci, 0, (size_t)total * 8, c->st));                 // multi-GPU: every rank writes its own openers, MAX combines
     }
+    // the S3 pre-filter only pays while it is sparse (2^28 bits against the registered k-mers): a dense result skips it
+    const char* dr = getenv("LHGT_DENSE_RECORDS");                    // test knob: the registered-k-mer count from which a result is "dense"
+    c->filter_on = (double)c->n_flagged * c->e < (dr ? atof(dr) : 0.7 * (double)(1u << kFilterLog2));
     c->n_peaks = total;
     if (n_peaks) *n_peaks = total;
     return 0;
 }
+
+// registration of the flagged positions of the needed tiles in [tile_begin, tile_end): loci + scatter-max into the peak table
+extern "C" int lhgt_s2_register(lhgt_ctx* c, long tile_begin, long tile_end) {
+    if (!c) return fail(LHGT_E_ARG, "null ctx");
+    if (c->n_peaks < 0) return fail(LHGT_E_STATE, "run lhgt_s2_ids first");
+    CU(cudaSetDevice(c->device));
+    long nt = (long)c->tiles.size();
+    if (tile_end < 0 || tile_end > nt) tile_end = nt;
+    if (tile_begin < 0 || tile_begin > tile_end) return fail(LHGT_E_ARG, "bad tile range");
+    long total = c->n_peaks;
+    if (total <= 0 || tile_end == tile_begin) return 0;
+    const uint32_t* need = c->need_buf.p; const uint32_t* n_need = c->d_misc + MISC_NEED;
+    uint64_t t_lo = (uint64_t)tile_begin, t_hi = (uint64_t)tile_end;
+    Span sp(c, 10);
+    uint32_t loci_cap = (uint32_t)std::min<long>(c->peaks_cap, 0xffffffffL);
+    uint32_t* prefilter = c->filter_on ? c->d_prefilter : nullptr;
+    const char* force = getenv("LHGT_REG_BUCKETED");               // test knob: 1 forces the bucketed form, 0 the direct one
+    double share = (double)(tile_end - tile_begin) / (double)nt;
+    double records = (double)c->n_flagged * c->e * share;          // expected in this range
+    bool bucketed = force ? atoi(force) != 0 : records >= 8e6;      // below that the direct atomics finish in well under a millisecond
+    if (bucketed && c->n_needed_tiles > 0) {
+        // record regions: the S1 leaf-stream pool when there is one (idle now), else a buffer of our own
+        const char* kb = getenv("LHGT_REG_POOL_KB");                 // test knob: small regions force chunks and overflow
+        uint2* pool = nullptr; uint64_t pool_records = 0;
+        if (!kb && c->d_bin_pool_b && c->bin_pool_b_entries / 2 >= ((uint64_t)32 << 20)) { pool = (uint2*)c->d_bin_pool_b; pool_records = c->bin_pool_b_entries / 2; }
+        else {
+            uint64_t want = kb ? std::max<uint64_t>(((uint64_t)atol(kb) << 10) / 8, (uint64_t)s2_reg_buckets() * 4)
+                               : std::min<uint64_t>((uint64_t)(records * 1.25) + (uint64_t)s2_reg_buckets() * 1024, (uint64_t)64 << 20);
+            int rc = c->reg_pool_buf.reserve(want);
+            if (rc) return rc;
+            pool = c->reg_pool_buf.p; pool_records = want;
+        }
+        int rc = c->reg_cursor_buf.reserve((size_t)s2_reg_cursor_words());
+        if (rc) return rc;
+        uint32_t cap = (uint32_t)std::min<uint64_t>(pool_records / (uint64_t)s2_reg_buckets(), 0xfffffff0u);
+        // the needed-tile list is walked in chunks whose records fit the regions (records per needed tile of the range, on average)
+        double per_tile = std::max(1.0, (double)c->n_flagged * c->e / (double)c->n_needed_tiles);
+        uint32_t chunk = (uint32_t)std::max(1.0, std::min((double)c->n_needed_tiles, 0.85 * (double)cap * s2_reg_buckets() / per_tile));   // fits even if every tile of the chunk lies in the range
+        for (uint32_t lo = 0; lo < c->n_needed_tiles; lo += chunk) {
+            CU(cudaMemsetAsync(c->reg_cursor_buf.p, 0, (size_t)s2_reg_cursor_words() * 4, c->st));
+            int nl = launch_s2_register_bucketed(c->d_image, c->d_contigs, c->d_tiles, need, n_need, lo, std::min(c->n_needed_tiles, lo + chunk), t_lo, t_hi, c->hp,
+                                                 c->d_count, c->d_flagged, c->d_tile_base, c->d_loci, loci_cap, c->d_peak_kmer, prefilter,
+                                                 pool, c->reg_cursor_buf.p, cap, c->st);
+            if (nl < 0) return fail(LHGT_E_CUDA, "registration kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            c->launches += nl;
+        }
+    } else {
+        c->launches += launch_s2_register(c->d_image, c->d_contigs, c->d_tiles, need, n_need, t_lo, t_hi, c->hp, c->d_count, c->d_flagged, c->d_tile_base,
+                                          c->d_loci, loci_cap, c->d_peak_kmer, prefilter, 0, c->st);
+    }
+    c->peak_tables_dirty = true;
+    return 0;
+}
+
+extern "C" int lhgt_s2_finish(lhgt_ctx* c, float hit_ratio, float match_ratio, long max_peak, long* n_peaks) {
+    int rc = lhgt_s2_windows(c, hit_ratio, match_ratio, 0, -1);
+    long n = 0;
+    if (!rc) rc = lhgt_s2_ids(c, max_peak, -1, &n);
+    if (!rc) rc = lhgt_s2_register(c, 0, -1);
+    if (!rc && n_peaks) *n_peaks = n;
+    return rc;
+}
+
+// whether the registered k-mers are many enough that the S3 pre-filter is skipped (the multi-GPU plan then registers by tile
+// block and combines the peak tables, instead of registering everything everywhere)
+extern "C" int lhgt_s2_dense(const lhgt_ctx* c) { return c && !c->filter_on; }
 
 extern "C" long lhgt_s2_peaks(lhgt_ctx* c, float hit_ratio, float match_ratio, long max_peak) {
     int rc = lhgt_s2_gather(c, 0, -1);
@@ -1737,6 +1803,30 @@ extern "C" void* lhgt_dev_hit_bits(lhgt_ctx* c, int which, uint64_t* bytes) {
     if (!c || !c->index_ready) return nullptr;
     if (bytes) *bytes = ((uint64_t)c->tiles.size() + kMaxPeers) * kTileWords * 4;   // the allocation: tiles + kMaxPeers of padding
     return which == 0 ? c->d_single : c->d_trio;
+}
+
+extern "C" void* lhgt_dev_tile_new(lhgt_ctx* c, uint64_t* bytes) {
+    if (!c || !c->index_ready) return nullptr;
+    if (bytes) *bytes = ((uint64_t)c->tiles.size() + kMaxPeers) * 4;
+    return c->d_tile_new;
+}
+
+extern "C" void* lhgt_dev_flagged(lhgt_ctx* c, uint64_t* bytes) {
+    if (!c || !c->index_ready) return nullptr;
+    if (bytes) *bytes = ((uint64_t)c->tiles.size() + kMaxPeers) * kTileWords * 4;
+    return c->d_flagged;
+}
+
+extern "C" void* lhgt_dev_peak_table(lhgt_ctx* c, uint64_t* bytes) {
+    if (!c) return nullptr;
+    if (bytes) *bytes = (1ull << c->k) * 4;
+    return c->d_peak_kmer;
+}
+
+extern "C" void* lhgt_dev_loci(lhgt_ctx* c, uint64_t* bytes) {
+    if (!c || c->n_peaks < 0) return nullptr;
+    if (bytes) *bytes = (uint64_t)c->n_peaks * 8;
+    return c->d_loci;
 }
 
 extern "C" void* lhgt_dev_peak_filter(lhgt_ctx* c, uint64_t* bytes) {

@@ -1414,6 +1414,7 @@ __device__ __forceinline__ void prefix_words(const uint32_t* words, int* cum, in
 // pass e: 500-wide window sums and the good-window flag (E:597-615), on the needed tiles
 __global__ void __launch_bounds__(256) s2_good_kernel(const Contig* __restrict__ contigs, const Tile* __restrict__ tiles,
                                                       const uint32_t* __restrict__ need_list, const uint32_t* __restrict__ n_need,
+                                                      uint64_t t_lo, uint64_t t_hi,
                                                       const uint32_t* __restrict__ single, const uint32_t* __restrict__ trio,
                                                       int one_min, int three_min, uint32_t* __restrict__ good) {
     __shared__ uint32_t ws[2 * kTileWords], wt[2 * kTileWords];
@@ -1421,6 +1422,7 @@ __global__ void __launch_bounds__(256) s2_good_kernel(const Contig* __restrict__
     const uint32_t n = *n_need;
     for (uint32_t it = blockIdx.x; it < n; it += gridDim.x) {
         const uint64_t tix = need_list[it];
+        if (tix < t_lo || tix >= t_hi) continue;
         Tile t = tiles[tix];
         Contig c = contigs[t.contig];
         bool has_prev = t.j0 > 0;
@@ -1457,7 +1459,8 @@ __global__ void __launch_bounds__(256) s2_good_kernel(const Contig* __restrict__
 //   peak[j] if some diff_t(j) <= -2;  peak[j-k-5-t] if diff_t(j) >= 2;  only for 2k+10 < j < len.
 __global__ void __launch_bounds__(256) s2_flag_kernel(const Contig* __restrict__ contigs, const Tile* __restrict__ tiles,
                                                       uint64_t ntiles, const uint32_t* __restrict__ need_list,
-                                                      const uint32_t* __restrict__ n_need, int k, const uint32_t* __restrict__ single,
+                                                      const uint32_t* __restrict__ n_need, uint64_t t_lo, uint64_t t_hi, int k,
+                                                      const uint32_t* __restrict__ single,
                                                       const uint32_t* __restrict__ good, uint32_t* __restrict__ flagged) {
     __shared__ uint32_t ws[3 * kTileWords + 1], wg[3 * kTileWords];
     __shared__ int cg[3 * kTileWords + 1];
@@ -1465,6 +1468,7 @@ __global__ void __launch_bounds__(256) s2_flag_kernel(const Contig* __restrict__
     const uint32_t n = *n_need;
     for (uint32_t it = blockIdx.x; it < n; it += gridDim.x) {
         const uint64_t tix = need_list[it];
+        if (tix < t_lo || tix >= t_hi) continue;
         Tile t = tiles[tix];
         Contig c = contigs[t.contig];
         bool has_prev = t.j0 > 0;
@@ -1545,12 +1549,14 @@ __device__ __forceinline__ bool opens_peak(const uint32_t* __restrict__ flagged,
 }
 
 __global__ void __launch_bounds__(256) s2_count_new_kernel(const Tile* __restrict__ tiles, const uint32_t* __restrict__ need_list,
-                                                           const uint32_t* __restrict__ n_need, const uint32_t* __restrict__ flagged,
+                                                           const uint32_t* __restrict__ n_need, uint64_t t_lo, uint64_t t_hi,
+                                                           const uint32_t* __restrict__ flagged,
                                                            uint32_t* __restrict__ tile_new, unsigned long long* __restrict__ flagged_total) {
     __shared__ uint32_t n_new, n_flag;
     const uint32_t n = *n_need;
     for (uint32_t it = blockIdx.x; it < n; it += gridDim.x) {
         const uint64_t tix = need_list[it];
+        if (tix < t_lo || tix >= t_hi) continue;
         if (threadIdx.x == 0) { n_new = 0; n_flag = 0; }
         __syncthreads();
         Tile t = tiles[tix];
@@ -1580,7 +1586,7 @@ __global__ void __launch_bounds__(256) s2_count_new_kernel(const Tile* __restric
 template <int E>
 __global__ void __launch_bounds__(256) s2_register_kernel(const uint32_t* __restrict__ image, const Contig* __restrict__ contigs,
                                                           const Tile* __restrict__ tiles, const uint32_t* __restrict__ need_list,
-                                                          const uint32_t* __restrict__ n_need, HashP hp,
+                                                          const uint32_t* __restrict__ n_need, uint64_t t_lo, uint64_t t_hi, HashP hp,
                                                           const uint32_t* __restrict__ count, const uint32_t* __restrict__ flagged,
                                                           const uint32_t* __restrict__ tile_base, int32_t* __restrict__ loci, uint32_t loci_cap,
                                                           uint32_t* __restrict__ peak_kmer, uint32_t* __restrict__ prefilter,
@@ -1592,6 +1598,7 @@ __global__ void __launch_bounds__(256) s2_register_kernel(const uint32_t* __rest
     const uint32_t n = *n_need;
     for (uint32_t it = blockIdx.x; it < n; it += gridDim.x) {
         const uint64_t tix = need_list[it];
+        if (tix < t_lo || tix >= t_hi) continue;
         Tile t = tiles[tix];
         Contig c = contigs[t.contig];
         bool fl[4], op[4];
@@ -1800,7 +1807,8 @@ __device__ __forceinline__ void reg_apply_one(uint32_t g, uint32_t id, const uin
 template <int E>
 __global__ void __launch_bounds__(256, 2) s2_regemit_kernel(const uint32_t* __restrict__ image, const Contig* __restrict__ contigs,
                                                             const Tile* __restrict__ tiles, const uint32_t* __restrict__ need_list,
-                                                            const uint32_t* __restrict__ n_need, uint32_t it_lo, uint32_t it_hi, HashP hp,
+                                                            const uint32_t* __restrict__ n_need, uint32_t it_lo, uint32_t it_hi,
+                                                            uint64_t t_lo, uint64_t t_hi, HashP hp,
                                                             const uint32_t* __restrict__ count, const uint32_t* __restrict__ flagged,
                                                             const uint32_t* __restrict__ tile_base, int32_t* __restrict__ loci, uint32_t loci_cap,
                                                             uint32_t* __restrict__ peak_kmer, uint32_t* __restrict__ prefilter, RegSink sink) {
@@ -1845,6 +1853,7 @@ __global__ void __launch_bounds__(256, 2) s2_regemit_kernel(const uint32_t* __re
     static_assert(kRegStage <= 32, "a run is written by one warp instruction");
     for (uint32_t it = it_lo + blockIdx.x; it < hi; it += gridDim.x) {
         const uint64_t tix = need_list[it];
+        if (tix < t_lo || tix >= t_hi) continue;
         Tile t = tiles[tix];
         Contig c = contigs[t.contig];
         bool fl[4], op[4];
@@ -1915,7 +1924,7 @@ int s2_reg_cursor_words() { return kRegBuckets * kRegCursorStride; }
 
 // one chunk of the needed-tile list [it_lo, it_hi): emit, then apply (cursor zeroed by the caller)
 int launch_s2_register_bucketed(const uint32_t* image, const Contig* contigs, const Tile* tiles, const uint32_t* need_list,
-                                const uint32_t* n_need, uint32_t it_lo, uint32_t it_hi, const HashP& hp, const uint32_t* count,
+                                const uint32_t* n_need, uint32_t it_lo, uint32_t it_hi, uint64_t t_lo, uint64_t t_hi, const HashP& hp, const uint32_t* count,
                                 const uint32_t* flagged, const uint32_t* tile_base, int32_t* loci, uint32_t loci_cap, uint32_t* peak_kmer,
                                 uint32_t* prefilter, uint2* pool, uint32_t* cursor, uint32_t cap, cudaStream_t st) {
     if (it_hi <= it_lo) return 0;
@@ -1926,7 +1935,7 @@ int launch_s2_register_bucketed(const uint32_t* image, const Contig* contigs, co
     do {                                                                                                                        \
         if (cudaFuncSetAttribute(s2_regemit_kernel<EE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) \
             return -1;                                                                                                          \
-        s2_regemit_kernel<EE><<<grid, 256, smem, st>>>(image, contigs, tiles, need_list, n_need, it_lo, it_hi, hp, count, flagged, \
+        s2_regemit_kernel<EE><<<grid, 256, smem, st>>>(image, contigs, tiles, need_list, n_need, it_lo, it_hi, t_lo, t_hi, hp, count, flagged, \
                                                       tile_base, loci, loci_cap, peak_kmer, prefilter, sink);                  \
     } while (0)
     if (hp.e == 3) LHGT_REGEMIT(3); else LHGT_REGEMIT(0);
@@ -1971,28 +1980,28 @@ int launch_s2_single(const uint32_t* image, const Contig* contigs, const Tile* t
     return 1;
 }
 
-int launch_s2_good(const Contig* contigs, const Tile* tiles, const uint32_t* need_list, const uint32_t* n_need, const uint32_t* single,
-                   const uint32_t* trio, int one_min, int three_min, uint32_t* good, cudaStream_t st) {
-    s2_good_kernel<<<kS2Grid, 256, 0, st>>>(contigs, tiles, need_list, n_need, single, trio, one_min, three_min, good);
+int launch_s2_good(const Contig* contigs, const Tile* tiles, const uint32_t* need_list, const uint32_t* n_need, uint64_t t_lo, uint64_t t_hi,
+                   const uint32_t* single, const uint32_t* trio, int one_min, int three_min, uint32_t* good, cudaStream_t st) {
+    s2_good_kernel<<<kS2Grid, 256, 0, st>>>(contigs, tiles, need_list, n_need, t_lo, t_hi, single, trio, one_min, three_min, good);
     return 1;
 }
 
-int launch_s2_flag(const Contig* contigs, const Tile* tiles, uint64_t ntiles, const uint32_t* need_list, const uint32_t* n_need, int k,
-                   const uint32_t* single, const uint32_t* good, uint32_t* flagged, cudaStream_t st) {
-    s2_flag_kernel<<<kS2Grid / 2, 256, 0, st>>>(contigs, tiles, ntiles, need_list, n_need, k, single, good, flagged);
+int launch_s2_flag(const Contig* contigs, const Tile* tiles, uint64_t ntiles, const uint32_t* need_list, const uint32_t* n_need,
+                   uint64_t t_lo, uint64_t t_hi, int k, const uint32_t* single, const uint32_t* good, uint32_t* flagged, cudaStream_t st) {
+    s2_flag_kernel<<<kS2Grid / 2, 256, 0, st>>>(contigs, tiles, ntiles, need_list, n_need, t_lo, t_hi, k, single, good, flagged);
     return 1;
 }
 
-int launch_s2_count_new(const Tile* tiles, const uint32_t* need_list, const uint32_t* n_need, const uint32_t* flagged,
-                        uint32_t* tile_new, unsigned long long* flagged_total, cudaStream_t st) {
-    s2_count_new_kernel<<<kS2Grid, 256, 0, st>>>(tiles, need_list, n_need, flagged, tile_new, flagged_total);
+int launch_s2_count_new(const Tile* tiles, const uint32_t* need_list, const uint32_t* n_need, uint64_t t_lo, uint64_t t_hi,
+                        const uint32_t* flagged, uint32_t* tile_new, unsigned long long* flagged_total, cudaStream_t st) {
+    s2_count_new_kernel<<<kS2Grid, 256, 0, st>>>(tiles, need_list, n_need, t_lo, t_hi, flagged, tile_new, flagged_total);
     return 1;
 }
 
 int launch_s2_register(const uint32_t* image, const Contig* contigs, const Tile* tiles, const uint32_t* need_list, const uint32_t* n_need,
-                       const HashP& hp, const uint32_t* count, const uint32_t* flagged, const uint32_t* tile_base, int32_t* loci,
-                       uint32_t loci_cap, uint32_t* peak_kmer, uint32_t* prefilter, int mode, cudaStream_t st) {
-    s2_register_kernel<0><<<kS2Grid, 256, 0, st>>>(image, contigs, tiles, need_list, n_need, hp, count, flagged, tile_base, loci, loci_cap,
+                       uint64_t t_lo, uint64_t t_hi, const HashP& hp, const uint32_t* count, const uint32_t* flagged, const uint32_t* tile_base,
+                       int32_t* loci, uint32_t loci_cap, uint32_t* peak_kmer, uint32_t* prefilter, int mode, cudaStream_t st) {
+    s2_register_kernel<0><<<kS2Grid, 256, 0, st>>>(image, contigs, tiles, need_list, n_need, t_lo, t_hi, hp, count, flagged, tile_base, loci, loci_cap,
                                                   peak_kmer, prefilter, mode);
     return 1;
 }

@@ -146,16 +146,17 @@ int launch_s2_mark(const Contig* contigs, const Tile* tiles, uint64_t ntiles, co
                    uint32_t* need_list, uint32_t* n_need, cudaStream_t st);
 int launch_s2_single(const uint32_t* image, const Contig* contigs, const Tile* tiles, const uint32_t* need_list, const uint32_t* n_need,
                      uint64_t tile_begin, uint64_t tile_end, const HashP& hp, const uint32_t* count, uint32_t* single, cudaStream_t st);
-int launch_s2_good(const Contig* contigs, const Tile* tiles, const uint32_t* need_list, const uint32_t* n_need, const uint32_t* single,
-                   const uint32_t* trio, int one_min, int three_min, uint32_t* good, cudaStream_t st);
-int launch_s2_flag(const Contig* contigs, const Tile* tiles, uint64_t ntiles, const uint32_t* need_list, const uint32_t* n_need, int k,
-                   const uint32_t* single, const uint32_t* good, uint32_t* flagged, cudaStream_t st);
-int launch_s2_count_new(const Tile* tiles, const uint32_t* need_list, const uint32_t* n_need, const uint32_t* flagged,
-                        uint32_t* tile_new, unsigned long long* flagged_total, cudaStream_t st);
+// [t_lo, t_hi): only the needed tiles inside that range are visited (multi-GPU: each rank its own block of tiles)
+int launch_s2_good(const Contig* contigs, const Tile* tiles, const uint32_t* need_list, const uint32_t* n_need, uint64_t t_lo, uint64_t t_hi,
+                   const uint32_t* single, const uint32_t* trio, int one_min, int three_min, uint32_t* good, cudaStream_t st);
+int launch_s2_flag(const Contig* contigs, const Tile* tiles, uint64_t ntiles, const uint32_t* need_list, const uint32_t* n_need,
+                   uint64_t t_lo, uint64_t t_hi, int k, const uint32_t* single, const uint32_t* good, uint32_t* flagged, cudaStream_t st);
+int launch_s2_count_new(const Tile* tiles, const uint32_t* need_list, const uint32_t* n_need, uint64_t t_lo, uint64_t t_hi,
+                        const uint32_t* flagged, uint32_t* tile_new, unsigned long long* flagged_total, cudaStream_t st);
 // mode 0: write loci + scatter-max peak ids + pre-filter bits; mode 1: clear what mode 0 wrote
 int launch_s2_register(const uint32_t* image, const Contig* contigs, const Tile* tiles, const uint32_t* need_list, const uint32_t* n_need,
-                       const HashP& hp, const uint32_t* count, const uint32_t* flagged, const uint32_t* tile_base, int32_t* loci,
-                       uint32_t loci_cap, uint32_t* peak_kmer, uint32_t* prefilter, int mode, cudaStream_t st);
+                       uint64_t t_lo, uint64_t t_hi, const HashP& hp, const uint32_t* count, const uint32_t* flagged, const uint32_t* tile_base,
+                       int32_t* loci, uint32_t loci_cap, uint32_t* peak_kmer, uint32_t* prefilter, int mode, cudaStream_t st);
 
 // S2 gather through table slices (tables > 128 MiB, e <= 4): one chunk of at most 2^18 tiles per call -- records into
 // s2_gs_buckets() regions of `cap` in `pool` (cursor: s2_gs_cursor_words() zeroed words), answered slice by slice into the e
@@ -175,7 +176,7 @@ size_t s2_regemit_smem();
 int s2_reg_buckets();
 int s2_reg_cursor_words();
 int launch_s2_register_bucketed(const uint32_t* image, const Contig* contigs, const Tile* tiles, const uint32_t* need_list,
-                                const uint32_t* n_need, uint32_t it_lo, uint32_t it_hi, const HashP& hp, const uint32_t* count,
+                                const uint32_t* n_need, uint32_t it_lo, uint32_t it_hi, uint64_t t_lo, uint64_t t_hi, const HashP& hp, const uint32_t* count,
                                 const uint32_t* flagged, const uint32_t* tile_base, int32_t* loci, uint32_t loci_cap, uint32_t* peak_kmer,
                                 uint32_t* prefilter, uint2* pool, uint32_t* cursor, uint32_t cap, cudaStream_t st);
 

@@ -73,6 +73,19 @@ class GpuEngine:
     def peak_filter(self):
         return self._wrap(self.scr.dev_peak_filter())
 
+    def tile_new(self):
+        return self._wrap(self.scr.dev_tile_new())
+
+    def flagged(self):
+        return self._wrap(self.scr.dev_flagged())
+
+    def peak_table(self):
+        return self._wrap(self.scr.dev_peak_table()).view(self.torch.int32)      # ids stay below 2^31 (max_peak)
+
+    def loci(self):
+        t = self._wrap(self.scr.dev_loci())
+        return None if t is None else t.view(self.torch.int32)
+
     def sync(self):
         self.scr.sync()
 
@@ -208,17 +221,19 @@ class Shard:
         lo = min(ntiles, self.rank * B)
         return B, lo, min(ntiles, lo + B)
 
-    def exchange_hit_bits(self, ntiles: int, which=(0, 1)) -> None:
-        """All-gather, in place, of the per-rank tile blocks of the hit-bit arrays (the arrays are padded to world * B tiles)."""
-        tb = self.eng.tile_bytes()
+    def _gather_blocks(self, t, ntiles: int, bytes_per_tile: int) -> None:
+        """All-gather, in place, of the per-rank tile blocks of a tile-major device array (padded to world * B tiles)."""
         B, _, _ = self.tile_block(ntiles)
+        n = B * bytes_per_tile
+        if t.numel() < self.world * n:
+            raise ValueError("tile-major array lacks the padding for equal tile blocks")
+        self.dist.all_gather_into_tensor(t[: self.world * n], t[self.rank * n:(self.rank + 1) * n])
+        self._fence(t)
+
+    def exchange_hit_bits(self, ntiles: int, which=(0, 1)) -> None:
         self._engine_done()
         for w_ in which:
-            bits = self.eng.hit_bits(w_)
-            if bits.numel() < self.world * B * tb:
-                raise ValueError("hit-bit array lacks the padding for equal tile blocks")
-            self.dist.all_gather_into_tensor(bits[: self.world * B * tb], bits[self.rank * B * tb:(self.rank + 1) * B * tb])
-            self._fence(bits)
+            self._gather_blocks(self.eng.hit_bits(w_), ntiles, self.eng.tile_bytes())
 
     # ---- the pass
     def screen(self, *, size1: int, sample_arg: float, seed: int, rand_skip: int, hit: float, match: float,
@@ -289,8 +304,33 @@ class Shard:
             self.exchange_hit_bits(nt, which=(0,))
             self._end(ev)
             t = lap("exchange_hit_bits", t)
-            n_peaks = eng.s2_finish(hit, match, max_peak)
-            t = lap("s2_finish", t)
+            # windows / peak opening by tile block; ids need every tile's new-peak count
+            eng.s2_windows(hit, match, lo, hi)
+            ev = self._span("exchange_tile_new")
+            self._engine_done()
+            self._gather_blocks(eng.tile_new(), nt, 4)
+            self._end(ev)
+            flagged_total = sum(r[0] for r in self._all_gather_ints([eng.s2_flagged_in_range()]))
+            n_peaks = eng.s2_ids(max_peak, flagged_total)
+            t = lap("s2_windows", t)
+            if n_peaks > 0 and eng.s2_dense():
+                # many registered k-mers: each rank registers its block, the tables are combined with MAX (= the last writer of
+                # the sequential loop, since ids grow with position)
+                eng.s2_register(lo, hi)
+                ev = self._span("reduce_peak_table")
+                self._engine_done()
+                for buf in (eng.peak_table(), eng.loci()):
+                    self.dist.all_reduce(buf, op=self.dist.ReduceOp.MAX)
+                    self._fence(buf)
+                self._end(ev)
+            elif n_peaks > 0:
+                # few: everybody registers everything, from the all-gathered flagged bits
+                ev = self._span("exchange_flagged")
+                self._engine_done()
+                self._gather_blocks(eng.flagged(), nt, self.eng.tile_bytes())
+                self._end(ev)
+                eng.s2_register(0, nt)
+            t = lap("s2_register", t)
         else:
             n_peaks = eng.s2_peaks(hit, match, max_peak)
             t = lap("s2", t)

@@ -42,6 +42,14 @@ def test_two_gpus_stream_counting_path(tmp_path):
     _run(2, str(tmp_path), "base_k24", "p2p", env={"LHGT_LEAF_LOG2": "12", "LHGT_TEST_S1_MODE": "2"})
 
 
+@pytest.mark.skipif(N_GPUS < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("case", ["base_k20", "noisy"])
+def test_two_gpus_dense_plan(case, tmp_path):
+    """The plan for results with many registered k-mers (forced here): every rank registers the flagged positions of its own
+    tile block, the peak tables and loci are combined with an element-wise MAX, S3 runs without the pre-filter."""
+    _run(2, str(tmp_path), case, "p2p", env={"LHGT_DENSE_RECORDS": "1000"})
+
+
 @pytest.mark.skipif(N_GPUS < 3, reason="needs 3 GPUs")
 @pytest.mark.parametrize("form", ["p2p", "nccl"])
 def test_three_gpus_uneven_slices(form, tmp_path):
