@@ -199,6 +199,10 @@ long     lhgt_s2_needed_tiles(const lhgt_ctx* c);        /* marked tiles of the 
  *            With lhgt_s2_dense() the ranks then combine their peak tables and loci with an element-wise MAX (ids grow
  *            with position, so the maximum is the last writer of the sequential loop); otherwise they all-gather the
  *            flagged bits and every rank registers everything. */
+/* The marked tiles are listed in tile order; lhgt_s2_need_range gives the tile range holding share `part` of `parts`
+ * equal shares of them (the shares tile the reference): the block a rank takes for windows and register -- the marked tiles
+ * cluster where the sample's genomes are, so equal blocks of ALL tiles would leave most ranks idle there. */
+int      lhgt_s2_need_range(lhgt_ctx* c, int part, int parts, long* tile_begin, long* tile_end);
 int      lhgt_s2_windows(lhgt_ctx* c, float hit_ratio, float match_ratio, long tile_begin, long tile_end);
 long     lhgt_s2_flagged_in_range(lhgt_ctx* c);
 int      lhgt_s2_ids(lhgt_ctx* c, long max_peak, long flagged_total, long* n_peaks);

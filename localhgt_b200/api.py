@@ -91,6 +91,7 @@ SYMBOLS = {
     "lhgt_s2_tiles": (_l, [_vp]),
     "lhgt_s2_gather": (_i, [_vp, _l, _l]),
     "lhgt_s2_finish": (_i, [_vp, _f, _f, _l, C.POINTER(_l)]),
+    "lhgt_s2_need_range": (_i, [_vp, _i, _i, C.POINTER(_l), C.POINTER(_l)]),
     "lhgt_s2_windows": (_i, [_vp, _f, _f, _l, _l]),
     "lhgt_s2_flagged_in_range": (_l, [_vp]),
     "lhgt_s2_ids": (_i, [_vp, _l, _l, C.POINTER(_l)]),
@@ -351,6 +352,11 @@ class Screen:
         _check(self._L.lhgt_s2_complete(self._h, tile_begin, tile_end))
 
     def s2_needed_tiles(self) -> int: return int(self._L.lhgt_s2_needed_tiles(self._h))
+
+    def s2_need_range(self, part: int, parts: int):
+        lo, hi = _l(0), _l(0)
+        _check(self._L.lhgt_s2_need_range(self._h, part, parts, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
 
     def s2_windows(self, hit_ratio: float, match_ratio: float, tile_begin: int = 0, tile_end: int = -1) -> None:
         _check(self._L.lhgt_s2_windows(self._h, hit_ratio, match_ratio, tile_begin, tile_end))

@@ -145,8 +145,9 @@ struct lhgt_ctx {
 
     uint32_t *d_single = nullptr, *d_trio = nullptr, *d_good = nullptr, *d_flagged = nullptr;
     uint32_t *d_tile_new = nullptr, *d_tile_base = nullptr, *d_scan_tmp = nullptr;
+    uint32_t share_lo = 0, share_hi = 0; long share_tile_lo = -1, share_tile_hi = -1, n_flagged_local = 0;   // this rank's share of the needed tiles
     bool gathered = false, marked = false, windows_done = false; float mark_match = 0.f; uint32_t n_needed_tiles = 0;
-    DevBuf<uint8_t> hot_buf; DevBuf<uint32_t> need_buf; uint32_t* d_misc = nullptr;
+    DevBuf<uint8_t> hot_buf; DevBuf<uint32_t> need_buf, mark_tmp_buf; uint32_t* d_misc = nullptr;
     DevBuf<uint2> gs_pool_buf; DevBuf<uint32_t> gs_cursor_buf, sat_buf; bool single_exact = false;   // S2 gather through table slices
     DevBuf<uint2> reg_pool_buf; DevBuf<uint32_t> reg_cursor_buf; bool filter_on = true;   // S2 registration through buckets
     DevBuf<uint32_t> contig_first_buf, s3_tables_buf; DevBuf<uint2> s3_arena_buf, s3_queue_buf;   // S3: peak -> contig search, vote hand-over
@@ -356,7 +357,7 @@ static void drop_index(lhgt_ctx* c, bool release = false) {     // forgets the i
     if (release) {
         c->image_buf.release(); c->single_buf.release(); c->trio_buf.release(); c->good_buf.release(); c->flagged_buf.release();
         c->tile_new_buf.release(); c->tile_base_buf.release(); c->scan_tmp_buf.release(); c->contigs_buf.release(); c->tiles_buf.release();
-        c->hot_buf.release(); c->need_buf.release();
+        c->hot_buf.release(); c->need_buf.release(); c->mark_tmp_buf.release();
         c->fq_cnt_buf.release(); c->fq_base_buf.release(); c->fq_tmp_buf.release();
     }
     c->d_image = nullptr; c->image_owned = true; c->image_words = 0;
@@ -1323,10 +1324,44 @@ extern "C" int lhgt_s2_mark(lhgt_ctx* c, float match_ratio) {
     CU(cudaMemsetAsync(c->d_misc + MISC_NEED, 0, sizeof(uint32_t), c->st));
     {
         Span sp(c, 3);
-        c->launches += launch_s2_mark(c->d_contigs, c->d_tiles, nt, c->d_trio, three_min, c->hot_buf.p, c->need_buf.p, c->d_misc + MISC_NEED, c->st);
+        int rc = c->mark_tmp_buf.reserve(s2_mark_scratch_words(nt));
+        if (rc) return rc;
+        c->launches += launch_s2_mark(c->d_contigs, c->d_tiles, nt, c->d_trio, three_min, c->hot_buf.p, c->need_buf.p, c->d_misc + MISC_NEED,
+                                      c->mark_tmp_buf.p, c->st);
     }
     c->marked = true;
     c->mark_match = match_ratio;
+    return 0;
+}
+
+// The tile range [*tile_begin, *tile_end) that holds share `part` of `parts` equal shares of the needed tiles (the list is in
+// tile order): what rank `part` of a multi-GPU run takes for the window passes and the registration.  Synchronises.
+extern "C" int lhgt_s2_need_range(lhgt_ctx* c, int part, int parts, long* tile_begin, long* tile_end) {
+    if (!c || !tile_begin || !tile_end || parts < 1 || part < 0 || part >= parts) return fail(LHGT_E_ARG, "lhgt_s2_need_range: bad argument");
+    if (!c->index_ready || !c->marked) return fail(LHGT_E_STATE, "mark the needed tiles first (lhgt_s2_mark)");
+    CU(cudaSetDevice(c->device));
+    uint32_t n = 0;
+    CU(cudaMemcpyAsync(&n, c->d_misc + MISC_NEED, 4, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    long nt = (long)c->tiles.size();
+    uint64_t lo = (uint64_t)n * part / parts, hi = (uint64_t)n * (part + 1) / parts;
+    uint32_t first = 0, last = 0;
+    if (hi > lo) {
+        CU(cudaMemcpyAsync(&first, c->need_buf.p + lo, 4, cudaMemcpyDeviceToHost, c->st));
+        CU(cudaMemcpyAsync(&last, c->need_buf.p + hi - 1, 4, cudaMemcpyDeviceToHost, c->st));
+        CU(cudaStreamSynchronize(c->st));
+    }
+    c->share_lo = (uint32_t)lo; c->share_hi = (uint32_t)hi;
+    // shares tile the whole reference: share 0 starts at tile 0, the last one ends at the last tile, empty shares are empty ranges
+    *tile_begin = hi > lo ? (part == 0 || lo == 0 ? 0 : (long)first) : (part == 0 ? 0 : nt);
+    *tile_end = hi > lo ? (hi == n ? nt : (long)last + 1) : *tile_begin;
+    if (hi > lo && hi < n) {                                      // ends where the next share's first needed tile begins
+        uint32_t next = 0;
+        CU(cudaMemcpyAsync(&next, c->need_buf.p + hi, 4, cudaMemcpyDeviceToHost, c->st));
+        CU(cudaStreamSynchronize(c->st));
+        *tile_end = (long)next;
+    }
+    c->share_tile_lo = *tile_begin; c->share_tile_hi = *tile_end;
     return 0;
 }
 
@@ -1432,6 +1467,7 @@ extern "C" int lhgt_s2_ids(lhgt_ctx* c, long max_peak, long flagged_total, long*
     CU(cudaStreamSynchronize(c->st));
     long total = (long)last_new + (long)last_base;
     c->n_flagged = flagged_total >= 0 ? flagged_total : (long)flagged_local;
+    c->n_flagged_local = (long)flagged_local;
     if (total > max_peak) return fail(LHGT_E_TOO_MANY_PEAKS, "%ld peaks exceed max_peak=%ld (E:272-274)", total, max_peak);
     if (total > c->peaks_cap) {
         dev_free(c->d_loci); dev_free(c->d_filter);
@@ -1474,11 +1510,13 @@ extern "C" int lhgt_s2_register(lhgt_ctx* c, long tile_begin, long tile_end) {
     uint32_t loci_cap = (uint32_t)std::min<long>(c->peaks_cap, 0xffffffffL);
     uint32_t* prefilter = c->filter_on ? c->d_prefilter : nullptr;
     const char* force = getenv("LHGT_REG_BUCKETED");               // test knob: 1 forces the bucketed form, 0 the direct one
-    double share = (double)(tile_end - tile_begin) / (double)nt;
-    double records = (double)c->n_flagged * c->e * share;          // expected in this range
+    // the part of the (tile-ordered) needed-tile list this call covers, and the records it will produce
+    bool own_share = c->share_tile_lo == tile_begin && c->share_tile_hi == tile_end && !(tile_begin == 0 && tile_end == nt);
+    uint32_t it_lo = own_share ? c->share_lo : 0u, it_hi = own_share ? c->share_hi : c->n_needed_tiles;
+    double records = (double)(own_share ? c->n_flagged_local : c->n_flagged) * c->e;
     bool bucketed = force ? atoi(force) != 0 : records >= 8e6;      // below that the direct atomics finish in well under a millisecond
-    if (bucketed && c->n_needed_tiles > 0) {
-        // record regions: the S1 leaf-stream pool when there is one (idle now), else a buffer of our own
+    if (bucketed && it_hi > it_lo) {
+        // record regions: the S1 stream pools when there are (idle now), else a buffer of our own
         const char* kb = getenv("LHGT_REG_POOL_KB");                 // test knob: small regions force chunks and overflow
         uint2* pool = nullptr; uint64_t pool_records = 0;
         if (!kb && c->d_bin_pool_b && c->bin_pool_b_entries / 2 >= ((uint64_t)32 << 20)) { pool = (uint2*)c->d_bin_pool_b; pool_records = c->bin_pool_b_entries / 2; }
@@ -1492,12 +1530,12 @@ extern "C" int lhgt_s2_register(lhgt_ctx* c, long tile_begin, long tile_end) {
         int rc = c->reg_cursor_buf.reserve((size_t)s2_reg_cursor_words());
         if (rc) return rc;
         uint32_t cap = (uint32_t)std::min<uint64_t>(pool_records / (uint64_t)s2_reg_buckets(), 0xfffffff0u);
-        // the needed-tile list is walked in chunks whose records fit the regions (records per needed tile of the range, on average)
-        double per_tile = std::max(1.0, (double)c->n_flagged * c->e / (double)c->n_needed_tiles);
-        uint32_t chunk = (uint32_t)std::max(1.0, std::min((double)c->n_needed_tiles, 0.85 * (double)cap * s2_reg_buckets() / per_tile));   // fits even if every tile of the chunk lies in the range
-        for (uint32_t lo = 0; lo < c->n_needed_tiles; lo += chunk) {
+        // the list is walked in chunks whose records fit the regions (records per needed tile, on average)
+        double per_tile = std::max(1.0, records / (double)(it_hi - it_lo));
+        uint32_t chunk = (uint32_t)std::max(1.0, std::min((double)(it_hi - it_lo), 0.85 * (double)cap * s2_reg_buckets() / per_tile));
+        for (uint32_t lo = it_lo; lo < it_hi; lo += chunk) {
             CU(cudaMemsetAsync(c->reg_cursor_buf.p, 0, (size_t)s2_reg_cursor_words() * 4, c->st));
-            int nl = launch_s2_register_bucketed(c->d_image, c->d_contigs, c->d_tiles, need, n_need, lo, std::min(c->n_needed_tiles, lo + chunk), t_lo, t_hi, c->hp,
+            int nl = launch_s2_register_bucketed(c->d_image, c->d_contigs, c->d_tiles, need, n_need, lo, std::min(it_hi, lo + chunk), t_lo, t_hi, c->hp,
                                                  c->d_count, c->d_flagged, c->d_tile_base, c->d_loci, loci_cap, c->d_peak_kmer, prefilter,
                                                  pool, c->reg_cursor_buf.p, cap, c->st);
             if (nl < 0) return fail(LHGT_E_CUDA, "registration kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));

@@ -1310,23 +1310,42 @@ __global__ void __launch_bounds__(256) s2_hot_kernel(const Contig* __restrict__ 
 // pass c: the tiles the remaining passes have to look at = those within two tiles of a hot one on the same contig: a good
 // window reaches 499 positions back for `one` (E:597-608), an interval 1000 positions either side of a good window
 // (E:617-638) and the coverage-edge test 2k+9 further (E:640-671).  Everywhere else good = flagged = 0 whatever `single`
-// holds.  The list is unordered (appended with one atomic per warp); every consumer treats tiles independently.
-__global__ void __launch_bounds__(256) s2_need_kernel(const Tile* __restrict__ tiles, uint64_t ntiles, const uint8_t* __restrict__ hot,
-                                                      uint32_t* __restrict__ need_list, uint32_t* __restrict__ n_need) {
-    uint64_t tix = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool need = false;
-    if (tix < ntiles) {
-        uint32_t contig = tiles[tix].contig;
-        for (long u = (long)tix - 2; u <= (long)tix + 2; ++u)
-            if (u >= 0 && u < (long)ntiles && hot[u] && tiles[u].contig == contig) need = true;
-    }
-    uint32_t m = __ballot_sync(kFull, need);
-    if (!m) return;
-    int lane = threadIdx.x & 31;
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(n_need, (uint32_t)__popc(m));
-    base = __shfl_sync(kFull, base, 0);
-    if (need) need_list[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)tix;
+// holds.  The list is compacted IN TILE ORDER (count per 1024 tiles, scan, write): every rank of a multi-GPU run holds the
+// same list and takes an equal share of it, which is a contiguous range of tiles.
+__device__ __forceinline__ bool tile_needed(const Tile* __restrict__ tiles, uint64_t ntiles, const uint8_t* __restrict__ hot, uint64_t tix) {
+    if (tix >= ntiles) return false;
+    uint32_t contig = tiles[tix].contig;
+    for (long u = (long)tix - 2; u <= (long)tix + 2; ++u)
+        if (u >= 0 && u < (long)ntiles && hot[u] && tiles[u].contig == contig) return true;
+    return false;
+}
+
+__global__ void __launch_bounds__(256) s2_need_count_kernel(const Tile* __restrict__ tiles, uint64_t ntiles, const uint8_t* __restrict__ hot,
+                                                            uint32_t* __restrict__ block_cnt) {
+    __shared__ uint32_t sm[33];
+    uint64_t base = (uint64_t)blockIdx.x * 1024 + threadIdx.x * 4;
+    uint32_t c = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) c += tile_needed(tiles, ntiles, hot, base + q);
+    uint32_t total;
+    block_exclusive_scan(c, &total, sm);
+    if (threadIdx.x == 0) block_cnt[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(256) s2_need_write_kernel(const Tile* __restrict__ tiles, uint64_t ntiles, const uint8_t* __restrict__ hot,
+                                                            const uint32_t* __restrict__ block_cnt, const uint32_t* __restrict__ block_base,
+                                                            uint32_t* __restrict__ need_list, uint32_t* __restrict__ n_need) {
+    __shared__ uint32_t sm[33];
+    uint64_t base = (uint64_t)blockIdx.x * 1024 + threadIdx.x * 4;
+    bool need[4];
+    uint32_t c = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { need[q] = tile_needed(tiles, ntiles, hot, base + q); c += need[q]; }
+    uint32_t total, at = block_exclusive_scan(c, &total, sm) + block_base[blockIdx.x];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (need[q]) need_list[at++] = (uint32_t)(base + q);
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *n_need = block_base[blockIdx.x] + block_cnt[blockIdx.x];
 }
 
 // pass d: `single` made exact on the needed tiles of [tile_begin, tile_end): a short-circuit OR over hashes 1..e-1 for the
@@ -1960,12 +1979,19 @@ int launch_s2_gather(const uint32_t* image, const Contig* contigs, const Tile* t
     return 1;
 }
 
+// scratch: 2 * ceil(ntiles / 1024) + scan_tmp_words(ceil(ntiles / 1024)) words
+size_t s2_mark_scratch_words(uint64_t ntiles) { uint64_t b = (ntiles + 1023) / 1024; return 2 * b + scan_tmp_words(b) + 2; }
+
 int launch_s2_mark(const Contig* contigs, const Tile* tiles, uint64_t ntiles, const uint32_t* trio, int three_min, uint8_t* hot,
-                   uint32_t* need_list, uint32_t* n_need, cudaStream_t st) {
+                   uint32_t* need_list, uint32_t* n_need, uint32_t* scratch, cudaStream_t st) {
     if (!ntiles) return 0;
+    uint64_t blocks = (ntiles + 1023) / 1024;
+    uint32_t *cnt = scratch, *base = scratch + blocks, *tmp = scratch + 2 * blocks;
     s2_hot_kernel<<<(unsigned)((ntiles + 7) / 8), 256, 0, st>>>(contigs, tiles, ntiles, trio, three_min, hot);
-    s2_need_kernel<<<(unsigned)((ntiles + 255) / 256), 256, 0, st>>>(tiles, ntiles, hot, need_list, n_need);
-    return 2;
+    s2_need_count_kernel<<<(unsigned)blocks, 256, 0, st>>>(tiles, ntiles, hot, cnt);
+    int l = 2 + launch_scan_exclusive(cnt, base, blocks, tmp, st);
+    s2_need_write_kernel<<<(unsigned)blocks, 256, 0, st>>>(tiles, ntiles, hot, cnt, base, need_list, n_need);
+    return l + 1;
 }
 
 int launch_s2_single(const uint32_t* image, const Contig* contigs, const Tile* tiles, const uint32_t* need_list, const uint32_t* n_need,

@@ -136,14 +136,15 @@ size_t s1_bin_smem_bytes(const BinP& bp);
 int s1_leaf_max_log2();              // largest table slice (log2 counters) s1_leaf_kernel holds in shared memory
 
 // S2.  gather: trio (exact) + hash-0 hits as the lower bound of single, for tiles [tile_begin, tile_end);
-// mark: hot tiles and the unordered list of tiles the remaining passes must visit (*n_need zeroed by the caller);
+// mark: hot tiles and the list, in tile order, of the tiles the remaining passes must visit;
 // single: `single` made exact on the needed tiles of [tile_begin, tile_end); the rest run over the needed tiles only
 // (good / flagged / tile_new must be zero elsewhere: the caller clears them).
 int launch_s2_gather(const uint32_t* image, const Contig* contigs, const Tile* tiles, uint64_t tile_begin,
                      uint64_t tile_end, const HashP& hp, const uint32_t* count, uint32_t* single,
                      uint32_t* trio, cudaStream_t st);
+size_t s2_mark_scratch_words(uint64_t ntiles);
 int launch_s2_mark(const Contig* contigs, const Tile* tiles, uint64_t ntiles, const uint32_t* trio, int three_min, uint8_t* hot,
-                   uint32_t* need_list, uint32_t* n_need, cudaStream_t st);
+                   uint32_t* need_list, uint32_t* n_need, uint32_t* scratch, cudaStream_t st);
 int launch_s2_single(const uint32_t* image, const Contig* contigs, const Tile* tiles, const uint32_t* need_list, const uint32_t* n_need,
                      uint64_t tile_begin, uint64_t tile_end, const HashP& hp, const uint32_t* count, uint32_t* single, cudaStream_t st);
 // [t_lo, t_hi): only the needed tiles inside that range are visited (multi-GPU: each rank its own block of tiles)

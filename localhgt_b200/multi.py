@@ -304,19 +304,23 @@ class Shard:
             self.exchange_hit_bits(nt, which=(0,))
             self._end(ev)
             t = lap("exchange_hit_bits", t)
-            # windows / peak opening by tile block; ids need every tile's new-peak count
-            eng.s2_windows(hit, match, lo, hi)
+            # windows / peak opening / registration by equal shares of the MARKED tiles (they cluster where the sample's genomes
+            # are); ids need every tile's new-peak count
+            wlo, whi = eng.s2_need_range(self.rank, w)
+            eng.s2_windows(hit, match, wlo, whi)
             ev = self._span("exchange_tile_new")
             self._engine_done()
-            self._gather_blocks(eng.tile_new(), nt, 4)
+            tn = eng.tile_new().view(self.torch.int32)
+            self.dist.all_reduce(tn)                                   # every tile is counted by exactly one rank
+            self._fence(tn)
             self._end(ev)
             flagged_total = sum(r[0] for r in self._all_gather_ints([eng.s2_flagged_in_range()]))
             n_peaks = eng.s2_ids(max_peak, flagged_total)
             t = lap("s2_windows", t)
             if n_peaks > 0 and eng.s2_dense():
-                # many registered k-mers: each rank registers its block, the tables are combined with MAX (= the last writer of
+                # many registered k-mers: each rank registers its share, the tables are combined with MAX (= the last writer of
                 # the sequential loop, since ids grow with position)
-                eng.s2_register(lo, hi)
+                eng.s2_register(wlo, whi)
                 ev = self._span("reduce_peak_table")
                 self._engine_done()
                 for buf in (eng.peak_table(), eng.loci()):
@@ -324,10 +328,13 @@ class Shard:
                     self._fence(buf)
                 self._end(ev)
             elif n_peaks > 0:
-                # few: everybody registers everything, from the all-gathered flagged bits
+                # few: everybody registers everything, from the combined flagged bits (a word is written by its owner and, for
+                # the halo tile, identically by the next share's owner: MAX of equal or zero words)
                 ev = self._span("exchange_flagged")
                 self._engine_done()
-                self._gather_blocks(eng.flagged(), nt, self.eng.tile_bytes())
+                fl = eng.flagged()                                     # as bytes: unsigned, so MAX never drops a word with its top bit set
+                self.dist.all_reduce(fl, op=self.dist.ReduceOp.MAX)
+                self._fence(fl)
                 self._end(ev)
                 eng.s2_register(0, nt)
             t = lap("s2_register", t)
