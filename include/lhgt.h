@@ -101,6 +101,15 @@ int      lhgt_index_len_text(const lhgt_ctx* c, char* dst, size_t cap, size_t* n
 /* One record of the resident image (E:921-931: u32 len, then (len-k+1)*e hashes) by its ordinal among the indexed
  * contigs; dst = NULL returns the number of 32-bit words. */
 long     lhgt_index_record(lhgt_ctx* c, long record, uint32_t* dst, uint64_t cap_words);
+/* Images larger than one GPU (row e-S): the ranks of a box each keep ONE block of the image -- equal runs of 1024-position
+ * tiles, block 0 with the header -- and build only that (lhgt_set_image_block before lhgt_index_build*; the FASTA is still
+ * parsed whole, it is 1/12 of the image at e = 3).  Every stage that reads stored hashes (S2 gather / complete / register)
+ * then accepts tile ranges inside the block only; the multi-GPU plan (localhgt_b200/multi.py) exchanges hit bits, flagged bits
+ * and peak tables so that no rank ever needs another rank's hashes.  lhgt_index_download / lhgt_index_write_block move the
+ * resident block; lhgt_index_block says where it sits in the file. */
+int      lhgt_set_image_block(lhgt_ctx* c, int part, int parts);
+int      lhgt_index_block(const lhgt_ctx* c, uint64_t* byte_offset, uint64_t* bytes, long* tile_begin, long* tile_end);
+int      lhgt_index_write_block(lhgt_ctx* c, const char* index_path);
 /* Makes an existing image HBM-resident (read_index's input, E:888-979) and adopts its coder
  * (E:1417).  lhgt_index_attach_device uses an image that already lives on this device. */
 int      lhgt_index_upload(lhgt_ctx* c, const uint8_t* image, uint64_t n);

@@ -64,6 +64,9 @@ SYMBOLS = {
     "lhgt_index_download": (_i, [_vp, _vp, _u64]),
     "lhgt_index_len_text": (_i, [_vp, _vp, _sz, C.POINTER(_sz)]),
     "lhgt_index_record": (_l, [_vp, _l, _vp, _u64]),
+    "lhgt_set_image_block": (_i, [_vp, _i, _i]),
+    "lhgt_index_block": (_i, [_vp, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_l), C.POINTER(_l)]),
+    "lhgt_index_write_block": (_i, [_vp, _s]),
     "lhgt_index_upload": (_i, [_vp, _vp, _u64]),
     "lhgt_index_build_file": (_i, [_vp, _s, _s, _s]),
     "lhgt_index_load_file": (_i, [_vp, _s]),
@@ -255,8 +258,21 @@ class Screen:
     def index_bases(self) -> int: return int(self._L.lhgt_index_bases(self._h))
     def index_contigs(self) -> int: return int(self._L.lhgt_index_contigs(self._h))
 
+    def set_image_block(self, part: int, parts: int) -> None:
+        """Keep only block `part` of `parts` of the image resident from the next index build on (images larger than one GPU)."""
+        _check(self._L.lhgt_set_image_block(self._h, part, parts))
+
+    def index_block(self):
+        """(byte offset in the file, bytes, first tile, end tile) of the resident part of the image."""
+        off, n, t0, t1 = _u64(0), _u64(0), _l(0), _l(0)
+        _check(self._L.lhgt_index_block(self._h, C.byref(off), C.byref(n), C.byref(t0), C.byref(t1)))
+        return int(off.value), int(n.value), int(t0.value), int(t1.value)
+
+    def index_write_block(self, path: str) -> None:
+        _check(self._L.lhgt_index_write_block(self._h, path.encode()))
+
     def index_download(self) -> np.ndarray:
-        out = np.zeros(self.index_bytes(), dtype=np.uint8)
+        out = np.zeros(self.index_block()[1], dtype=np.uint8)
         _check(self._L.lhgt_index_download(self._h, _ptr(out), out.size))
         return out
 

@@ -134,6 +134,9 @@ struct lhgt_ctx {
     uint32_t* d_prefilter = nullptr;
 
     uint32_t* d_image = nullptr; uint64_t image_words = 0; bool image_owned = true;
+    // image block (multi-GPU, images larger than one GPU): only words [blk_word_lo, blk_word_hi) = tiles [blk_tile_lo, blk_tile_hi) are
+    // resident; d_image is then the VIRTUAL base (resident pointer - blk_word_lo) so that every kernel indexes it as if it were whole
+    int blk_part = 0, blk_parts = 1; uint64_t blk_word_lo = 0, blk_word_hi = 0; long blk_tile_lo = 0, blk_tile_hi = 0; bool image_partial = false;
     DevBuf<uint32_t> image_buf, single_buf, trio_buf, good_buf, flagged_buf, tile_new_buf, tile_base_buf, scan_tmp_buf;
     DevBuf<uint32_t> fq_cnt_buf, fq_base_buf, fq_tmp_buf;    // FASTQ newline-scan temporaries
     DevBuf<Contig> contigs_buf; DevBuf<Tile> tiles_buf;
@@ -185,6 +188,7 @@ struct lhgt_ctx {
 struct Reads;
 static int index_reads(lhgt_ctx* c, Reads& r, int last_byte, uint64_t tail_start);
 static uint64_t last_line_start(const uint8_t* p, uint64_t n);
+static int ring_ready(lhgt_ctx* c);
 static int start_prefetch(lhgt_ctx* c, lhgt_ctx::Prefetch& p, void* dst, const void* host, uint64_t n);
 static bool adopt_prefetch(lhgt_ctx* c, lhgt_ctx::Prefetch& p, const void* host, uint64_t n);
 
@@ -470,6 +474,29 @@ static int alloc_image(lhgt_ctx* c, uint64_t words) {
     int rc = c->image_buf.reserve(words);
     if (rc) return rc;
     c->d_image = c->image_buf.p; c->image_words = words; c->image_owned = true;
+    c->image_partial = false; c->blk_word_lo = 0; c->blk_word_hi = words;
+    return 0;
+}
+
+// word of the image at which tile t begins (its contig's length word included when it is the contig's first tile)
+static uint64_t tile_word(const lhgt_ctx* c, size_t t) {
+    const Tile& tl = c->tiles[t];
+    const Contig& g = c->contigs[tl.contig];
+    return g.hash_word + (uint64_t)tl.j0 * c->e - (tl.j0 == 0 ? 1 : 0);
+}
+
+// Keeps only this context's block of the image resident (lhgt_set_image_block): equal blocks of tiles, block 0 with the header.
+static int alloc_image_block(lhgt_ctx* c, uint64_t words) {
+    size_t nt = c->tiles.size();
+    long B = (long)((nt + c->blk_parts - 1) / c->blk_parts);
+    long lo = std::min<long>((long)nt, c->blk_part * B), hi = std::min<long>((long)nt, lo + B);
+    uint64_t wlo = c->blk_part == 0 ? 0 : (lo < (long)nt ? tile_word(c, (size_t)lo) : words);
+    uint64_t whi = (c->blk_part == c->blk_parts - 1 || hi >= (long)nt) ? words : tile_word(c, (size_t)hi);
+    int rc = c->image_buf.reserve(std::max<uint64_t>(whi - wlo, 1));
+    if (rc) return rc;
+    c->d_image = (uint32_t*)((uintptr_t)c->image_buf.p - (uintptr_t)wlo * 4);
+    c->image_words = words; c->image_owned = true;
+    c->image_partial = c->blk_parts > 1; c->blk_word_lo = wlo; c->blk_word_hi = whi; c->blk_tile_lo = lo; c->blk_tile_hi = hi;
     return 0;
 }
 
@@ -567,13 +594,16 @@ static int index_build_from_device(lhgt_ctx* c, const uint8_t* d_fa, size_t n) {
     c->len_text = pf.len_text;
     uint64_t words = LHGT_CODER_SLOTS;
     for (auto& g : c->contigs) words += 1 + (uint64_t)(g.len - c->k + 1) * c->e;
-    if ((rc = alloc_image(c, words)) || (rc = finish_index_tables(c))) return rc;
+    if ((rc = finish_index_tables(c))) return rc;
+    if (c->blk_parts > 1) rc = alloc_image_block(c, words); else rc = alloc_image(c, words);
+    if (rc) return rc;
     uint32_t header[LHGT_CODER_SLOTS];
     lhgt_coder_to_header(c->cc, header);
-    CU(cudaMemcpyAsync(c->d_image, header, sizeof header, cudaMemcpyHostToDevice, c->st));
+    if (c->blk_word_lo == 0) CU(cudaMemcpyAsync(c->d_image, header, sizeof header, cudaMemcpyHostToDevice, c->st));
     {
         Span sp(c, 5);
-        c->launches += launch_index_build(d_seq, c->d_contigs, c->d_tiles, c->tiles.size(), c->hp, c->d_image, nullptr, c->st);
+        size_t t0 = c->image_partial ? (size_t)c->blk_tile_lo : 0, t1 = c->image_partial ? (size_t)c->blk_tile_hi : c->tiles.size();
+        c->launches += launch_index_build(d_seq, c->d_contigs, c->d_tiles + t0, t1 - t0, c->hp, c->d_image, nullptr, c->st);
     }
     cudaError_t e1 = cudaStreamSynchronize(c->st);
     if (!c->keep_fasta_buf) { c->fa_seq_buf.release(); c->fa_words_buf.release(); }   // one-off builds give the big scratch back
@@ -640,15 +670,58 @@ extern "C" int lhgt_hash_seq(lhgt_ctx* c, const uint8_t* ascii, size_t n, uint32
 }
 
 extern "C" uint64_t lhgt_index_bytes(const lhgt_ctx* c) { return c && c->index_ready ? c->image_words * 4 : 0; }
+
+extern "C" int lhgt_set_image_block(lhgt_ctx* c, int part, int parts) {
+    if (!c || parts < 1 || parts > kMaxPeers || part < 0 || part >= parts) return fail(LHGT_E_ARG, "lhgt_set_image_block: bad argument");
+    drop_index(c);
+    c->blk_part = part; c->blk_parts = parts;
+    return 0;
+}
+
+extern "C" int lhgt_index_block(const lhgt_ctx* c, uint64_t* byte_offset, uint64_t* bytes, long* tile_begin, long* tile_end) {
+    if (!c || !c->index_ready) return fail(LHGT_E_STATE, "no index resident");
+    if (byte_offset) *byte_offset = c->blk_word_lo * 4;
+    if (bytes) *bytes = (c->blk_word_hi - c->blk_word_lo) * 4;
+    if (tile_begin) *tile_begin = c->image_partial ? c->blk_tile_lo : 0;
+    if (tile_end) *tile_end = c->image_partial ? c->blk_tile_hi : (long)c->tiles.size();
+    return 0;
+}
+
+// this context's block written at its place in the index file (created if absent, never truncated: the ranks write side by side)
+extern "C" int lhgt_index_write_block(lhgt_ctx* c, const char* index_path) {
+    if (!c || !index_path) return fail(LHGT_E_ARG, "null pointer");
+    if (!c->index_ready) return fail(LHGT_E_STATE, "no index resident");
+    CU(cudaSetDevice(c->device));
+    int fd = open(index_path, O_WRONLY | O_CREAT, 0644);
+    if (fd < 0) return fail(LHGT_E_IO, "cannot create %s", index_path);
+    const size_t chunk = (size_t)64 << 20;
+    int rc = ring_ready(c);
+    uint64_t total = (c->blk_word_hi - c->blk_word_lo) * 4, done = 0;
+    const uint8_t* src = (const uint8_t*)(c->d_image + c->blk_word_lo);
+    while (!rc && done < total) {                                     // (a two-slot pipeline would overlap copy and write; IB output is a one-off)
+        size_t m = (size_t)std::min<uint64_t>(chunk, total - done);
+        if (cudaMemcpyAsync(c->ring[0], src + done, m, cudaMemcpyDeviceToHost, c->st) != cudaSuccess || cudaStreamSynchronize(c->st) != cudaSuccess) { rc = fail(LHGT_E_CUDA, "index download failed"); break; }
+        size_t w = 0;
+        while (w < m) {
+            ssize_t r = pwrite(fd, c->ring[0] + w, m - w, (off_t)(c->blk_word_lo * 4 + done + w));
+            if (r <= 0) { rc = fail(LHGT_E_IO, "short write on %s", index_path); break; }
+            w += (size_t)r;
+        }
+        done += m;
+    }
+    if (close(fd) != 0 && !rc) rc = fail(LHGT_E_IO, "close failed on %s", index_path);
+    return rc;
+}
 extern "C" uint64_t lhgt_index_bases(const lhgt_ctx* c) { return c ? c->index_bases : 0; }
 extern "C" long lhgt_index_contigs(const lhgt_ctx* c) { return c ? (long)c->contigs.size() : 0; }
 
 extern "C" int lhgt_index_download(lhgt_ctx* c, uint8_t* dst, uint64_t cap) {
     if (!c || !dst) return fail(LHGT_E_ARG, "null pointer");
     if (!c->index_ready) return fail(LHGT_E_STATE, "no index resident");
-    if (cap < c->image_words * 4) return fail(LHGT_E_ARG, "buffer too small for the index image");
+    uint64_t words = c->blk_word_hi - c->blk_word_lo;                   // the resident block (the whole image unless lhgt_set_image_block)
+    if (cap < words * 4) return fail(LHGT_E_ARG, "buffer too small for the index image");
     CU(cudaSetDevice(c->device));
-    CU(cudaMemcpyAsync(dst, c->d_image, c->image_words * 4, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(dst, c->d_image + c->blk_word_lo, words * 4, cudaMemcpyDeviceToHost, c->st));
     CU(cudaStreamSynchronize(c->st));
     return 0;
 }
@@ -661,6 +734,7 @@ extern "C" long lhgt_index_record(lhgt_ctx* c, long record, uint32_t* dst, uint6
     uint64_t words = 1 + (uint64_t)(g.len - c->k + 1) * c->e;
     if (!dst) return (long)words;
     if (cap_words < words) return fail(LHGT_E_ARG, "buffer too small for the index record");
+    if (g.hash_word - 1 < c->blk_word_lo || g.hash_word - 1 + words > c->blk_word_hi) return fail(LHGT_E_STATE, "record lies outside this context's image block");
     CU(cudaSetDevice(c->device));
     CU(cudaMemcpyAsync(dst, c->d_image + g.hash_word - 1, words * 4, cudaMemcpyDeviceToHost, c->st));
     CU(cudaStreamSynchronize(c->st));
@@ -830,7 +904,7 @@ static int file_size_of(const char* path, size_t* n) {
     return 0;
 }
 
-static int stream_file_to_device(lhgt_ctx* c, const char* path, uint8_t* d_dst, size_t n, std::vector<uint8_t>* tail) {
+static int stream_file_to_device(lhgt_ctx* c, const char* path, uint8_t* d_dst, size_t n, std::vector<uint8_t>* tail, size_t file_off = 0) {
     int rc = ring_ready(c);
     if (rc) return rc;
     int fd = open(path, O_RDONLY);
@@ -849,7 +923,7 @@ static int stream_file_to_device(lhgt_ctx* c, const char* path, uint8_t* d_dst, 
         if (cudaEventSynchronize(c->ring_free[slot]) != cudaSuccess) { rc = fail(LHGT_E_CUDA, "staging ring failed"); break; }   // its previous copy has left
         size_t got = 0;
         while (got < m) {
-            ssize_t r = pread(fd, c->ring[slot] + got, m - got, (off_t)(done + got));
+            ssize_t r = pread(fd, c->ring[slot] + got, m - got, (off_t)(file_off + done + got));
             if (r <= 0) break;
             got += (size_t)r;
         }
@@ -880,6 +954,10 @@ extern "C" int lhgt_index_build_file(lhgt_ctx* c, const char* fasta_path, const 
     rc = index_build_from_device(c, c->fasta_buf.p, n);
     if (!c->keep_fasta_buf) c->fasta_buf.release();
     if (rc) return rc;
+    if (c->blk_parts > 1) {                                               // every rank writes its block side by side; block 0 adds the text file
+        if ((rc = lhgt_index_write_block(c, index_path))) return rc;
+        return c->blk_part == 0 ? spill(len_path, c->len_text.data(), c->len_text.size()) : 0;
+    }
     // stream the image out through two pinned staging buffers
     FILE* f = fopen(index_path, "wb");
     if (!f) return fail(LHGT_E_IO, "cannot create %s", index_path);
@@ -948,8 +1026,11 @@ extern "C" int lhgt_index_load_file(lhgt_ctx* c, const char* index_path) {
         at += 1 + span;
     }
     close(fd);
-    if ((rc = alloc_image(c, nwords)) || (rc = stream_file_to_device(c, index_path, (uint8_t*)c->d_image, n, nullptr))) return rc;
-    return finish_index_tables(c);
+    if ((rc = finish_index_tables(c))) return rc;
+    if (c->blk_parts > 1) rc = alloc_image_block(c, nwords); else rc = alloc_image(c, nwords);
+    if (rc) return rc;
+    uint64_t bytes = (c->blk_word_hi - c->blk_word_lo) * 4;
+    return bytes ? stream_file_to_device(c, index_path, (uint8_t*)(c->d_image + c->blk_word_lo), bytes, nullptr, c->blk_word_lo * 4) : 0;
 }
 
 extern "C" int lhgt_reads_upload_file(lhgt_ctx* c, int mate, const char* path) {
@@ -1272,6 +1353,8 @@ extern "C" int lhgt_s2_gather(lhgt_ctx* c, long tile_begin, long tile_end) {
     long nt = (long)c->tiles.size();
     if (tile_end < 0 || tile_end > nt) tile_end = nt;
     if (tile_begin < 0 || tile_begin > tile_end) return fail(LHGT_E_ARG, "bad tile range");
+    if (c->image_partial && tile_end > tile_begin && (tile_begin < c->blk_tile_lo || tile_end > c->blk_tile_hi))
+        return fail(LHGT_E_STATE, "tiles [%ld, %ld) are outside this context's image block [%ld, %ld)", tile_begin, tile_end, c->blk_tile_lo, c->blk_tile_hi);
     CU(cudaSetDevice(c->device));
     Span sp(c, 2);
     // Tables far beyond L2 are gathered slice by slice (records bucketed by table slice, answered while the slice is
@@ -1371,6 +1454,8 @@ extern "C" int lhgt_s2_complete(lhgt_ctx* c, long tile_begin, long tile_end) {
     long nt = (long)c->tiles.size();
     if (tile_end < 0 || tile_end > nt) tile_end = nt;
     if (tile_begin < 0 || tile_begin > tile_end) return fail(LHGT_E_ARG, "bad tile range");
+    if (c->image_partial && !c->single_exact && tile_end > tile_begin && (tile_begin < c->blk_tile_lo || tile_end > c->blk_tile_hi))
+        return fail(LHGT_E_STATE, "tiles [%ld, %ld) are outside this context's image block", tile_begin, tile_end);
     CU(cudaSetDevice(c->device));
     if (c->single_exact) return 0;                                   // the sliced gather answered every hash
     Span sp(c, 2);
@@ -1386,7 +1471,7 @@ static int clear_peak_tables(lhgt_ctx* c) {
         // one (cfg3: half of a 1 Gbp reference flagged) is cheaper to clear.
         double unwrite_s = (double)c->n_flagged * c->e * 50e-12;
         double clear_s = ((double)(1ull << c->k) * 4 + (double)kFilterWords * 4) / 5e12;
-        if (unwrite_s <= clear_s) {
+        if (unwrite_s <= clear_s && !c->image_partial) {
             c->launches += launch_s2_register(c->d_image, c->d_contigs, c->d_tiles, c->need_buf.p, c->d_misc + MISC_NEED, 0, c->tiles.size(), c->hp, c->d_count,
                                               c->d_flagged, c->d_tile_base, c->d_loci, 0u, c->d_peak_kmer, c->d_prefilter, 1, c->st);
         } else {
@@ -1489,6 +1574,7 @@ extern "C" int lhgt_s2_ids(lhgt_ctx* c, long max_peak, long flagged_total, long*
     // the S3 pre-filter only pays while it is sparse (2^28 bits against the registered k-mers): a dense result skips it
     const char* dr = getenv("LHGT_DENSE_RECORDS");                    // test knob: the registered-k-mer count from which a result is "dense"
     c->filter_on = (double)c->n_flagged * c->e < (dr ? atof(dr) : 0.7 * (double)(1u << kFilterLog2));
+    if (c->image_partial) c->filter_on = false;                     // a rank registers its image block only: the peak tables are MAX-combined, a bit filter cannot be
     c->n_peaks = total;
     if (n_peaks) *n_peaks = total;
     return 0;
@@ -1504,6 +1590,8 @@ extern "C" int lhgt_s2_register(lhgt_ctx* c, long tile_begin, long tile_end) {
     if (tile_begin < 0 || tile_begin > tile_end) return fail(LHGT_E_ARG, "bad tile range");
     long total = c->n_peaks;
     if (total <= 0 || tile_end == tile_begin) return 0;
+    if (c->image_partial && (tile_begin < c->blk_tile_lo || tile_end > c->blk_tile_hi))
+        return fail(LHGT_E_STATE, "tiles [%ld, %ld) are outside this context's image block", tile_begin, tile_end);
     const uint32_t* need = c->need_buf.p; const uint32_t* n_need = c->d_misc + MISC_NEED;
     uint64_t t_lo = (uint64_t)tile_begin, t_hi = (uint64_t)tile_end;
     Span sp(c, 10);

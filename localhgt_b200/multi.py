@@ -291,6 +291,10 @@ class Shard:
         if w > 1 and eng.sharded_s2:
             nt = eng.s2_tiles()
             _, lo, hi = self.tile_block(nt)
+            blk = eng.index_block() if hasattr(eng, "index_block") else None
+            partial = blk is not None and (blk[2], blk[3]) != (0, nt)      # this rank holds one block of the image only (row e-S)
+            if partial and (blk[2], blk[3]) != (lo, hi):
+                raise ValueError("image block and tile block differ: build the index with set_image_block(rank, world)")
             eng.s2_gather(lo, hi)
             t = lap("s2_gather", t)
             ev = self._span("exchange_hit_bits")
@@ -317,7 +321,23 @@ class Shard:
             flagged_total = sum(r[0] for r in self._all_gather_ints([eng.s2_flagged_in_range()]))
             n_peaks = eng.s2_ids(max_peak, flagged_total)
             t = lap("s2_windows", t)
-            if n_peaks > 0 and eng.s2_dense():
+            if n_peaks > 0 and partial:
+                # the hashes of a tile live on one rank only: flagged bits go to everybody, every rank registers its image block,
+                # the tables are combined with MAX
+                ev = self._span("exchange_flagged")
+                self._engine_done()
+                fl = eng.flagged()
+                self.dist.all_reduce(fl, op=self.dist.ReduceOp.MAX)
+                self._fence(fl)
+                self._end(ev)
+                eng.s2_register(lo, hi)
+                ev = self._span("reduce_peak_table")
+                self._engine_done()
+                for buf in (eng.peak_table(), eng.loci()):
+                    self.dist.all_reduce(buf, op=self.dist.ReduceOp.MAX)
+                    self._fence(buf)
+                self._end(ev)
+            elif n_peaks > 0 and eng.s2_dense():
                 # many registered k-mers: each rank registers its share, the tables are combined with MAX (= the last writer of
                 # the sequential loop, since ids grow with position)
                 eng.s2_register(wlo, whi)

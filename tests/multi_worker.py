@@ -62,7 +62,12 @@ def main():
     with torch.cuda.stream(stream), api.Screen(k, e, device=local) as s:
         s.set_stream(stream.cuda_stream)
         s.set_coder(cc)
+        if os.environ.get("LHGT_TEST_BLOCKS"):                 # every rank keeps one block of the image only (row e-S)
+            s.set_image_block(rank, world)
         s.index_build(open(fa, "rb").read())
+        if os.environ.get("LHGT_TEST_BLOCKS"):
+            off, nbytes, t0, t1 = s.index_block()
+            assert world == 1 or nbytes < s.index_bytes()
         if os.environ.get("LHGT_TEST_S1_MODE"):
             s.set_s1_mode(int(os.environ["LHGT_TEST_S1_MODE"]))
         shard = multi.Shard(s, rank, world, dist, torch, same_stream=True, force_nccl=(form == "nccl"))

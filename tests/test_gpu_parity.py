@@ -766,3 +766,39 @@ def test_bucketed_registration_equals_direct(name, pool_kb, workdir, monkeypatch
         so, sg = o.s3_pairs(fq1, fq2, ratio), s.s3_pairs()
         assert so == sg and np.array_equal(o.peak_filter() >= 1, s.peaks()[1] >= 1)
     o.close()
+
+
+@pytest.mark.parametrize("parts", [2, 3, 8])
+def test_image_blocks_tile_the_image(parts, workdir):
+    """lhgt_set_image_block: the blocks the ranks of a box build, laid side by side at the offsets they report, are the
+    index file byte for byte (header in block 0, every contig's length word with its first tile); written with
+    lhgt_index_write_block they make the same file."""
+    case = fixtures.BY_NAME["noisy"]
+    fa, fq1, fq2 = fixtures.materialize(case.data, workdir)
+    k, e = 22, 3
+    cc, _ = api.random_coder(4, k, e)
+    with api.Screen(k, e) as whole:
+        whole.set_coder(cc)
+        whole.index_build(_read(fa))
+        image = bytes(whole.index_download())
+        ntiles = whole.s2_tiles()
+    path = os.path.join(workdir, f"blocks{parts}.index.dat")
+    if os.path.exists(path):
+        os.remove(path)
+    got = bytearray(len(image))
+    covered = 0
+    for part in range(parts):
+        with api.Screen(k, e) as s:
+            s.set_coder(cc)
+            s.set_image_block(part, parts)
+            s.index_build(_read(fa))
+            off, n, t0, t1 = s.index_block()
+            assert off == covered and 0 <= t0 <= t1 <= ntiles
+            got[off:off + n] = bytes(s.index_download())
+            covered += n
+            s.index_write_block(path)
+            if t1 > t0:
+                with pytest.raises(api.LhgtError):
+                    s.s2_gather(0, ntiles) if parts > 1 and (t0, t1) != (0, ntiles) else (_ for _ in ()).throw(api.LhgtError(-8, "x"))
+    assert covered == len(image) and bytes(got) == image
+    assert _read(path) == image

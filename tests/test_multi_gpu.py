@@ -50,6 +50,14 @@ def test_two_gpus_dense_plan(case, tmp_path):
     _run(2, str(tmp_path), case, "p2p", env={"LHGT_DENSE_RECORDS": "1000"})
 
 
+@pytest.mark.skipif(N_GPUS < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("case", ["base_k24", "noisy", "base_k20"])
+def test_two_gpus_image_blocks(case, tmp_path):
+    """Images larger than one GPU: every rank builds and keeps ONE block of the index image; hit bits, flagged bits and peak
+    tables are exchanged so that no rank needs another rank's hashes.  Same answer as the oracle over the whole files."""
+    _run(2, str(tmp_path), case, "p2p", env={"LHGT_TEST_BLOCKS": "1"})
+
+
 @pytest.mark.skipif(N_GPUS < 3, reason="needs 3 GPUs")
 @pytest.mark.parametrize("form", ["p2p", "nccl"])
 def test_three_gpus_uneven_slices(form, tmp_path):
