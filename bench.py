@@ -59,6 +59,7 @@ WORKLOADS = {
     "cfg2": (40, 2_000_000, 5_000_000, 40),
     "cfg3": (500, 2_000_000, 10_000_000, 200),                          # BASELINE.json configs[2]
     "cfg4": (2000, 2_500_000, 30_000_000, 400),                         # BASELINE.json configs[3]: the headline
+    "cfg5": (4000, 2_500_000, 10_000_000, 400),                         # BASELINE.json configs[4]: 10 Gbp, e = 1..4 sweep, image in blocks
     "mini": (20, 2_500_000, 300_000, 4),
     "small": (8, 500_000, 200_000, 6),
 }
@@ -114,7 +115,7 @@ def spec_of(name: str, scale: int = 1):
     from localhgt_b200 import synth_dev
     n_genomes, genome_len, n_pairs, n_events = WORKLOADS[name]
     return synth_dev.Spec(name if scale == 1 else f"{name}/{scale}", max(4, n_genomes // scale), genome_len, max(1000, n_pairs // scale),
-                          max(2, n_events // scale), seed={"cfg3": 3, "cfg4": 4, "mini": 4}.get(name, 9))
+                          max(2, n_events // scale), seed={"cfg3": 3, "cfg4": 4, "mini": 4, "cfg5": 5}.get(name, 9))
 
 
 class Workload:
@@ -459,11 +460,26 @@ def ours(args) -> None:
     torch.cuda.empty_cache()
     gen_s = time.perf_counter() - t_setup
 
+    blocks = world > 1 and (args.image_blocks or args.workload == "cfg5")    # every rank keeps one block of the index image (row e-S)
+    sweep = index_sweep(args, api, torch, dist, d_fa, wl, rank, local_rank, world) if args.workload == "cfg5" else None
+    image_gb = wl.ref_bases * 4 * E / 1e9 / (world if blocks else 1)
+    if image_gb > 100:
+        if rank == 0:
+            print(json.dumps({"metric": "read pairs/sec through k-mer screen+peak extract", "value": None, "unit": "pairs/s", "n_gpus": world,
+                              "config": config_dict(args.workload), "index_sweep": sweep,
+                              "skipped": f"a {image_gb:.0f} GB index image per GPU does not fit beside the tables and the sample: run {args.workload} "
+                                         f"with --gpus >= 2 (the image is then kept in blocks, one per GPU)"}))
+        if dist:
+            dist.destroy_process_group()
+        return
+
     stream = torch.cuda.Stream()
     scr = api.Screen(K, E, device=local_rank)
     cc, skip = api.random_coder(SEED, K, E)
     scr.set_coder(cc)
     scr.set_s1_mode(args.s1_mode)
+    if blocks:
+        scr.set_image_block(rank, world)
     size1_total = wl.n_pairs * wl.stride                                   # E:1419: size(fq1) of the whole sample (Q15 budget)
 
     with torch.cuda.stream(stream):
@@ -497,7 +513,7 @@ def ours(args) -> None:
         text_whole = None
         if world > 1:
             text_sharded = step_resident()
-            if rank == 0 and not args.no_whole_check:
+            if rank == 0 and not args.no_whole_check and not blocks:
                 w1, w2 = wl.reads_dev(0, wl.n_pairs)
                 scr.reads_attach_device(0, w1.data_ptr(), w1.numel()); scr.reads_attach_device(1, w2.data_ptr(), w2.numel())
                 text_whole = solo.screen(size1=w1.numel(), sample_arg=SAMPLE, seed=SEED, rand_skip=0, hit=HIT, match=MATCH, max_peak=MAX_PEAK)
@@ -603,6 +619,7 @@ def ours(args) -> None:
         "parallelism": {"plan": f"one sample split {world} ways by record ranges, index replicated" if world > 1 else "1 GPU",
                         "count_exchange": ("one kernel over NVLink peer memory (CUDA IPC)" if shard.p2p else "NCCL all-to-all + merge + all-gather")
                         if world > 1 else "none",
+                        "index_image": (f"in {world} blocks, one per GPU ({image_gb:.1f} GB each)" if blocks else "replicated" if world > 1 else "whole"),
                         "whole_sample_check": ("rank 0 screened the whole sample alone: identical text" if text_whole is not None else
                                                "skipped" if world > 1 else "n/a")},
         "sampled_pairs_per_s": {"value": frac * value, "e2e": frac * e2e_value, "sampled_fraction": frac},
@@ -623,6 +640,8 @@ def ours(args) -> None:
         "host_wall_ms_last_resident_step": {k: round(v, 3) for k, v in wall_resident.items()},
         "setup_seconds": {"generate_inputs": round(gen_s, 2)},
     }
+    if sweep:
+        line["index_sweep"] = sweep
     if world == 1 and not args.no_cpu:
         try:
             line["cpu_baseline"] = cpu_baseline(args, scr)
@@ -633,6 +652,46 @@ def ours(args) -> None:
     print(json.dumps(line))
     if dist:
         dist.destroy_process_group()
+
+
+def index_sweep(args, api, torch, dist, d_fa, wl, rank, local_rank, world):
+    """BASELINE.json configs[4]: index build over the 10 Gbp reference for e = 1..4, the image kept in `world` blocks (one per
+    GPU).  Per e: best of 3 builds, device time of the hashing kernel and wall time of lhgt_index_build_device, max over ranks."""
+    out = []
+    peak, _ = measured_peak_gbs()
+    for e in (1, 2, 3, 4):
+        gb = wl.ref_bases * 4 * e / 1e9 / world
+        if gb > 120:
+            out.append({"e": e, "skipped": f"{gb:.0f} GB of image per GPU: needs more GPUs"})
+            continue
+        scr = api.Screen(K, e, device=local_rank)
+        cc, _ = api.random_coder(SEED, K, e)
+        scr.set_coder(cc)
+        if world > 1:
+            scr.set_image_block(rank, world)
+        kern, wall = [], []
+        for _ in range(3):
+            if dist:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            scr.index_build_device(d_fa.data_ptr(), d_fa.numel())
+            scr.sync()
+            wall.append(1000 * (time.perf_counter() - t))
+            kern.append(float(scr.stage_ms()[5]))
+        k_ms, w_ms = min(kern), min(wall)
+        if dist:
+            tt = torch.tensor([k_ms, w_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            k_ms, w_ms = float(tt[0]), float(tt[1])
+        bases, image_bytes = scr.index_bases(), scr.index_bytes()
+        scr.close()
+        torch.cuda.empty_cache()
+        out.append({"e": e, "index_bytes": int(image_bytes), "image_gb_per_gpu": round(gb, 1), "kernel_ms": k_ms, "gbp_per_s": bases / 1e6 / k_ms,
+                    "device_ms": w_ms, "device_gbp_per_s": bases / 1e6 / w_ms,
+                    "roofline": {"bytes_per_base": 1 + 4 * e, "achieved_gbs_per_gpu": bases * (1 + 4 * e) / 1e6 / k_ms / world,
+                                 "frac": bases * (1 + 4 * e) / 1e6 / k_ms / world / peak}})
+    return out
 
 
 def make_roofline(stage, wl, frac, world, peak, peak_src, fastq_bytes):
@@ -746,6 +805,7 @@ def main():
     ap.add_argument("--ref-pairs", type=int, default=0, help="pairs in the CPU reference's bounded sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-whole-check", action="store_true", help="N > 1: skip rank 0's single-GPU screen of the whole sample")
+    ap.add_argument("--image-blocks", action="store_true", help="N > 1: every GPU keeps one block of the index image instead of a replica (cfg5 always does)")
     ap.add_argument("--s1-mode", type=int, default=0, help="0 auto (hash streams for tables > 64 MiB), 1 direct probes, 2 streams")
     args = ap.parse_args()
     _, _, world = _rank_env()
