@@ -1606,18 +1606,21 @@ extern "C" int lhgt_s2_register(lhgt_ctx* c, long tile_begin, long tile_end) {
     if (bucketed && it_hi > it_lo) {
         // record regions: the S1 stream pools when there are (idle now), else a buffer of our own
         const char* kb = getenv("LHGT_REG_POOL_KB");                 // test knob: small regions force chunks and overflow
-        uint2* pool = nullptr; uint64_t pool_records = 0;
-        if (!kb && c->d_bin_pool_b && c->bin_pool_b_entries / 2 >= ((uint64_t)32 << 20)) { pool = (uint2*)c->d_bin_pool_b; pool_records = c->bin_pool_b_entries / 2; }
-        else {
+        uint2 *pool_lo = nullptr, *pool_hi = nullptr; uint64_t half_records = 0;     // half of the buckets live in each
+        if (!kb && c->d_bin_pool_a && c->d_bin_pool_b && std::min(c->bin_pool_a_entries, c->bin_pool_b_entries) / 2 >= ((uint64_t)32 << 20)) {
+            pool_lo = (uint2*)c->d_bin_pool_a; pool_hi = (uint2*)c->d_bin_pool_b;
+            half_records = std::min(c->bin_pool_a_entries, c->bin_pool_b_entries) / 2;
+        } else {
             uint64_t want = kb ? std::max<uint64_t>(((uint64_t)atol(kb) << 10) / 8, (uint64_t)s2_reg_buckets() * 4)
                                : std::min<uint64_t>((uint64_t)(records * 1.25) + (uint64_t)s2_reg_buckets() * 1024, (uint64_t)64 << 20);
+            want = (want + 1) & ~(uint64_t)1;
             int rc = c->reg_pool_buf.reserve(want);
             if (rc) return rc;
-            pool = c->reg_pool_buf.p; pool_records = want;
+            pool_lo = c->reg_pool_buf.p; pool_hi = c->reg_pool_buf.p + want / 2; half_records = want / 2;
         }
         int rc = c->reg_cursor_buf.reserve((size_t)s2_reg_cursor_words());
         if (rc) return rc;
-        uint32_t cap = (uint32_t)std::min<uint64_t>(pool_records / (uint64_t)s2_reg_buckets(), 0xfffffff0u);
+        uint32_t cap = (uint32_t)std::min<uint64_t>(half_records / (uint64_t)(s2_reg_buckets() / 2), 0xfffffff0u);
         // the list is walked in chunks whose records fit the regions (records per needed tile, on average)
         double per_tile = std::max(1.0, records / (double)(it_hi - it_lo));
         uint32_t chunk = (uint32_t)std::max(1.0, std::min((double)(it_hi - it_lo), 0.85 * (double)cap * s2_reg_buckets() / per_tile));
@@ -1625,7 +1628,7 @@ extern "C" int lhgt_s2_register(lhgt_ctx* c, long tile_begin, long tile_end) {
             CU(cudaMemsetAsync(c->reg_cursor_buf.p, 0, (size_t)s2_reg_cursor_words() * 4, c->st));
             int nl = launch_s2_register_bucketed(c->d_image, c->d_contigs, c->d_tiles, need, n_need, lo, std::min(it_hi, lo + chunk), t_lo, t_hi, c->hp,
                                                  c->d_count, c->d_flagged, c->d_tile_base, c->d_loci, loci_cap, c->d_peak_kmer, prefilter,
-                                                 pool, c->reg_cursor_buf.p, cap, c->st);
+                                                 pool_lo, pool_hi, c->reg_cursor_buf.p, cap, c->st);
             if (nl < 0) return fail(LHGT_E_CUDA, "registration kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             c->launches += nl;
         }

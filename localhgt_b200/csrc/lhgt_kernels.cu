@@ -1807,12 +1807,13 @@ int launch_s2_gather_combine(const uint32_t* sat, size_t plane_words, int e, uin
 // 1/512 of both tables (32 MiB and 2 MiB at k = 32), so while it is being applied the scatter-max and the count > 0 test
 // (E:250,265) run against L2, not DRAM.
 // ------------------------------------------------------------------------------------------------
-constexpr int kRegBuckets = 512, kRegStage = 24, kRegFlushMin = 8;
+constexpr int kRegBuckets = 512, kRegStage = 16, kRegFlushMin = 4;    // 66 KiB of stage per CTA: three CTAs per SM (24 / 8 gave two: 25 % warps active, profiles/r02g)
 constexpr int kRegCursorStride = 32;                           // words between bucket cursors (own 128-byte line each)
 
 struct RegSink {
-    uint2* pool; uint32_t* cursor; uint32_t cap;               // bucket b occupies pool[b * cap .. +cap); cursor[b * kRegCursorStride]
-    int shift;                                                 // bucket of table index g = g >> shift (its top 9 bits)
+    uint2* pool[2]; uint32_t* cursor; uint32_t cap;            // bucket b occupies pool[b >> 8][(b & 255) * cap .. +cap) (two pools: the two S1
+    int shift;                                                 // stream pools, both idle now); cursor[b * kRegCursorStride]; bucket = g >> shift
+    __device__ __forceinline__ uint2* region(uint32_t b) const { return pool[b >> 8] + (size_t)(b & 255u) * cap; }
 };
 
 // record = (table index g, peak id)
@@ -1824,7 +1825,7 @@ __device__ __forceinline__ void reg_apply_one(uint32_t g, uint32_t id, const uin
 }
 
 template <int E>
-__global__ void __launch_bounds__(256, 2) s2_regemit_kernel(const uint32_t* __restrict__ image, const Contig* __restrict__ contigs,
+__global__ void __launch_bounds__(256, 3) s2_regemit_kernel(const uint32_t* __restrict__ image, const Contig* __restrict__ contigs,
                                                             const Tile* __restrict__ tiles, const uint32_t* __restrict__ need_list,
                                                             const uint32_t* __restrict__ n_need, uint32_t it_lo, uint32_t it_hi,
                                                             uint64_t t_lo, uint64_t t_hi, HashP hp,
@@ -1842,7 +1843,7 @@ __global__ void __launch_bounds__(256, 2) s2_regemit_kernel(const uint32_t* __re
     const uint32_t hi = min(it_hi, *n_need);
     auto direct = [&](uint32_t b, uint2 r) {                     // past a stage or a bucket region: rare, exact either way
         uint32_t g = atomicAdd(sink.cursor + b * kRegCursorStride, 1u);
-        if (g < sink.cap) sink.pool[(size_t)b * sink.cap + g] = r;
+        if (g < sink.cap) sink.region(b)[g] = r;
         else reg_apply_one(r.x, r.y, count, peak_kmer, prefilter);
     };
     // A warp hands over its share of the buckets, 32 at a time: lane l looks at bucket base + l, the reservations are one
@@ -1863,7 +1864,7 @@ __global__ void __launch_bounds__(256, 2) s2_regemit_kernel(const uint32_t* __re
                 int bb = base + src;
                 if ((uint32_t)lane < nb) {
                     uint2 r = stage[bb * kRegStage + lane];
-                    if (gb + lane < sink.cap) sink.pool[(size_t)bb * sink.cap + gb + lane] = r;
+                    if (gb + lane < sink.cap) sink.region(bb)[gb + lane] = r;
                     else reg_apply_one(r.x, r.y, count, peak_kmer, prefilter);
                 }
             }
@@ -1929,7 +1930,7 @@ __global__ void __launch_bounds__(256, 4) s2_regapply_kernel(RegSink sink, const
                                                              uint32_t* __restrict__ peak_kmer, uint32_t* __restrict__ prefilter) {
     const uint32_t b = blockIdx.y;
     const uint32_t n = min(sink.cursor[b * kRegCursorStride], sink.cap);
-    const uint2* __restrict__ in = sink.pool + (size_t)b * sink.cap;
+    const uint2* __restrict__ in = sink.region(b);
     for (uint32_t x = blockIdx.x * 256 + threadIdx.x; x < n; x += gridDim.x * 256) {
         uint2 r;
         asm volatile("ld.global.cs.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(in + x));   // evict-first: the table slices are what L2 is for
@@ -1945,11 +1946,11 @@ int s2_reg_cursor_words() { return kRegBuckets * kRegCursorStride; }
 int launch_s2_register_bucketed(const uint32_t* image, const Contig* contigs, const Tile* tiles, const uint32_t* need_list,
                                 const uint32_t* n_need, uint32_t it_lo, uint32_t it_hi, uint64_t t_lo, uint64_t t_hi, const HashP& hp, const uint32_t* count,
                                 const uint32_t* flagged, const uint32_t* tile_base, int32_t* loci, uint32_t loci_cap, uint32_t* peak_kmer,
-                                uint32_t* prefilter, uint2* pool, uint32_t* cursor, uint32_t cap, cudaStream_t st) {
+                                uint32_t* prefilter, uint2* pool_lo, uint2* pool_hi, uint32_t* cursor, uint32_t cap, cudaStream_t st) {
     if (it_hi <= it_lo) return 0;
-    RegSink sink{pool, cursor, cap, hp.k > 9 ? hp.k - 9 : 0};
+    RegSink sink{{pool_lo, pool_hi}, cursor, cap, hp.k > 9 ? hp.k - 9 : 0};
     size_t smem = s2_regemit_smem();
-    unsigned grid = it_hi - it_lo < (uint32_t)kSMs * 2 ? it_hi - it_lo : (uint32_t)kSMs * 2;
+    unsigned grid = it_hi - it_lo < (uint32_t)kSMs * 3 ? it_hi - it_lo : (uint32_t)kSMs * 3;
 #define LHGT_REGEMIT(EE)                                                                                                        \
     do {                                                                                                                        \
         if (cudaFuncSetAttribute(s2_regemit_kernel<EE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) \

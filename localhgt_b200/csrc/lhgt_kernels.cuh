@@ -171,7 +171,7 @@ int launch_s2_gather_combine(const uint32_t* sat, size_t plane_words, int e, uin
                              uint32_t* trio, cudaStream_t st);
 
 // Registration through buckets, one chunk [it_lo, it_hi) of the needed-tile list: (hash, id) records are appended to
-// s2_reg_buckets() regions of `cap` records each in `pool` (cursor: s2_reg_cursor_words() zeroed words) and applied bucket by
+// s2_reg_buckets() regions of `cap` records each, the first half of them in pool_lo, the second in pool_hi (cursor: s2_reg_cursor_words() zeroed words) and applied bucket by
 // bucket against L2-resident slices of the tables.  Whatever does not fit is applied directly: exact either way.
 size_t s2_regemit_smem();
 int s2_reg_buckets();
@@ -179,7 +179,7 @@ int s2_reg_cursor_words();
 int launch_s2_register_bucketed(const uint32_t* image, const Contig* contigs, const Tile* tiles, const uint32_t* need_list,
                                 const uint32_t* n_need, uint32_t it_lo, uint32_t it_hi, uint64_t t_lo, uint64_t t_hi, const HashP& hp, const uint32_t* count,
                                 const uint32_t* flagged, const uint32_t* tile_base, int32_t* loci, uint32_t loci_cap, uint32_t* peak_kmer,
-                                uint32_t* prefilter, uint2* pool, uint32_t* cursor, uint32_t cap, cudaStream_t st);
+                                uint32_t* prefilter, uint2* pool_lo, uint2* pool_hi, uint32_t* cursor, uint32_t cap, cudaStream_t st);
 
 // kept peaks (filter != 0) in id order: phase 0 counts per 1024-peak block and scans (block_cnt / block_base: peaks_keep_blocks(n)
 // words, scan_tmp: scan_tmp_words of that), phase 1 writes (contig, position) pairs into `out`
