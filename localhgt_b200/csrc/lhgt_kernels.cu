@@ -1857,20 +1857,30 @@ __global__ void __launch_bounds__(256, 3) s2_regemit_kernel(const uint32_t* __re
             uint32_t g = go ? atomicAdd(sink.cursor + b * kRegCursorStride, n) : 0u;
             if (go) cnt[b] = 0; else cnt[b] = n;
             uint32_t m = __ballot_sync(kFull, go);
+            // four flushing buckets per step, eight lanes each (a run is at most 16 records: two stores per lane): with ~6
+            // records arriving per bucket per tile nearly every bucket flushes every round, and one bucket per step made
+            // this loop most of the kernel's instructions (profiles/r02g_s2_regemit_kernel.md)
+            const int grp = lane >> 3, sub = lane & 7;
             while (m) {
-                int src = __ffs(m) - 1;
-                m &= m - 1;
+                uint32_t pos = __fns(m, 0, grp + 1);              // the (grp+1)-th flushing bucket of the group, 0xffffffff if none
+                int src = pos < 32u ? (int)pos : 0;
                 uint32_t nb = __shfl_sync(kFull, n, src), gb = __shfl_sync(kFull, g, src);
-                int bb = base + src;
-                if ((uint32_t)lane < nb) {
-                    uint2 r = stage[bb * kRegStage + lane];
-                    if (gb + lane < sink.cap) sink.region(bb)[gb + lane] = r;
-                    else reg_apply_one(r.x, r.y, count, peak_kmer, prefilter);
+                if (pos < 32u) {
+                    int bb = base + src;
+#pragma unroll
+                    for (int q = sub; q < kRegStage; q += 8)
+                        if ((uint32_t)q < nb) {
+                            uint2 r = stage[bb * kRegStage + q];
+                            if (gb + q < sink.cap) sink.region(bb)[gb + q] = r;
+                            else reg_apply_one(r.x, r.y, count, peak_kmer, prefilter);
+                        }
                 }
+                // drop the (up to) four lowest set bits
+                m &= m - 1; m &= m - 1; m &= m - 1; m &= m - 1;
             }
         }
     };
-    static_assert(kRegStage <= 32, "a run is written by one warp instruction");
+    static_assert(kRegStage <= 16, "a run is written by eight lanes, two records each");
     for (uint32_t it = it_lo + blockIdx.x; it < hi; it += gridDim.x) {
         const uint64_t tix = need_list[it];
         if (tix < t_lo || tix >= t_hi) continue;
