@@ -2263,6 +2263,44 @@ __device__ __forceinline__ bool s3_vote_warp(const uint32_t* cands, const int32_
     return true;
 }
 
+// Can this pair's vote mark anything?  check_split (E:161-202) needs TWO contigs with >= 6 votes, and a contig cannot get
+// more votes than the positions at which it is a candidate.  So: take the contig c* most common among 32 sampled
+// candidates, count its candidates exactly, and count the others in 256 hashed 16-bit slots (a slot may merge contigs:
+// an upper bound); unless [c* has >= 6] + sum over slots of floor(count / 6) reaches 2 the vote cannot have two such
+// contigs and is skipped.  Exact (a necessary condition), and in a dense result -- where every position of every pair
+// holds candidates, nearly all of them of the read's own genome plus scattered collisions -- it spares almost every
+// pair the serial vote and the trip through the arena.
+constexpr int kMaySlots = 256;
+__device__ __forceinline__ bool s3_may_split(const int32_t* __restrict__ cont, int n_entries, uint32_t* __restrict__ tw /* kMaySlots / 2 words */, int lane) {
+    for (int x = lane; x < kMaySlots / 2; x += 32) tw[x] = 0u;
+    int probe = __ldcg(cont + (int)(((long)lane * n_entries) >> 5));               // 32 evenly spaced entries (some are 0 = no candidate)
+    uint32_t same = __match_any_sync(kFull, probe);
+    int votes = probe ? __popc(same) : 0, best = votes;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) best = max(best, __shfl_xor_sync(kFull, best, d));
+    uint32_t who = __ballot_sync(kFull, votes == best && probe != 0);
+    if (!who) return false;                                                          // (no candidate among the samples: cannot happen with n_listed >= 6 ... but then nothing to vote on either way)
+    const int cstar = __shfl_sync(kFull, probe, __ffs(who) - 1);
+    __syncwarp();
+    int mine = 0;
+    for (int x = lane; x < n_entries; x += 32) {
+        int c = __ldcg(cont + x);
+        if (c == cstar) ++mine;
+        else if (c) {
+            uint32_t slot = ((uint32_t)c * 2654435761u) >> 24;                       // 8 bits
+            atomicAdd(tw + (slot >> 1), 1u << ((slot & 1u) * 16));                   // < 2^16 candidates per pair: no carry into the neighbour
+        }
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) mine += __shfl_xor_sync(kFull, mine, d);
+    __syncwarp();
+    int potential = 0;
+    for (int x = lane; x < kMaySlots / 2; x += 32) { uint32_t w = tw[x]; potential += (int)((w & 0xffffu) / 6u) + (int)((w >> 16) / 6u); }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) potential += __shfl_xor_sync(kFull, potential, d);
+    return (mine >= 6 ? 1 : 0) + potential >= 2;
+}
+
 struct PairOff { uint64_t a0, b0; uint32_t l1, l2; bool ok; };
 
 // One warp per pair, two pairs ahead: while a pair is voted on, the TMA unit is staging the bytes of the next sampled
@@ -2280,6 +2318,7 @@ __global__ void __launch_bounds__(kS3Warps * 32, LHGT_S3_CTAS) s3_pairs_kernel(
     __shared__ uint8_t lut[256];
     __shared__ __align__(16) uint8_t stage[kS3Warps][4][kStageBytes];
     __shared__ __align__(8) uint64_t sbar[kS3Warps][2];        // "pair staged", one per slot pair
+    __shared__ uint32_t may_tw[kS3Warps][kMaySlots / 2];       // s3_may_split's slots
     const int e = E ? E : hp.e;
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) { mbar_init(&sbar[warp][0], 1); mbar_init(&sbar[warp][1], 1); }
@@ -2342,7 +2381,7 @@ __global__ void __launch_bounds__(kS3Warps * 32, LHGT_S3_CTAS) s3_pairs_kernel(
         uint32_t m1 = (uint32_t)cur.a0 & 15u, m2 = (uint32_t)cur.b0 & 15u;
         int n_listed = s3_scan_mate<E>(stage[warp][2 * slot] + m1, (int)cur.l1, lut, hp, prefilter, peak_kmer, contig_first, n_contigs, cands, cont, 0, lane);
         n_listed = s3_scan_mate<E>(stage[warp][2 * slot + 1] + m2, (int)cur.l2, lut, hp, prefilter, peak_kmer, contig_first, n_contigs, cands, cont, n_listed, lane);
-        if (n_listed >= 6) {                                 // base_hits >= MIN_BASE_NUM (E:496)
+        if (n_listed >= 6 && (__syncwarp(), s3_may_split(cont, n_listed * e, may_tw[warp], lane))) {   // base_hits >= MIN_BASE_NUM (E:496)
             __syncwarp();
             // The order-dependent vote is handed to s3_vote_kernel (one THREAD per pair, 32 pairs per warp in flight): the
             // pair's candidates move to the arena and the pair joins the queue.  When either is full the warp votes itself.
