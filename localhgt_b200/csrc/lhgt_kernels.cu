@@ -2265,12 +2265,12 @@ __device__ __forceinline__ bool s3_vote_warp(const uint32_t* cands, const int32_
 
 // Can this pair's vote mark anything?  check_split (E:161-202) needs TWO contigs with >= 6 votes, and a contig cannot get
 // more votes than the positions at which it is a candidate.  So: take the contig c* most common among 32 sampled
-// candidates, count its candidates exactly, and count the others in 256 hashed 16-bit slots (a slot may merge contigs:
+// candidates, count its candidates exactly, and count the others in 2048 hashed 16-bit slots (a slot may merge contigs:
 // an upper bound); unless [c* has >= 6] + sum over slots of floor(count / 6) reaches 2 the vote cannot have two such
 // contigs and is skipped.  Exact (a necessary condition), and in a dense result -- where every position of every pair
 // holds candidates, nearly all of them of the read's own genome plus scattered collisions -- it spares almost every
 // pair the serial vote and the trip through the arena.
-constexpr int kMaySlots = 256;
+constexpr int kMaySlots = 2048;                                // (256 slots let cfg4's ~500 collision candidates per pair fake a second contig in every pair)
 __device__ __forceinline__ bool s3_may_split(const int32_t* __restrict__ cont, int n_entries, uint32_t* __restrict__ tw /* kMaySlots / 2 words */, int lane) {
     for (int x = lane; x < kMaySlots / 2; x += 32) tw[x] = 0u;
     int probe = __ldcg(cont + (int)(((long)lane * n_entries) >> 5));               // 32 evenly spaced entries (some are 0 = no candidate)
@@ -2287,7 +2287,7 @@ __device__ __forceinline__ bool s3_may_split(const int32_t* __restrict__ cont, i
         int c = __ldcg(cont + x);
         if (c == cstar) ++mine;
         else if (c) {
-            uint32_t slot = ((uint32_t)c * 2654435761u) >> 24;                       // 8 bits
+            uint32_t slot = ((uint32_t)c * 2654435761u) >> 21;                       // 11 bits
             atomicAdd(tw + (slot >> 1), 1u << ((slot & 1u) * 16));                   // < 2^16 candidates per pair: no carry into the neighbour
         }
     }
@@ -2318,7 +2318,7 @@ __global__ void __launch_bounds__(kS3Warps * 32, LHGT_S3_CTAS) s3_pairs_kernel(
     __shared__ uint8_t lut[256];
     __shared__ __align__(16) uint8_t stage[kS3Warps][4][kStageBytes];
     __shared__ __align__(8) uint64_t sbar[kS3Warps][2];        // "pair staged", one per slot pair
-    __shared__ uint32_t may_tw[kS3Warps][kMaySlots / 2];       // s3_may_split's slots
+    extern __shared__ uint32_t may_dyn[];                      // s3_may_split's slots: kS3Warps x kMaySlots / 2 words
     const int e = E ? E : hp.e;
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) { mbar_init(&sbar[warp][0], 1); mbar_init(&sbar[warp][1], 1); }
@@ -2381,7 +2381,7 @@ __global__ void __launch_bounds__(kS3Warps * 32, LHGT_S3_CTAS) s3_pairs_kernel(
         uint32_t m1 = (uint32_t)cur.a0 & 15u, m2 = (uint32_t)cur.b0 & 15u;
         int n_listed = s3_scan_mate<E>(stage[warp][2 * slot] + m1, (int)cur.l1, lut, hp, prefilter, peak_kmer, contig_first, n_contigs, cands, cont, 0, lane);
         n_listed = s3_scan_mate<E>(stage[warp][2 * slot + 1] + m2, (int)cur.l2, lut, hp, prefilter, peak_kmer, contig_first, n_contigs, cands, cont, n_listed, lane);
-        if (n_listed >= 6 && (__syncwarp(), s3_may_split(cont, n_listed * e, may_tw[warp], lane))) {   // base_hits >= MIN_BASE_NUM (E:496)
+        if (n_listed >= 6 && (__syncwarp(), s3_may_split(cont, n_listed * e, may_dyn + warp * (kMaySlots / 2), lane))) {   // base_hits >= MIN_BASE_NUM (E:496)
             __syncwarp();
             // The order-dependent vote is handed to s3_vote_kernel (one THREAD per pair, 32 pairs per warp in flight): the
             // pair's candidates move to the arena and the pair joins the queue.  When either is full the warp votes itself.
@@ -2541,8 +2541,10 @@ int launch_s3(const uint8_t* fq1, const uint64_t* s1, const uint64_t* e1, uint64
               const uint32_t* peak_kmer, const int32_t* loci, uint8_t* peak_filter, S3Scratch scratch, int grid_blocks,
               unsigned long long* n_sampled, int* err, cudaStream_t st) {
     if (count == 0 || nrec1 == 0) return 0;
+    const size_t may_smem = (size_t)kS3Warps * (kMaySlots / 2) * sizeof(uint32_t);
 #define LHGT_S3(EE)                                                                                                   \
-    s3_pairs_kernel<EE><<<grid_blocks, kS3Warps * 32, 0, st>>>(fq1, s1, e1, nrec1, fq2, s2, e2, nrec2, tail_start,    \
+    if (cudaFuncSetAttribute(s3_pairs_kernel<EE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)may_smem) != cudaSuccess) return -1; \
+    s3_pairs_kernel<EE><<<grid_blocks, kS3Warps * 32, may_smem, st>>>(fq1, s1, e1, nrec1, fq2, s2, e2, nrec2, tail_start,    \
                                                                tail_len, first, count, sample_bits, ordinal_base, hp, prefilter,   \
                                                                peak_kmer, loci, peak_filter, scratch, n_sampled, err)
     switch (hp.e) {
