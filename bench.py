@@ -721,10 +721,11 @@ def make_roofline(stage, wl, frac, world, peak, peak_src, fastq_bytes):
         kernels["s1_leaf_kernel"] = (stage[10] / 2, 4 * probes_per_mate + 2 * table_bytes, probes_per_mate * SECTOR)
     else:
         kernels["s1_count_kernel<3>"] = (stage[1] / 2, probes_per_mate * SECTOR, probes_per_mate * SECTOR)
-    kernels["s3_pairs_kernel<3>"] = (stage[4], 2 * probes_per_mate * SECTOR, 2 * probes_per_mate * SECTOR)
-    kernels["s2_gather_kernel<3>"] = (stage[2], ref_share * (E * SECTOR + 4 * E), ref_share * (E * SECTOR + 4 * E))
+    s3_scan = max(float(stage[4] - stage[12]), 0.0)                     # stage[4] covers the scan launches and the vote launches
+    kernels["s3_pairs_kernel<3>"] = (s3_scan, 2 * probes_per_mate * SECTOR, 2 * probes_per_mate * SECTOR)
+    kernels["s2_gsemit+gsapply"] = (stage[2], ref_share * (E * SECTOR + 4 * E), ref_share * (E * SECTOR + 4 * E))
     share = {"s1_bin_kernel<3>": stage[8], "s1_split_kernel": stage[9], "s1_leaf_kernel": stage[10], "s1_count_kernel<3>": stage[1],
-             "s3_pairs_kernel<3>": stage[4], "s2_gather_kernel<3>": stage[2]}
+             "s3_pairs_kernel<3>": s3_scan, "s2_gsemit+gsapply": stage[2]}
     dom = max(kernels, key=lambda k: share[k])
     per_kernel = {}
     for k, (ms, nbytes, conv) in kernels.items():
@@ -735,10 +736,16 @@ def make_roofline(stage, wl, frac, world, peak, peak_src, fastq_bytes):
                          "probe_convention": {"bytes_per_launch": int(conv), "achieved": conv / 1e6 / ms, "frac": conv / 1e6 / ms / peak}}
     d = per_kernel[dom]
     device_ms = float(stage[0] + stage[1] + stage[2] + stage[3] + stage[4] + stage[6] + stage[11])
+    overhead = {"fastq_record_scan": float(stage[0]), "s2_mark_windows_ids": float(stage[3]), "s2_register": float(stage[11]),
+                "s3_vote": float(stage[12]), "exchange": float(stage[6])}
     whole_bytes = pairs_rank * frac * 2 * 2 * P * E * SECTOR + ref_share * (E * SECTOR + 4 * E)
     return {"bound": "hbm", "kernel": dom, "achieved": d["achieved"], "peak": peak, "unit": "GB/s", "frac": d["frac"],
             "traffic": (traffic or {}).get(dom), "peak_source": peak_src, "algorithmic_bytes_per_launch": d["algorithmic_bytes_per_launch"],
             "ms_per_launch": d["ms_per_launch"], "kernels": per_kernel,
+            "per_launch_note": "figures are per STEP for stages that run as several equal launches (S3 scan: one per arena batch, S2 gather: "
+                               "an emit + apply pair per record chunk, S1: one set per mate -> halved); bytes and time scale together, so achieved "
+                               "and frac are those of a single launch; traffic (profiles/traffic.json) is per step too",
+            "stages_outside_the_byte_model_ms": {k: round(v, 3) for k, v in overhead.items()},
             "whole_step": {"algorithmic_bytes": int(whole_bytes), "device_ms": device_ms, "achieved": whole_bytes / 1e6 / max(device_ms, 1e-9),
                            "frac": whole_bytes / 1e6 / max(device_ms, 1e-9) / peak,
                            "what": "SURVEY 8(d): sampled pairs x 45 696 B + reference bases x 108 B over the summed device time of the step's stages"},

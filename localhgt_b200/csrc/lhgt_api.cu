@@ -2278,6 +2278,7 @@ extern "C" int lhgt_regions_fasta(const uint8_t* fasta, size_t n_fasta, const ch
     struct Seq { size_t first = 0, end = 0; size_t len = 0; std::vector<std::pair<size_t, size_t>> lines; };   // (offset in file, bases before it)
     std::map<std::string, Seq> seqs;
     Seq* cur = nullptr;
+    Seq repeated;                                               // a name seen before: faidx keeps the first record, the later one is parsed and dropped
     for (size_t p = 0; p < n_fasta;) {
         const uint8_t* nl = (const uint8_t*)memchr(fasta + p, '\n', n_fasta - p);
         size_t le = nl ? (size_t)(nl - fasta) : n_fasta;
@@ -2286,8 +2287,8 @@ extern "C" int lhgt_regions_fasta(const uint8_t* fasta, size_t n_fasta, const ch
         if (l && fasta[p] == '>') {
             size_t q = p + 1;
             while (q < p + l && !(fasta[q] == ' ' || (fasta[q] >= '\t' && fasta[q] <= '\r'))) ++q;
-            cur = &seqs[std::string((const char*)fasta + p + 1, q - p - 1)];
-            *cur = Seq();
+            auto ins = seqs.emplace(std::string((const char*)fasta + p + 1, q - p - 1), Seq());
+            if (ins.second) cur = &ins.first->second; else { repeated = Seq(); cur = &repeated; }
         } else if (l && cur) {
             cur->lines.emplace_back(p, cur->len);
             cur->len += l;

@@ -2062,11 +2062,11 @@ int s3_grid_blocks(int) { return kSMs * LHGT_S3_CTAS; }
 // Peak ids are handed out in (contig, position) order, so the contig of a peak is a search in the first-id-per-contig
 // array (n_contigs + 1 entries, a few KB: on chip) instead of a random gather from the per-peak loci.  Returns the 1-based
 // record ordinal = the largest c with contig_first[c - 1] <= id (contigs without peaks share their successor's first id).
-__device__ __forceinline__ int contig_of_peak(const uint32_t* __restrict__ contig_first, uint32_t n_contigs, uint32_t id) {
+__device__ __forceinline__ int contig_of_peak(const uint32_t* contig_first, uint32_t n_contigs, uint32_t id) {
     uint32_t lo = 0, hi = n_contigs;                             // invariant: contig_first[lo] <= id (peak 0 opens contig_first[.] = 0)
     while (hi - lo > 1) {
         uint32_t mid = (lo + hi) >> 1;
-        if (__ldg(contig_first + mid) <= id) lo = mid; else hi = mid;
+        if (contig_first[mid] <= id) lo = mid; else hi = mid;
     }
     return (int)lo + 1;
 }
@@ -2075,7 +2075,7 @@ __device__ __forceinline__ int contig_of_peak(const uint32_t* __restrict__ conti
 template <int E>
 __device__ __forceinline__ int s3_scan_mate(const uint8_t* src, int len, const uint8_t* lut, const HashP& hp,
                                             const uint32_t* __restrict__ prefilter,
-                                            const uint32_t* __restrict__ peak_kmer, const uint32_t* __restrict__ contig_first, uint32_t n_contigs,
+                                            const uint32_t* __restrict__ peak_kmer, const uint32_t* contig_first, uint32_t n_contigs,
                                             uint32_t* __restrict__ cands, int32_t* __restrict__ cont, int n_listed, int lane) {
     const int e = E ? E : hp.e;
     int np = len - hp.k + 1;
@@ -2265,12 +2265,13 @@ __device__ __forceinline__ bool s3_vote_warp(const uint32_t* cands, const int32_
 
 // Can this pair's vote mark anything?  check_split (E:161-202) needs TWO contigs with >= 6 votes, and a contig cannot get
 // more votes than the positions at which it is a candidate.  So: take the contig c* most common among 32 sampled
-// candidates, count its candidates exactly, and count the others in 2048 hashed 16-bit slots (a slot may merge contigs:
+// candidates, count its candidates exactly, and count the others in 1024 hashed 16-bit slots (a slot may merge contigs:
 // an upper bound); unless [c* has >= 6] + sum over slots of floor(count / 6) reaches 2 the vote cannot have two such
 // contigs and is skipped.  Exact (a necessary condition), and in a dense result -- where every position of every pair
 // holds candidates, nearly all of them of the read's own genome plus scattered collisions -- it spares almost every
 // pair the serial vote and the trip through the arena.
-constexpr int kMaySlots = 2048;                                // (256 slots let cfg4's ~500 collision candidates per pair fake a second contig in every pair)
+constexpr int kMaySlots = 1024;                                // (256 slots let cfg4's ~500 collision candidates per pair fake a second contig in every pair)
+constexpr int kCfShared = 4096;                                // contig_first entries kept in shared memory (s3_pairs_kernel)
 __device__ __forceinline__ bool s3_may_split(const int32_t* __restrict__ cont, int n_entries, uint32_t* __restrict__ tw /* kMaySlots / 2 words */, int lane) {
     for (int x = lane; x < kMaySlots / 2; x += 32) tw[x] = 0u;
     int probe = __ldcg(cont + (int)(((long)lane * n_entries) >> 5));               // 32 evenly spaced entries (some are 0 = no candidate)
@@ -2287,7 +2288,7 @@ __device__ __forceinline__ bool s3_may_split(const int32_t* __restrict__ cont, i
         int c = __ldcg(cont + x);
         if (c == cstar) ++mine;
         else if (c) {
-            uint32_t slot = ((uint32_t)c * 2654435761u) >> 21;                       // 11 bits
+            uint32_t slot = ((uint32_t)c * 2654435761u) >> 22;                       // 10 bits
             atomicAdd(tw + (slot >> 1), 1u << ((slot & 1u) * 16));                   // < 2^16 candidates per pair: no carry into the neighbour
         }
     }
@@ -2313,12 +2314,18 @@ __global__ void __launch_bounds__(kS3Warps * 32, LHGT_S3_CTAS) s3_pairs_kernel(
     uint64_t ordinal_base, HashP hp, const uint32_t* __restrict__ prefilter, const uint32_t* __restrict__ peak_kmer,
     const int32_t* __restrict__ loci, uint8_t* __restrict__ peak_filter, S3Scratch scratch,
     unsigned long long* __restrict__ n_sampled, int* __restrict__ err) {
-    const uint32_t* __restrict__ contig_first = scratch.contig_first;
     const uint32_t n_contigs = scratch.n_contigs;
     __shared__ uint8_t lut[256];
     __shared__ __align__(16) uint8_t stage[kS3Warps][4][kStageBytes];
     __shared__ __align__(8) uint64_t sbar[kS3Warps][2];        // "pair staged", one per slot pair
-    extern __shared__ uint32_t may_dyn[];                      // s3_may_split's slots: kS3Warps x kMaySlots / 2 words
+    extern __shared__ uint32_t may_dyn[];                      // s3_may_split's slots: kS3Warps x kMaySlots / 2 words, then contig_first
+    // The peak -> contig search runs up to e times per position (11 dependent loads each at 2 000 contigs): from shared
+    // memory when the array fits, because what is left of L1 beside this kernel's shared memory does not keep it (measured:
+    // the scan went from 148 to 209 ms when the slots above grew and squeezed L1).
+    uint32_t* cf_s = may_dyn + kS3Warps * (kMaySlots / 2);
+    const bool cf_fits = n_contigs + 1 <= (uint32_t)kCfShared;
+    if (cf_fits) for (uint32_t x = threadIdx.x; x <= n_contigs; x += blockDim.x) cf_s[x] = scratch.contig_first[x];
+    const uint32_t* contig_first = cf_fits ? cf_s : scratch.contig_first;
     const int e = E ? E : hp.e;
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) { mbar_init(&sbar[warp][0], 1); mbar_init(&sbar[warp][1], 1); }
@@ -2541,7 +2548,7 @@ int launch_s3(const uint8_t* fq1, const uint64_t* s1, const uint64_t* e1, uint64
               const uint32_t* peak_kmer, const int32_t* loci, uint8_t* peak_filter, S3Scratch scratch, int grid_blocks,
               unsigned long long* n_sampled, int* err, cudaStream_t st) {
     if (count == 0 || nrec1 == 0) return 0;
-    const size_t may_smem = (size_t)kS3Warps * (kMaySlots / 2) * sizeof(uint32_t);
+    const size_t may_smem = ((size_t)kS3Warps * (kMaySlots / 2) + (scratch.n_contigs + 1 <= (uint32_t)kCfShared ? scratch.n_contigs + 1 : 0)) * sizeof(uint32_t);
 #define LHGT_S3(EE)                                                                                                   \
     if (cudaFuncSetAttribute(s3_pairs_kernel<EE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)may_smem) != cudaSuccess) return -1; \
     s3_pairs_kernel<EE><<<grid_blocks, kS3Warps * 32, may_smem, st>>>(fq1, s1, e1, nrec1, fq2, s2, e2, nrec2, tail_start,    \
