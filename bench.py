@@ -564,17 +564,19 @@ def ours(args) -> None:
         n1, n2, nfa = d1.numel(), d2.numel(), d_fa.numel()
         del d1, d2, d_fa
         torch.cuda.empty_cache()
-        fa_bcast = torch.empty(nfa + 64, dtype=torch.uint8, device=dev)[:nfa] if world > 1 else None
+        # N > 1: the FASTA crosses PCIe once per BOX, 1/N of it per rank (every rank holds the bytes in pinned memory), and
+        # NVLink carries the slices to everybody (in-place all-gather of equal slices)
+        fa_slice = -(-nfa // world)
+        fa_bcast = torch.empty(fa_slice * world + 64, dtype=torch.uint8, device=dev) if world > 1 else None
 
         def build_index_e2e():
             if world == 1:
                 scr.index_build_ptr(hfa.data_ptr(), nfa)                # adopts the prefetch issued at the top of the step
                 return
-            # the FASTA crosses PCIe once per box: rank 0 uploads it, NVLink carries it to the others
-            if rank == 0:
-                fa_bcast.copy_(hfa, non_blocking=True)
-            dist.broadcast(fa_bcast, src=0)
-            torch.cuda.current_stream().synchronize()
+            lo, hi = rank * fa_slice, min(nfa, (rank + 1) * fa_slice)
+            if hi > lo:
+                fa_bcast[lo:hi].copy_(hfa[lo:hi], non_blocking=True)
+            dist.all_gather_into_tensor(fa_bcast[: fa_slice * world], fa_bcast[rank * fa_slice:(rank + 1) * fa_slice])
             scr.index_build_device(fa_bcast.data_ptr(), nfa)
 
         def step_e2e():
@@ -610,7 +612,7 @@ def ours(args) -> None:
     frac = sampled_fraction(wl.n_pairs)
     roofline = make_roofline(stage, wl, frac, world, peak, peak_src, n1 + n2)
     roofline["stage_ms_per_step"] = stage_ms
-    h2d = n1 + n2 + (nfa if rank == 0 else 0)
+    h2d = n1 + n2 + (nfa if world == 1 else -(-nfa // world))
     line = {
         "metric": "read pairs/sec through k-mer screen+peak extract", "value": value, "unit": "pairs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
