@@ -1472,6 +1472,41 @@ __global__ void __launch_bounds__(256) s2_good_kernel(const Contig* __restrict__
     }
 }
 
+// min of the unsigned bytes / max of the signed bytes a[lo .. lo + n), 1 <= n <= 32, `a` 4-byte aligned in shared memory and
+// readable up to lo + 35: nine word loads re-aligned with funnel shifts, then byte-SIMD min/max -- instead of n byte loads.
+__device__ __forceinline__ uint32_t window_min_u8(const signed char* a, int lo, int n) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a) + (lo >> 2);
+    const int sh = (lo & 3) * 8;
+    uint32_t acc = 0xffffffffu;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        uint32_t v = __funnelshift_r(w[j], w[j + 1], sh);             // bytes lo + 4j .. lo + 4j + 3
+        int left = n - 4 * j;                                        // how many of them belong to the window
+        if (left <= 0) break;
+        if (left < 4) v |= 0xffffffffu << (8 * left);
+        acc = __vminu4(acc, v);
+    }
+    acc = __vminu4(acc, acc >> 16);
+    acc = __vminu4(acc, acc >> 8);
+    return acc & 0xffu;
+}
+__device__ __forceinline__ int window_max_s8(const signed char* a, int lo, int n) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a) + (lo >> 2);
+    const int sh = (lo & 3) * 8;
+    uint32_t acc = 0x80808080u;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        uint32_t v = __funnelshift_r(w[j], w[j + 1], sh);
+        int left = n - 4 * j;
+        if (left <= 0) break;
+        if (left < 4) v = (v & ~(0xffffffffu << (8 * left))) | (0x80808080u << (8 * left));
+        acc = __vmaxs4(acc, v);
+    }
+    acc = __vmaxs4(acc, acc >> 16);
+    acc = __vmaxs4(acc, acc >> 8);
+    return (int)(signed char)(acc & 0xffu);
+}
+
 // pass c: interval membership (E:617-638, 675-686 collapse to "a good window within +-1000") and the
 // coverage-edge peak test (E:640-671) in its closed form:
 //   D(x) = sum single[x-4..x],  C(j) = D(j-5) - D(j-k-5) - D(j),  diff_t(j) = C(j) + D(j-k-5-t), t in [0,k)
@@ -1483,7 +1518,7 @@ __global__ void __launch_bounds__(256) s2_flag_kernel(const Contig* __restrict__
                                                       const uint32_t* __restrict__ good, uint32_t* __restrict__ flagged) {
     __shared__ uint32_t ws[3 * kTileWords + 1], wg[3 * kTileWords];
     __shared__ int cg[3 * kTileWords + 1];
-    __shared__ signed char D[3 * kTile], C[3 * kTile];
+    __shared__ __align__(4) signed char D[3 * kTile + 8], C[3 * kTile + 8];
     const uint32_t n = *n_need;
     for (uint32_t it = blockIdx.x; it < n; it += gridDim.x) {
         const uint64_t tix = need_list[it];
@@ -1537,12 +1572,8 @@ __global__ void __launch_bounds__(256) s2_flag_kernel(const Contig* __restrict__
                 if (in_iv) {
                     int cj = C[x], dq = D[x];
                     bool pk = false;
-                    if (cj != -100) {
-                        int m = 100;
-                        for (int tt = 0; tt < k; ++tt) m = min(m, (int)D[x - k - 5 - tt]);
-                        pk = cj + m <= -2;
-                    }
-                    for (int tt = 0; tt < k && !pk; ++tt) pk = (int)C[x + k + 5 + tt] + dq >= 2;
+                    if (cj != -100) pk = cj + (int)window_min_u8(D, x - 2 * k - 4, k) <= -2;        // min over D[x-k-5-t], t in [0, k)
+                    if (!pk) pk = window_max_s8(C, x + k + 5, k) + dq >= 2;                          // some C[x+k+5+t] + D[x] >= 2
                     f = pk;
                 }
             }
