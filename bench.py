@@ -453,6 +453,10 @@ def ours(args) -> None:
         dist = dist_
         dist.init_process_group("nccl", device_id=dev)
     t_setup = time.perf_counter()
+    if args.workload in FILE_WORKLOADS and dist:                          # one rank writes the files, the others wait for them
+        if rank == 0:
+            make_workload(args.workload, 0)
+        dist.barrier()
     wl = Workload(args.workload, rank, world, torch, dev)
     d_fa = wl.fasta_dev()
     d1, d2 = wl.reads_dev()
