@@ -12,9 +12,10 @@ donors) and 30 M simulated 150 bp read pairs with planted transfers, k=32 e=3, L
 (1 Gbp, 10 M pairs), `cfg2` configs[1] (80 Mbp, 5 M pairs, every pair sampled), `mini` a 1/100 cfg4 for quick checks.
 
   value      input pairs/s with the FASTQ bytes and the index already resident in HBM (CUDA events, max over ranks)
-  e2e        the same metric through the C ABI with HOST (pinned) buffers: both FASTQ images and the reference FASTA are
-             copied host->device inside the timed region (the 60 GB index image is re-built from the 5 GB of FASTA on the
-             device instead of crossing PCIe) and the interval text comes back device->host
+  e2e        the same metric through the C ABI with HOST (pinned) buffers, as a stream of samples against the resident index:
+             both FASTQ images are copied host->device inside the timed region (sample i+1's while sample i is screened) and
+             the interval text comes back device->host; `e2e_cold` carries nothing over: the reference FASTA crosses PCIe too
+             and the 60 GB index image is re-built from it on the device inside the step
   roofline   the dominant kernel against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
   cpu_baseline  the UNMODIFIED reference binary (oracle/_ref/extract_ref) on this box's host cores, on a bounded,
              self-consistent 1/f scale model of the workload (pairs and contigs), extrapolated linearly and said so
@@ -584,8 +585,18 @@ def ours(args) -> None:
             scr.index_build_device(fa_bcast.data_ptr(), nfa)
 
         def step_e2e():
-            # the host->device copies are queued on the copy stream up front, in the order the stages need them; each stage
-            # adopts its input when it gets there (fq2 lands behind S1 of fq1, the FASTA behind S1 of fq2)
+            """A sample from pinned host buffers against the RESIDENT index (the reference, too, builds its index once and reuses
+            the file for every sample, E:1401-1417): the sample's FASTQ images are adopted -- the previous step started their
+            host->device copies into the alternate buffers while it was screening -- and the next sample's copies are started."""
+            scr.reads_upload_ptr(0, h1.data_ptr(), n1)
+            scr.reads_upload_ptr(1, h2.data_ptr(), n2)
+            scr.reads_prefetch_next_ptr(0, h1.data_ptr(), n1)
+            scr.reads_prefetch_next_ptr(1, h2.data_ptr(), n2)
+            return shard.screen(size1=n1, size2=n2, sample_arg=SAMPLE, seed=SEED, rand_skip=0, hit=HIT, match=MATCH, max_peak=MAX_PEAK)
+
+        def step_e2e_cold():
+            """Everything from host buffers, nothing carried over: FASTQ x2 and the reference FASTA cross PCIe in the order the
+            stages need them (fq2 lands behind S1 of fq1, the FASTA behind S1 of fq2) and the index image is re-built on the device."""
             scr.reads_prefetch_ptr(0, h1.data_ptr(), n1)
             scr.reads_prefetch_ptr(1, h2.data_ptr(), n2)
             if world == 1:
@@ -594,6 +605,9 @@ def ours(args) -> None:
             return shard.screen(size1=n1, size2=n2, sample_arg=SAMPLE, seed=SEED, rand_skip=0, hit=HIT, match=MATCH, max_peak=MAX_PEAK,
                                 before_mate2=lambda: scr.reads_upload_ptr(1, h2.data_ptr(), n2), before_s2=build_index_e2e)
 
+        cold_steps = max(1, min(args.steps, 3))
+        ms_cold, res_cold, stage_cold, _, _ = timed(step_e2e_cold, cold_steps, 1)
+        assert res_cold == text_resident, "resident and cold host-buffer passes disagree"
         ms_e2e, res_e2e, stage_e2e, _, _ = timed(step_e2e, args.steps, max(1, min(args.warmup, 2)))
         assert res_e2e == text_resident, "resident and host-buffer passes disagree"
 
@@ -616,7 +630,8 @@ def ours(args) -> None:
     frac = sampled_fraction(wl.n_pairs)
     roofline = make_roofline(stage, wl, frac, world, peak, peak_src, n1 + n2)
     roofline["stage_ms_per_step"] = stage_ms
-    h2d = n1 + n2 + (nfa if world == 1 else -(-nfa // world))
+    h2d = n1 + n2
+    h2d_cold = n1 + n2 + (nfa if world == 1 else -(-nfa // world))
     line = {
         "metric": "read pairs/sec through k-mer screen+peak extract", "value": value, "unit": "pairs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
@@ -633,10 +648,17 @@ def ours(args) -> None:
         "e2e": {"value": e2e_value, "unit": "pairs/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": len(text_resident) + 64,
                 "pcie_gbs": h2d / 1e6 / (ms_e2e / args.steps),
-                "what": "pinned host FASTQ x2 + reference FASTA -> HBM (copy stream, overlapping S1) -> index image re-built on the device -> S1,S2,S3 "
-                        "-> interval text on host, through the C ABI; every input byte crosses PCIe inside the timed region (rank 0's figure; "
-                        "at N > 1 the FASTA crosses PCIe once and is broadcast over NVLink)",
+                "what": "a stream of samples against the resident index (the reference builds its index once and reuses the file): pinned host "
+                        "FASTQ x2 -> HBM -> S1,S2,S3 -> interval text on host, through the C ABI; each sample's copies run on the copy stream "
+                        "into alternate buffers while the previous sample is screened (lhgt_reads_prefetch_next), every byte of every step "
+                        "crosses PCIe inside the timed region (rank 0's figure)",
                 "stage_ms_per_step": {nm: round(float(v), 3) for nm, v in zip(names, stage_e2e)}},
+        "e2e_cold": {"value": wl.n_pairs * cold_steps / (ms_cold / 1000), "unit": "pairs/s", "ms_per_step": ms_cold / cold_steps, "steps": cold_steps,
+                     "h2d_bytes_per_step": int(h2d_cold), "pcie_gbs": h2d_cold / 1e6 / (ms_cold / cold_steps),
+                     "what": "nothing carried over between steps: FASTQ x2 + the reference FASTA cross PCIe (copy stream, overlapping S1) and the "
+                             "index image is re-built on the device inside the step (at N > 1 the FASTA crosses PCIe once per box, 1/N per rank, "
+                             "and NVLink all-gathers the slices)",
+                     "stage_ms_per_step": {nm: round(float(v), 3) for nm, v in zip(names, stage_cold)}},
         "gpu_launches": int(launches), "roofline": roofline, "index_build": index_build,
         "result": {"interval_lines": len(text_resident.splitlines()), "interval_sha256": sha,
                    "matches_unmodified_reference": bool(known) or None,

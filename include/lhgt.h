@@ -119,6 +119,10 @@ int      lhgt_index_upload(lhgt_ctx* c, const uint8_t* image, uint64_t n);
  * returns; the later lhgt_reads_upload / lhgt_index_upload call with the SAME pointer and size adopts the copy
  * instead of repeating it.  The host buffer must stay valid and unchanged until that call returns. */
 int      lhgt_reads_prefetch(lhgt_ctx* c, int mate, const uint8_t* fq, uint64_t n);
+/* Across samples: while sample i is screened (index resident), sample i+1's FASTQ images cross PCIe into the mates'
+ * alternate buffers; lhgt_reads_upload of sample i+1 (same pointer and size) swaps buffers instead of copying.  Call after
+ * both mates of sample i were uploaded.  Costs a second pair of image buffers in HBM. */
+int      lhgt_reads_prefetch_next(lhgt_ctx* c, int mate, const uint8_t* fq, uint64_t n);
 int      lhgt_index_prefetch(lhgt_ctx* c, const uint8_t* image, uint64_t n);
 /* File-level forms (what main() does at E:1401-1417). */
 int      lhgt_index_build_file(lhgt_ctx* c, const char* fasta_path, const char* index_path,

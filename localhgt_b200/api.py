@@ -73,6 +73,7 @@ SYMBOLS = {
     "lhgt_reads_upload": (_i, [_vp, _i, _vp, _u64]),
     "lhgt_reads_prefetch": (_i, [_vp, _i, _vp, _u64]),
     "lhgt_reads_upload_file": (_i, [_vp, _i, _s]),
+    "lhgt_reads_prefetch_next": (_i, [_vp, _i, _vp, _u64]),
     "lhgt_index_prefetch": (_i, [_vp, _vp, _u64]),
     "lhgt_reads_attach_device": (_i, [_vp, _i, _vp, _u64]),
     "lhgt_reads_records": (_l, [_vp, _i]),
@@ -316,6 +317,10 @@ class Screen:
     def reads_prefetch_ptr(self, mate: int, host_ptr: int, n: int) -> None:
         """Starts the H2D copy on the copy stream; reads_upload_ptr(mate, same ptr, same n) adopts it later."""
         _check(self._L.lhgt_reads_prefetch(self._h, mate, host_ptr, n))
+
+    def reads_prefetch_next_ptr(self, mate: int, host_ptr: int, n: int) -> None:
+        """The NEXT sample's image starts its H2D copy into the alternate buffer; its reads_upload_ptr adopts it."""
+        _check(self._L.lhgt_reads_prefetch_next(self._h, mate, host_ptr, n))
 
     def index_prefetch_ptr(self, host_ptr: int, n: int) -> None:
         _check(self._L.lhgt_index_prefetch(self._h, host_ptr, n))

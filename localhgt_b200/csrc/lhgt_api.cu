@@ -106,6 +106,7 @@ struct Reads {
     uint64_t* d_start = nullptr;               // = start_buf.p / end_buf.p once located
     uint64_t* d_end = nullptr;
     DevBuf<uint8_t> fq_buf;                    // backing store of an uploaded image (owned)
+    DevBuf<uint8_t> fq_alt;                    // the NEXT sample's image while this one is screened (lhgt_reads_prefetch_next)
     DevBuf<uint64_t> start_buf, end_buf;
     uint64_t tail_start = 0, tail_len = 0;   // what std::getline leaves behind once the file is exhausted
     bool ready = false;
@@ -125,7 +126,7 @@ struct lhgt_ctx {
     cudaStream_t own = nullptr, st = nullptr;
     cudaStream_t copy_st = nullptr;              // host->device prefetches run here, beside the kernels on `st`
     struct Prefetch { const void* host = nullptr; uint64_t n = 0; cudaEvent_t done = nullptr; bool active = false; };
-    Prefetch pf_reads[2], pf_index, pf_fasta;
+    Prefetch pf_reads[2], pf_index, pf_fasta, pf_next[2];
     DevBuf<ByteSpan> fa_spans_buf; DevBuf<uint64_t> fa_words_buf; DevBuf<uint8_t> fa_text_buf, fa_seq_buf;   // FASTA ingest scratch
     DevBuf<uint8_t> fasta_buf; bool keep_fasta_buf = false;   // raw FASTA bytes of lhgt_index_build (kept when prefetched: a context that re-builds per sample)
 
@@ -348,7 +349,7 @@ extern "C" int lhgt_create(lhgt_ctx** out, int device, int k, int e) {
 }
 
 static void drop_reads(Reads& r, bool release = false) {      // forgets the sample, keeps the buffers
-    if (release) { r.fq_buf.release(); r.start_buf.release(); r.end_buf.release(); }
+    if (release) { r.fq_buf.release(); r.fq_alt.release(); r.start_buf.release(); r.end_buf.release(); }
     r.d_fq = nullptr; r.owned = false; r.n = r.nrec = r.seq_bases = r.max_len = 0;
     r.d_start = r.d_end = nullptr; r.tail_start = r.tail_len = 0; r.ready = false;
 }
@@ -392,7 +393,7 @@ extern "C" void lhgt_destroy(lhgt_ctx* c) {
     c->keep_cnt_buf.release(); c->keep_base_buf.release(); c->keep_tmp_buf.release(); c->keep_out_buf.release();
     peers_close(c);
     if (c->copy_st) { cudaStreamSynchronize(c->copy_st); cudaStreamDestroy(c->copy_st); }
-    for (lhgt_ctx::Prefetch* p : {&c->pf_reads[0], &c->pf_reads[1], &c->pf_index, &c->pf_fasta}) if (p->done) cudaEventDestroy(p->done);
+    for (lhgt_ctx::Prefetch* p : {&c->pf_reads[0], &c->pf_reads[1], &c->pf_index, &c->pf_fasta, &c->pf_next[0], &c->pf_next[1]}) if (p->done) cudaEventDestroy(p->done);
     if (c->own) cudaStreamDestroy(c->own);
     delete c;
 }
@@ -806,6 +807,18 @@ extern "C" int lhgt_reads_prefetch(lhgt_ctx* c, int mate, const uint8_t* fq, uin
     return start_prefetch(c, c->pf_reads[mate], r.fq_buf.p, fq, n);
 }
 
+// The NEXT sample's FASTQ image starts crossing PCIe while the current one is screened: it lands in the mate's alternate
+// buffer (idle since the previous sample's S3), and the lhgt_reads_upload call of the next sample with the same pointer and
+// size swaps the buffers instead of copying.  Call it after BOTH mates of the current sample were uploaded.
+extern "C" int lhgt_reads_prefetch_next(lhgt_ctx* c, int mate, const uint8_t* fq, uint64_t n) {
+    if (!c || mate < 0 || mate > 1 || (!fq && n)) return fail(LHGT_E_ARG, "lhgt_reads_prefetch_next: bad argument");
+    CU(cudaSetDevice(c->device));
+    Reads& r = c->reads[mate];
+    int rc = r.fq_alt.reserve(n + 64);
+    if (rc) return rc;
+    return start_prefetch(c, c->pf_next[mate], r.fq_alt.p, fq, n);
+}
+
 extern "C" int lhgt_index_prefetch(lhgt_ctx* c, const uint8_t* image, uint64_t n) {
     if (!c || !image) return fail(LHGT_E_ARG, "null pointer");
     if (n % 4) return fail(LHGT_E_FORMAT, "index image size is not a multiple of 4");
@@ -1110,11 +1123,19 @@ extern "C" int lhgt_reads_upload(lhgt_ctx* c, int mate, const uint8_t* fq, uint6
     CU(cudaSetDevice(c->device));
     Reads& r = c->reads[mate];
     drop_reads(r);
-    int rc = r.fq_buf.reserve(n + 64);
-    if (rc) return rc;
-    uint8_t* d = r.fq_buf.p;
-    r.d_fq = d; r.owned = true; r.n = n;
-    if (!adopt_prefetch(c, c->pf_reads[mate], fq, n) && n) CU(cudaMemcpyAsync(d, fq, n, cudaMemcpyHostToDevice, c->st));
+    lhgt_ctx::Prefetch& nx = c->pf_next[mate];
+    if (nx.active && nx.host == fq && nx.n == n && r.fq_alt.p) {            // the previous sample's step already brought it in
+        nx.active = false;
+        std::swap(r.fq_buf, r.fq_alt);
+        CU(cudaStreamWaitEvent(c->st, nx.done, 0));
+        r.d_fq = r.fq_buf.p; r.owned = true; r.n = n;
+    } else {
+        int rc = r.fq_buf.reserve(n + 64);
+        if (rc) return rc;
+        uint8_t* d = r.fq_buf.p;
+        r.d_fq = d; r.owned = true; r.n = n;
+        if (!adopt_prefetch(c, c->pf_reads[mate], fq, n) && n) CU(cudaMemcpyAsync(d, fq, n, cudaMemcpyHostToDevice, c->st));
+    }
     uint64_t tail = 0;
     int last = '\n';
     if (n) {

@@ -802,3 +802,48 @@ def test_image_blocks_tile_the_image(parts, workdir):
                     s.s2_gather(0, ntiles) if parts > 1 and (t0, t1) != (0, ntiles) else (_ for _ in ()).throw(api.LhgtError(-8, "x"))
     assert covered == len(image) and bytes(got) == image
     assert _read(path) == image
+
+
+def test_next_sample_prefetch_swaps_the_right_images(workdir):
+    """lhgt_reads_prefetch_next: while sample A is screened, sample B's FASTQ images cross PCIe into the alternate buffers and
+    B's upload adopts them (and vice versa, several rounds): every sample gets exactly the answer it gets on its own."""
+    import torch
+    case = fixtures.BY_NAME["base_k24"]
+    fa, fq1, fq2 = fixtures.materialize(case.data, workdir)
+    a1, a2 = _read(fq1), _read(fq2)
+
+    def head(buf, n_rec):
+        pos = 0
+        for _ in range(4 * n_rec):
+            pos = buf.index(b"\n", pos) + 1
+        return buf[:pos]
+
+    b1, b2 = head(a1, 2500), head(a2, 2500)
+    cc, skip = api.random_coder(case.seed, case.k, case.e)
+
+    def alone(m1, m2):
+        with api.Screen(case.k, case.e) as s:
+            s.set_coder(cc); s.index_build(_read(fa))
+            s.reads_upload(0, m1); s.reads_upload(1, m2)
+            s.set_sampling(100.0, case.seed, skip)
+            s.s1_count(0, len(m1)); s.s1_count(1, len(m1))
+            s.s2_peaks(case.hit, case.match, case.max_peak); s.s3_pairs()
+            return s.intervals()
+
+    want = {"A": alone(a1, a2), "B": alone(b1, b2)}
+    assert want["A"] != want["B"]
+    pin = {k: torch.frombuffer(bytearray(v), dtype=torch.uint8).pin_memory() for k, v in (("A1", a1), ("A2", a2), ("B1", b1), ("B2", b2))}
+    with api.Screen(case.k, case.e) as s:
+        s.set_coder(cc); s.index_build(_read(fa))
+        order = ["A", "B", "B", "A", "B"]
+        for i, name in enumerate(order):
+            m1, m2 = pin[name + "1"], pin[name + "2"]
+            s.reset()
+            s.reads_upload_ptr(0, m1.data_ptr(), m1.numel()); s.reads_upload_ptr(1, m2.data_ptr(), m2.numel())
+            if i + 1 < len(order):
+                n1, n2 = pin[order[i + 1] + "1"], pin[order[i + 1] + "2"]
+                s.reads_prefetch_next_ptr(0, n1.data_ptr(), n1.numel()); s.reads_prefetch_next_ptr(1, n2.data_ptr(), n2.numel())
+            s.set_sampling(100.0, case.seed, skip)
+            s.s1_count(0, m1.numel()); s.s1_count(1, m1.numel())
+            s.s2_peaks(case.hit, case.match, case.max_peak); s.s3_pairs()
+            assert s.intervals() == want[name], (i, name)
