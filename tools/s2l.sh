@@ -14,4 +14,5 @@ try:
 except Exception as ex: print('no json', ex)
 P
 tail -3 $O/bench_default.err
+if [ -n "${MEMCHECK:-}" ]; then timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -x -q -k "s3_vote_paths or s2_in_steps or bucketed or image_blocks or next_sample or marks_few or many_contigs" > $O/memcheck.log 2>&1; echo "memcheck rc=$?"; tail -4 $O/memcheck.log; fi
 ( time timeout 1500 python bench.py --impl reference --steps ${RSTEPS:-2} --warmup 1 > $O/bench_ref.json 2> $O/bench_ref.err ); echo "ref rc=$?"; cat $O/bench_ref.json | cut -c1-2500; tail -3 $O/bench_ref.err
