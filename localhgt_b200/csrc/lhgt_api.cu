@@ -1248,14 +1248,7 @@ extern "C" int lhgt_set_s1_mode(lhgt_ctx* c, int mode) {
 
 static uint64_t bin_pool_limit_entries() {                           // per pool (there are two)
     const char* g = getenv("LHGT_BIN_POOL_MB");                      // test knob: forces several chunks
-    uint64_t mb = 0;
-    if (g) mb = (uint64_t)atol(g);
-    else {
-        // 12 GiB each on a 180 GB part (cfg4 then counts a mate in one chunk, registers in two, votes in four batches), 8 GiB
-        // on anything smaller; the pools only grow to what a sample needs
-        size_t free_b = 0, total_b = 0;
-        mb = (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b >= ((size_t)160 << 30)) ? (uint64_t)12 << 10 : (uint64_t)8 << 10;
-    }
+    uint64_t mb = g ? (uint64_t)atol(g) : (uint64_t)8 << 10;         // (12 GiB each was measured on cfg4: register 145 -> 139 ms, nothing else: not worth the HBM)
     if (mb < 1) mb = 1;
     return (mb << 20) / 4;
 }
