@@ -1205,7 +1205,8 @@ int launch_s1_binned(const uint8_t* fq, const uint64_t* rec_start, const uint64_
 }
 
 // ------------------------------------------------------------------------------------------------
-// S2 (E:888-979 + E:550-725 + E:239-301) as five data-parallel passes over 1024-position tiles.
+// S2 (E:888-979 + E:550-725 + E:239-301) as data-parallel passes over 1024-position tiles: gather (direct form below, sliced
+// form further down), mark, complete, windows (good / flag / count_new), ids (scan), register (direct or through buckets).
 // Bit arrays are little-endian in bit order: tile t, local position x -> word t*32 + x/32, bit x%32.
 // ------------------------------------------------------------------------------------------------
 
@@ -2075,10 +2076,11 @@ int launch_s2_register(const uint32_t* image, const Contig* contigs, const Tile*
 }
 
 // ------------------------------------------------------------------------------------------------
-// S3: read-pair confirmation (E:419-499 + Split_reads E:109-202).  One warp per pair.  Lanes hash
-// positions in parallel and test an L2-resident pre-filter; only k-mers that pass it touch the
-// 2^k-entry peak table.  Positions that hold a peak k-mer are appended, in read order, to a per-warp
-// list; the order-dependent vote (judge_base) then runs on lane 0 over that (usually empty) list.
+// S3: read-pair confirmation (E:419-499 + Split_reads E:109-202).  Scan: one warp per pair; lanes hash
+// positions in parallel, test the L2-resident pre-filter (sparse results only) and probe the 2^k-entry peak
+// table; positions that hold a peak k-mer are appended, in read order, to a per-warp list.  Vote: pairs that
+// pass the exact pre-check (s3_may_split) hand their list to s3_vote_kernel (one thread per pair); when the
+// hand-over is not possible the warp runs the order-dependent vote (judge_base) itself.
 // ------------------------------------------------------------------------------------------------
 #ifndef LHGT_S3_WARPS
 #define LHGT_S3_WARPS 16

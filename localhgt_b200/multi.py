@@ -9,9 +9,14 @@ What is sharded and what is exchanged:
        (lhgt_count_exchange_p2p) — no staging buffer, no separate merge pass.  NCCL form (when IPC is not
        available): all-to-all of table slices, local merge, all-gather of the merged slices.  Either way
        2 x table bytes cross each rank's links instead of (N-1) x.
-  S2   the table gather (the HBM-bound part) is sharded over reference tiles; the per-position hit bits
-       (2 bits per reference base) are exchanged; the cheap scans/peak registration then run replicated,
-       so every rank ends with identical peak ids and an identical peak_kmer table without moving it.
+  S2   the table gather runs on equal blocks of reference tiles and the per-position hit bits (2 bits per
+       reference base) are all-gathered in place; the tiles where anything can happen are marked (replicated,
+       cheap); windows and peak registration run on equal SHARES OF THE MARKED TILES (they cluster where the
+       sample's genomes are), with the per-tile new-peak counts summed so that every rank derives the same peak
+       ids.  Dense results: every rank registers its share and the peak tables are MAX-combined (ids grow with
+       position, so MAX = the last writer of the reference's sequential loop); sparse results: the flagged bits
+       are combined and everybody registers everything.  With the image kept in blocks (set_image_block, indexes
+       larger than one GPU) registration follows the image blocks instead.
   S3   each rank confirms peaks with its own pairs; only `peak_filter >= 1` is consumed (E:526), so the
        verdict bytes are max-reduced.
   OUT  identical on every rank; rank 0's text is the result.
